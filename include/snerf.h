@@ -1,0 +1,240 @@
+/*
+ * snerf.h -- C ABI of libsnerf_b200.so: the B200-native (sm_100a) NeRF rendering hot path of
+ * earslan25/Stable-NeRF (ray/AABB -> occupancy marching -> hash-grid encode -> sigma/colour MLP ->
+ * alpha compositing, forward and backward).
+ *
+ * This header is the drop-in boundary.  Every entry point replaces one function of the reference's
+ * pybind11 module `_raymarching` (submodules/raymarching/src/raymarching.h:7-18, bindings.cpp:5-18)
+ * or one tiny-cuda-nn module call made by nerf/network.py:23-37.  Differences from the reference
+ * interface are deliberate and uniform:
+ *   - plain device pointers + sizes instead of at::Tensor (no torch types in any signature);
+ *   - every function takes the CUDA stream to launch on (the reference launches on the legacy
+ *     default stream, raymarching.cu:155 etc.);
+ *   - every function returns an int: 0 = ok, >0 = cudaError_t, <0 = SNERF_E_* argument error
+ *     (the reference returns void and never checks, raymarching.cu:13-16 are unused);
+ *   - nothing here allocates, frees or synchronises.  Scratch memory is passed in by the caller;
+ *     the *_workspace_bytes() queries say how much.
+ *
+ * All arrays are contiguous, row-major; float = IEEE fp32; indices int32; the bitfield is uint8.
+ * The reference's python call site for each function is given as file:line under /root/reference.
+ */
+#ifndef SNERF_H_
+#define SNERF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* snerf_stream_t; /* cudaStream_t */
+
+#define SNERF_OK 0
+#define SNERF_E_BADARG (-1)       /* null pointer / zero-size misuse                                */
+#define SNERF_E_CHANNELS (-2)     /* channel_dim must be in 1..4 (raymarching.cu:18 MAX_NUM_CHANNELS) */
+#define SNERF_E_GRID (-3)         /* H must be a power of two <= 1024, C in 1..8     */
+#define SNERF_E_WORKSPACE (-4)    /* workspace too small                                            */
+#define SNERF_E_UNSUPPORTED (-5)  /* configuration not supported by this build                      */
+
+#define SNERF_MAX_CHANNELS 4
+#define SNERF_MAX_LEVELS 16
+
+/* precision of the sigma/colour MLP */
+#define SNERF_PRECISION_FP32 0 /* CUDA-core fp32 GEMMs: reference-accuracy mode                    */
+#define SNERF_PRECISION_BF16 1 /* tcgen05 tensor-core path: bf16 operands, fp32 accumulate in TMEM */
+
+int snerf_version(void);
+const char* snerf_error_string(int code);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+uint64_t snerf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ray utilities  (reference: raymarching.h:7-11)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* raymarching.cu:92-157, called from raymarching.py:45.  rays_o/rays_d [N,3], aabb [6] -> nears/fars [N]. */
+int snerf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                             float min_near, float* nears, float* fars, snerf_stream_t stream);
+
+/* raymarching.cu:163-210, raymarching.py:76.  -> coords [N,2] */
+int snerf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                       snerf_stream_t stream);
+
+/* raymarching.cu:215-233, raymarching.py:100.  coords int32 [N,3] -> indices int32 [N] */
+int snerf_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, snerf_stream_t stream);
+
+/* raymarching.cu:238-261, raymarching.py:122.  indices int32 [N] -> coords int32 [N,3] */
+int snerf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, snerf_stream_t stream);
+
+/* raymarching.cu:268-301, raymarching.py:151.  grid f32 [8N] -> bitfield u8 [N]; bit i = grid[8n+i] > thresh.
+ * N must be a multiple of 4 or the tail is handled bytewise. */
+int snerf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, snerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training march + compositing  (reference: raymarching.h:13-15)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* bytes of scratch snerf_march_rays_train needs for N rays */
+size_t snerf_march_rays_train_workspace_bytes(uint32_t N);
+
+/* raymarching.cu:312-491, raymarching.py:218.
+ * Same inputs and outputs as the reference.  Differences: sample offsets come from a
+ * deterministic exclusive scan in ray order instead of atomicAdd, so rays[n] = (n, offset_n, count_n)
+ * and the packed sample order is ray order.  counter[0] += total samples, counter[1] += N exactly as the
+ * reference's atomics would leave them.  Rays whose segment does not fit in M rows keep their (offset,
+ * count) but write no samples (raymarching.cu:417).  xyzs/dirs/deltas rows not written are left untouched
+ * (the python wrapper zero-fills like raymarching.py:206-208). */
+int snerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                           float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                           const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                           int32_t* rays, int32_t* counter, const float* noises, void* workspace,
+                           size_t workspace_bytes, snerf_stream_t stream);
+
+/* The same computation in two calls, for callers that size the sample arrays from the measured total
+ * (the reference's first-epoch path allocates N*max_steps rows and slices after a D2H read,
+ * raymarching.py:196-231): _count runs the counting pass and the scan (counter is updated, the per-ray
+ * offsets stay in the workspace); _write re-marches and writes rays/xyzs/dirs/deltas.  If zero_unwritten
+ * is non-zero, every row of xyzs/dirs/deltas in [0,M) that no ray writes (alignment padding, dropped rays)
+ * is zero-filled by the kernel, so the caller may pass uninitialised memory.  n_samples_out (device int32,
+ * may be NULL) receives the total number of samples of this call. */
+int snerf_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                 const float* nears, const float* fars, int32_t* counter, const float* noises,
+                                 void* workspace, size_t workspace_bytes, snerf_stream_t stream);
+int snerf_march_rays_train_write(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                 const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                                 int32_t* rays, const float* noises, int zero_unwritten, int32_t* n_samples_out,
+                                 void* workspace, size_t workspace_bytes, snerf_stream_t stream);
+
+/* raymarching.cu:501-601, raymarching.py:264. */
+int snerf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                       const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                       uint32_t channel_dim, float* weights_sum, float* depth, float* image,
+                                       snerf_stream_t stream);
+
+/* raymarching.cu:614-726, raymarching.py:286.  Unlike the reference, grad_sigmas/grad_rgbs need NOT be
+ * pre-zeroed: every one of the M rows is written (zeros where the reference leaves its memset). */
+int snerf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                        const float* sigmas, const float* rgbs, const float* deltas,
+                                        const int32_t* rays, const float* weights_sum, const float* image,
+                                        uint32_t M, uint32_t N, float T_thresh, uint32_t channel_dim,
+                                        float* grad_sigmas, float* grad_rgbs, snerf_stream_t stream);
+
+/* Same, plus n_samples: device pointer to the number of packed samples actually produced by
+ * snerf_march_rays_train (its counter[0]).  When given, only the alignment-padding rows [*n_samples, M) are
+ * zero-filled (in-kernel) instead of clearing both gradient arrays with a memset first. */
+int snerf_composite_rays_train_backward_ex(const float* grad_weights_sum, const float* grad_image,
+                                           const float* sigmas, const float* rgbs, const float* deltas,
+                                           const int32_t* rays, const float* weights_sum, const float* image,
+                                           uint32_t M, uint32_t N, float T_thresh, uint32_t channel_dim,
+                                           float* grad_sigmas, float* grad_rgbs, const int32_t* n_samples,
+                                           snerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Inference march + compositing + compaction  (reference: raymarching.h:17-18, nerf/renderer.py:158)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* raymarching.cu:733-848, raymarching.py:344.  xyzs/dirs/deltas have n_alive*n_step rows (+padding) and
+ * must be zero-initialised by the caller (a zero delta is the terminator, raymarching.cu:885). */
+int snerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                     const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                     uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars,
+                     float* xyzs, float* dirs, float* deltas, const float* noises, snerf_stream_t stream);
+
+/* Same, for n_rows >= n_alive*n_step allocated rows that need NOT be zero-initialised: the kernel writes the
+ * zero terminators and the padding rows itself. */
+int snerf_march_rays_ex(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                        const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                        uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars,
+                        float* xyzs, float* dirs, float* deltas, const float* noises, uint32_t n_rows,
+                        snerf_stream_t stream);
+
+/* raymarching.cu:851-958, raymarching.py:369.  In place on rays_alive/rays_t/weights_sum/depth/image. */
+int snerf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, uint32_t channel_dim,
+                         int32_t* rays_alive, float* rays_t, const float* sigmas, const float* rgbs,
+                         const float* deltas, float* weights_sum, float* depth, float* image,
+                         snerf_stream_t stream);
+
+size_t snerf_compact_rays_workspace_bytes(uint32_t n_alive);
+
+/* Replaces `rays_alive = rays_alive[rays_alive >= 0]` (nerf/renderer.py:158): stable, order-preserving
+ * removal of negative ids.  out may not alias in.  *n_out (device int32) receives the new length. */
+int snerf_compact_rays(const int32_t* rays_alive_in, uint32_t n_alive, int32_t* rays_alive_out, int32_t* n_out,
+                       void* workspace, size_t workspace_bytes, snerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Field: multiresolution hash grid + SH-4 + sigma/colour MLP
+ * (reference: tiny-cuda-nn modules built in nerf/network.py:23-37 from nerf/config.py:47-72 and called
+ *  from nerf/network.py:39-76.  tiny-cuda-nn is an un-vendored, unpinned dependency; the arithmetic below
+ *  is this repo's frozen restatement of its published algorithm, see DESIGN.md "parity unpinned".)
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct snerf_grid_desc {
+  uint32_t n_levels;   /* <= SNERF_MAX_LEVELS                                                       */
+  uint32_t n_features; /* features per level; this build supports 2                                 */
+  uint32_t n_entries;  /* total entries (sum of size[])                                             */
+  uint32_t reserved;
+  float scale[SNERF_MAX_LEVELS];         /* s_l = exp2(l*log2(per_level_scale))*base - 1              */
+  uint32_t resolution[SNERF_MAX_LEVELS]; /* ceil(s_l) + 1                                            */
+  uint32_t offset[SNERF_MAX_LEVELS];     /* first entry of the level in the table                    */
+  uint32_t size[SNERF_MAX_LEVELS];       /* entries in the level = min(ceil8(res^3), 2^log2_hashmap) */
+  uint32_t hashed[SNERF_MAX_LEVELS];     /* 1: spatial hash, 0: dense index                          */
+} snerf_grid_desc;
+
+typedef struct snerf_field_desc {
+  snerf_grid_desc grid;
+  uint32_t width;          /* neurons per hidden layer; this build supports 128 (nerf/config.py:59)  */
+  uint32_t n_hidden_sigma; /* 3 (nerf/config.py:60)                                                  */
+  uint32_t n_hidden_color; /* 4 (nerf/config.py:71)                                                  */
+  uint32_t geo_feat_dim;   /* 15 (nerf/network.py:14)                                                */
+  uint32_t channel_dim;    /* colour channels, 1..4                                                  */
+  float bound;             /* scene bound: x01 = (x + bound) / (2*bound)  (nerf/network.py:43)       */
+} snerf_field_desc;
+
+/* x01 [M,3] in [0,1] -> enc [M, n_levels*n_features] fp32, level-major. */
+int snerf_hashgrid_forward(const snerf_grid_desc* g, const float* x01, const float* table, uint32_t M, float* enc,
+                           snerf_stream_t stream);
+/* grad_table [n_entries*n_features] += scatter of grad_enc.  No gradient flows to x01 (sample positions
+ * carry no gradient in the reference either: march_rays_train has no backward, raymarching.py:161-235). */
+int snerf_hashgrid_backward(const snerf_grid_desc* g, const float* x01, const float* grad_enc, uint32_t M,
+                            float* grad_table, snerf_stream_t stream);
+/* d01 [M,3] in [0,1] (= (d+1)/2, nerf/network.py:51) -> sh [M,16], degree-4 real SH of 2*d01-1. */
+int snerf_sh4_forward(const float* d01, uint32_t M, float* sh, snerf_stream_t stream);
+
+/* number of fp32 parameters of the sigma / colour MLP (layer order, each layer row-major [out,in]) */
+uint32_t snerf_mlp_sigma_params(const snerf_field_desc* f);
+uint32_t snerf_mlp_color_params(const snerf_field_desc* f);
+
+size_t snerf_field_workspace_bytes(const snerf_field_desc* f, uint32_t M, int precision, int backward);
+
+/* nerf/network.py:39-61 (NeRFNetwork.forward): xyzs [M,3] in [-bound,bound], dirs [M,3] unit ->
+ * sigmas [M] (after ReLU), rgbs [M,channel_dim] (after sigmoid). */
+int snerf_field_forward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M,
+                        const float* table, const float* w_sigma, const float* w_color, int precision,
+                        float* sigmas, float* rgbs, void* workspace, size_t workspace_bytes,
+                        snerf_stream_t stream);
+
+/* nerf/network.py:63-76 (NeRFNetwork.density): sigma only; geo_feat [M,geo_feat_dim] optional (may be NULL). */
+int snerf_field_density(const snerf_field_desc* f, const float* xyzs, uint32_t M, const float* table,
+                        const float* w_sigma, int precision, float* sigmas, float* geo_feat, void* workspace,
+                        size_t workspace_bytes, snerf_stream_t stream);
+
+/* Backward of snerf_field_forward.  Recomputes the forward activations from (xyzs, dirs) tile by tile, so
+ * nothing but the inputs has to be kept between forward and backward.  grad_table / grad_w_* are
+ * ACCUMULATED into (caller zeroes them when a new step starts). */
+int snerf_field_backward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M,
+                         const float* table, const float* w_sigma, const float* w_color,
+                         const float* grad_sigmas, const float* grad_rgbs, int precision, float* grad_table,
+                         float* grad_w_sigma, float* grad_w_color, void* workspace, size_t workspace_bytes,
+                         snerf_stream_t stream);
+
+/* nerf/activation.py:6-18.  y = exp(x); dx = g * exp(clamp(x,-15,15)). */
+int snerf_trunc_exp_forward(const float* x, uint32_t n, float* y, snerf_stream_t stream);
+int snerf_trunc_exp_backward(const float* g, const float* x, uint32_t n, float* dx, snerf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNERF_H_ */

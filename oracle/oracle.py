@@ -1,0 +1,254 @@
+"""numpy front-end of the CPU oracle (oracle/snerf_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs.  Never
+imported by anything under stable_nerf_b200/ (tests/test_boundary.py checks that).  See snerf_oracle.h for the
+pinning status of each function.
+"""
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_float, c_int, c_uint32, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libsnerf_oracle.so")
+ORC_MAX_LEVELS = 16
+
+
+class GridDesc(ctypes.Structure):
+    _fields_ = [("n_levels", c_uint32), ("n_features", c_uint32), ("n_entries", c_uint32), ("reserved", c_uint32),
+                ("scale", c_float * ORC_MAX_LEVELS), ("resolution", c_uint32 * ORC_MAX_LEVELS),
+                ("offset", c_uint32 * ORC_MAX_LEVELS), ("size", c_uint32 * ORC_MAX_LEVELS),
+                ("hashed", c_uint32 * ORC_MAX_LEVELS)]
+
+
+class FieldDesc(ctypes.Structure):
+    _fields_ = [("grid", GridDesc), ("width", c_uint32), ("n_hidden_sigma", c_uint32), ("n_hidden_color", c_uint32),
+                ("geo_feat_dim", c_uint32), ("channel_dim", c_uint32), ("bound", c_float)]
+
+
+def build(force=False):
+    """Compile the oracle with gcc (oracle/Makefile)."""
+    if force or not os.path.exists(_LIB_PATH) or \
+            os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "snerf_oracle.c")):
+        subprocess.run(["make", "-C", _HERE, "libsnerf_oracle.so"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        _lib.orc_compact_rays.restype = c_uint32
+        _lib.orc_get_threads.restype = c_int
+    return _lib
+
+
+def set_threads(n):
+    lib().orc_set_threads(c_int(int(n)))
+
+
+def get_threads():
+    return int(lib().orc_get_threads())
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(c_void_p)
+
+
+def copy_desc(src, cls):
+    """Convert a stable_nerf_b200._lib GridDesc/FieldDesc (same memory layout) into the oracle's ctypes struct."""
+    dst = cls()
+    ctypes.memmove(ctypes.byref(dst), ctypes.byref(src), ctypes.sizeof(cls))
+    return dst
+
+
+# ------------------------------------------------------------------------------------------- raymarching
+
+def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2):
+    rays_o, rays_d, aabb = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3), _f32(aabb)
+    N = rays_o.shape[0]
+    nears, fars = np.empty(N, np.float32), np.empty(N, np.float32)
+    lib().orc_near_far_from_aabb(_p(rays_o), _p(rays_d), _p(aabb), c_uint32(N), c_float(min_near), _p(nears), _p(fars))
+    return nears, fars
+
+
+def sph_from_ray(rays_o, rays_d, radius):
+    rays_o, rays_d = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
+    N = rays_o.shape[0]
+    coords = np.empty((N, 2), np.float32)
+    lib().orc_sph_from_ray(_p(rays_o), _p(rays_d), c_float(radius), c_uint32(N), _p(coords))
+    return coords
+
+
+def morton3D(coords):
+    coords = _i32(coords).reshape(-1, 3)
+    out = np.empty(coords.shape[0], np.int32)
+    lib().orc_morton3D(_p(coords), c_uint32(coords.shape[0]), _p(out))
+    return out
+
+
+def morton3D_invert(indices):
+    indices = _i32(indices).reshape(-1)
+    out = np.empty((indices.shape[0], 3), np.int32)
+    lib().orc_morton3D_invert(_p(indices), c_uint32(indices.shape[0]), _p(out))
+    return out
+
+
+def packbits(grid, thresh):
+    grid = _f32(grid).reshape(-1)
+    N = grid.shape[0] // 8
+    out = np.empty(N, np.uint8)
+    lib().orc_packbits(_p(grid), c_uint32(N), c_float(thresh), _p(out))
+    return out
+
+
+def march_rays_train(rays_o, rays_d, bound, bitfield, C, H, nears, fars, noises=None, dt_gamma=0.0, max_steps=1024,
+                     M=None):
+    """Returns xyzs, dirs, deltas [M,...], rays [N,3], counter [2].  M=None sizes the outputs to the exact total."""
+    rays_o, rays_d = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
+    nears, fars = _f32(nears), _f32(fars)
+    N = rays_o.shape[0]
+    noises = np.zeros(N, np.float32) if noises is None else _f32(noises)
+    bitfield = np.ascontiguousarray(bitfield, dtype=np.uint8)
+    args = lambda: (_p(rays_o), _p(rays_d), _p(bitfield), c_float(bound), c_float(dt_gamma), c_uint32(max_steps),
+                    c_uint32(N), c_uint32(C), c_uint32(H))
+    if M is None:
+        rays = np.empty((N, 3), np.int32)
+        counter = np.zeros(2, np.int32)
+        lib().orc_march_rays_train(*args(), c_uint32(0), _p(nears), _p(fars), None, None, None, _p(rays), _p(counter),
+                                   _p(noises))
+        M = int(counter[0])
+    xyzs, dirs, deltas = np.zeros((M, 3), np.float32), np.zeros((M, 3), np.float32), np.zeros((M, 2), np.float32)
+    rays = np.empty((N, 3), np.int32)
+    counter = np.zeros(2, np.int32)
+    lib().orc_march_rays_train(*args(), c_uint32(M), _p(nears), _p(fars), _p(xyzs), _p(dirs), _p(deltas), _p(rays),
+                               _p(counter), _p(noises))
+    return xyzs, dirs, deltas, rays, counter
+
+
+def composite_rays_train_forward(sigmas, rgbs, deltas, rays, T_thresh=1e-4):
+    sigmas, rgbs, deltas, rays = _f32(sigmas), _f32(rgbs), _f32(deltas), _i32(rays)
+    M, N, C = sigmas.shape[0], rays.shape[0], rgbs.shape[1]
+    ws, depth, image = np.empty(N, np.float32), np.empty(N, np.float32), np.empty((N, C), np.float32)
+    lib().orc_composite_rays_train_forward(_p(sigmas), _p(rgbs), _p(deltas), _p(rays), c_uint32(M), c_uint32(N),
+                                           c_float(T_thresh), c_uint32(C), _p(ws), _p(depth), _p(image))
+    return ws, depth, image
+
+
+def composite_rays_train_backward(grad_ws, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, T_thresh=1e-4):
+    sigmas, rgbs, deltas, rays = _f32(sigmas), _f32(rgbs), _f32(deltas), _i32(rays)
+    grad_ws, grad_image, weights_sum, image = _f32(grad_ws), _f32(grad_image), _f32(weights_sum), _f32(image)
+    M, N, C = sigmas.shape[0], rays.shape[0], rgbs.shape[1]
+    gs, gr = np.zeros(M, np.float32), np.zeros((M, C), np.float32)
+    lib().orc_composite_rays_train_backward(_p(grad_ws), _p(grad_image), _p(sigmas), _p(rgbs), _p(deltas), _p(rays),
+                                            _p(weights_sum), _p(image), c_uint32(M), c_uint32(N), c_float(T_thresh),
+                                            c_uint32(C), _p(gs), _p(gr))
+    return gs, gr
+
+
+def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, bitfield, C, H, nears, fars, noises=None,
+               dt_gamma=0.0, max_steps=1024, M=None):
+    rays_o, rays_d = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
+    rays_alive, rays_t, nears, fars = _i32(rays_alive), _f32(rays_t), _f32(nears), _f32(fars)
+    noises = np.zeros(n_alive, np.float32) if noises is None else _f32(noises)
+    bitfield = np.ascontiguousarray(bitfield, dtype=np.uint8)
+    M = n_alive * n_step if M is None else M
+    xyzs, dirs, deltas = np.zeros((M, 3), np.float32), np.zeros((M, 3), np.float32), np.zeros((M, 2), np.float32)
+    lib().orc_march_rays(c_uint32(n_alive), c_uint32(n_step), _p(rays_alive), _p(rays_t), _p(rays_o), _p(rays_d),
+                         c_float(bound), c_float(dt_gamma), c_uint32(max_steps), c_uint32(C), c_uint32(H), _p(bitfield),
+                         _p(nears), _p(fars), _p(xyzs), _p(dirs), _p(deltas), _p(noises))
+    return xyzs, dirs, deltas
+
+
+def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh=1e-2):
+    """In place on rays_alive, rays_t, weights_sum, depth, image (numpy arrays of the right dtype)."""
+    C = image.shape[1]
+    sigmas, rgbs, deltas = _f32(sigmas), _f32(rgbs), _f32(deltas)
+    for a, dt in ((rays_alive, np.int32), (rays_t, np.float32), (weights_sum, np.float32), (depth, np.float32),
+                  (image, np.float32)):
+        assert a.dtype == dt and a.flags.c_contiguous
+    lib().orc_composite_rays(c_uint32(n_alive), c_uint32(n_step), c_float(T_thresh), c_uint32(C), _p(rays_alive),
+                             _p(rays_t), _p(sigmas), _p(rgbs), _p(deltas), _p(weights_sum), _p(depth), _p(image))
+
+
+def compact_rays(rays_alive, n_alive=None):
+    rays_alive = _i32(rays_alive)
+    n = rays_alive.shape[0] if n_alive is None else n_alive
+    out = np.empty(max(n, 1), np.int32)
+    k = lib().orc_compact_rays(_p(rays_alive), c_uint32(n), _p(out))
+    return out[:k].copy()
+
+
+# ------------------------------------------------------------------------------------------- field
+
+def hashgrid_forward(gdesc, x01, table):
+    x01, table = _f32(x01).reshape(-1, 3), _f32(table)
+    M = x01.shape[0]
+    enc = np.empty((M, gdesc.n_levels * gdesc.n_features), np.float32)
+    lib().orc_hashgrid_forward(ctypes.byref(gdesc), _p(x01), _p(table), c_uint32(M), _p(enc))
+    return enc
+
+
+def hashgrid_backward(gdesc, x01, grad_enc):
+    x01, grad_enc = _f32(x01).reshape(-1, 3), _f32(grad_enc)
+    M = x01.shape[0]
+    gt = np.zeros(gdesc.n_entries * gdesc.n_features, np.float32)
+    lib().orc_hashgrid_backward(ctypes.byref(gdesc), _p(x01), _p(grad_enc), c_uint32(M), _p(gt))
+    return gt
+
+
+def sh4_forward(d01):
+    d01 = _f32(d01).reshape(-1, 3)
+    out = np.empty((d01.shape[0], 16), np.float32)
+    lib().orc_sh4_forward(_p(d01), c_uint32(d01.shape[0]), _p(out))
+    return out
+
+
+def field_forward(fdesc, xyzs, dirs, table, w_sigma, w_color, emulate_bf16=False, want_geo=False):
+    xyzs, dirs = _f32(xyzs).reshape(-1, 3), _f32(dirs).reshape(-1, 3)
+    table, w_sigma, w_color = _f32(table), _f32(w_sigma), _f32(w_color)
+    M = xyzs.shape[0]
+    sig, rgb = np.empty(M, np.float32), np.empty((M, fdesc.channel_dim), np.float32)
+    geo = np.empty((M, fdesc.geo_feat_dim), np.float32) if want_geo else None
+    lib().orc_field_forward(ctypes.byref(fdesc), _p(xyzs), _p(dirs), c_uint32(M), _p(table), _p(w_sigma), _p(w_color),
+                            c_int(int(emulate_bf16)), _p(sig), _p(rgb), _p(geo))
+    return (sig, rgb, geo) if want_geo else (sig, rgb)
+
+
+def field_backward(fdesc, xyzs, dirs, table, w_sigma, w_color, grad_sigmas, grad_rgbs, emulate_bf16=False):
+    xyzs, dirs = _f32(xyzs).reshape(-1, 3), _f32(dirs).reshape(-1, 3)
+    table, w_sigma, w_color = _f32(table), _f32(w_sigma), _f32(w_color)
+    grad_sigmas, grad_rgbs = _f32(grad_sigmas), _f32(grad_rgbs)
+    M = xyzs.shape[0]
+    gt, gws, gwc = np.zeros_like(table), np.zeros_like(w_sigma), np.zeros_like(w_color)
+    lib().orc_field_backward(ctypes.byref(fdesc), _p(xyzs), _p(dirs), c_uint32(M), _p(table), _p(w_sigma), _p(w_color),
+                             _p(grad_sigmas), _p(grad_rgbs), c_int(int(emulate_bf16)), _p(gt), _p(gws), _p(gwc))
+    return gt, gws, gwc
+
+
+def trunc_exp_forward(x):
+    x = _f32(x).reshape(-1)
+    y = np.empty_like(x)
+    lib().orc_trunc_exp_forward(_p(x), c_uint32(x.shape[0]), _p(y))
+    return y
+
+
+def trunc_exp_backward(g, x):
+    g, x = _f32(g).reshape(-1), _f32(x).reshape(-1)
+    dx = np.empty_like(x)
+    lib().orc_trunc_exp_backward(_p(g), _p(x), c_uint32(x.shape[0]), _p(dx))
+    return dx

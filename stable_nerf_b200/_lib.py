@@ -1,0 +1,150 @@
+"""ctypes binding of libsnerf_b200.so (C ABI declared in include/snerf.h).
+
+There is no CPU fallback and no other backend: if the shared library is missing or a call returns a non-zero
+code, a RuntimeError is raised.  The library is built in-tree by ``__graft_entry__.build()`` /
+``make -C stable_nerf_b200/csrc``.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_size_t, c_uint32, c_uint64, c_void_p, POINTER
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsnerf_b200.so")
+
+SNERF_MAX_LEVELS = 16
+PRECISION_FP32 = 0
+PRECISION_BF16 = 1
+
+
+class GridDesc(ctypes.Structure):
+    """snerf_grid_desc (include/snerf.h)."""
+    _fields_ = [
+        ("n_levels", c_uint32), ("n_features", c_uint32), ("n_entries", c_uint32), ("reserved", c_uint32),
+        ("scale", c_float * SNERF_MAX_LEVELS),
+        ("resolution", c_uint32 * SNERF_MAX_LEVELS),
+        ("offset", c_uint32 * SNERF_MAX_LEVELS),
+        ("size", c_uint32 * SNERF_MAX_LEVELS),
+        ("hashed", c_uint32 * SNERF_MAX_LEVELS),
+    ]
+
+
+class FieldDesc(ctypes.Structure):
+    """snerf_field_desc (include/snerf.h)."""
+    _fields_ = [
+        ("grid", GridDesc),
+        ("width", c_uint32), ("n_hidden_sigma", c_uint32), ("n_hidden_color", c_uint32),
+        ("geo_feat_dim", c_uint32), ("channel_dim", c_uint32), ("bound", c_float),
+    ]
+
+
+_P = c_void_p
+_U = c_uint32
+_F = c_float
+_S = c_void_p  # stream
+
+# name -> (restype, argtypes); mirrors include/snerf.h one to one
+SIGNATURES = {
+    "snerf_version": (c_int, []),
+    "snerf_error_string": (c_char_p, [c_int]),
+    "snerf_launch_count": (c_uint64, []),
+    "snerf_near_far_from_aabb": (c_int, [_P, _P, _P, _U, _F, _P, _P, _S]),
+    "snerf_sph_from_ray": (c_int, [_P, _P, _F, _U, _P, _S]),
+    "snerf_morton3D": (c_int, [_P, _U, _P, _S]),
+    "snerf_morton3D_invert": (c_int, [_P, _U, _P, _S]),
+    "snerf_packbits": (c_int, [_P, _U, _F, _P, _S]),
+    "snerf_march_rays_train_workspace_bytes": (c_size_t, [_U]),
+    "snerf_march_rays_train_count": (c_int, [_P, _P, _P, _F, _F, _U, _U, _U, _U, _P, _P, _P, _P, _P, c_size_t, _S]),
+    "snerf_march_rays_train_write": (c_int, [_P, _P, _P, _F, _F, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, c_int,
+                                             _P, _P, c_size_t, _S]),
+    "snerf_march_rays_ex": (c_int, [_U, _U, _P, _P, _P, _P, _F, _F, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _U, _S]),
+    "snerf_march_rays_train": (c_int, [_P, _P, _P, _F, _F, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                       c_size_t, _S]),
+    "snerf_composite_rays_train_forward": (c_int, [_P, _P, _P, _P, _U, _U, _F, _U, _P, _P, _P, _S]),
+    "snerf_composite_rays_train_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _F, _U, _P, _P, _S]),
+    "snerf_composite_rays_train_backward_ex": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _F, _U, _P, _P, _P, _S]),
+    "snerf_march_rays": (c_int, [_U, _U, _P, _P, _P, _P, _F, _F, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _S]),
+    "snerf_composite_rays": (c_int, [_U, _U, _F, _U, _P, _P, _P, _P, _P, _P, _P, _P, _S]),
+    "snerf_compact_rays_workspace_bytes": (c_size_t, [_U]),
+    "snerf_compact_rays": (c_int, [_P, _U, _P, _P, _P, c_size_t, _S]),
+    "snerf_hashgrid_forward": (c_int, [POINTER(GridDesc), _P, _P, _U, _P, _S]),
+    "snerf_hashgrid_backward": (c_int, [POINTER(GridDesc), _P, _P, _U, _P, _S]),
+    "snerf_sh4_forward": (c_int, [_P, _U, _P, _S]),
+    "snerf_mlp_sigma_params": (c_uint32, [POINTER(FieldDesc)]),
+    "snerf_mlp_color_params": (c_uint32, [POINTER(FieldDesc)]),
+    "snerf_field_workspace_bytes": (c_size_t, [POINTER(FieldDesc), _U, c_int, c_int]),
+    "snerf_field_forward": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, c_int, _P, _P, _P, c_size_t, _S]),
+    "snerf_field_density": (c_int, [POINTER(FieldDesc), _P, _U, _P, _P, c_int, _P, _P, _P, c_size_t, _S]),
+    "snerf_field_backward": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P,
+                                     c_size_t, _S]),
+    "snerf_trunc_exp_forward": (c_int, [_P, _U, _P, _S]),
+    "snerf_trunc_exp_backward": (c_int, [_P, _P, _U, _P, _S]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libsnerf_b200.so once; raise loudly if it is not there (no fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
+                f"g.build()'` or `make -C stable_nerf_b200/csrc`. There is no CPU or PyTorch fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().snerf_error_string(int(code)).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {code})")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("stable_nerf_b200 runs on CUDA tensors only (sm_100a); got a CPU tensor")
+
+
+def launch_count():
+    return int(load().snerf_launch_count())
+
+
+class Workspace:
+    """Grow-only per-device scratch buffers keyed by name.
+
+    The reference wrappers allocate fresh torch.zeros/empty tensors on every call and call
+    torch.cuda.empty_cache() on the sync path (raymarching.py:206-231); the kernels here borrow scratch
+    from this cache instead.
+    """
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, name, nbytes, device):
+        key = (name, str(device))
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
+
+
+workspace = Workspace()

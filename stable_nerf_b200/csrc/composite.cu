@@ -1,0 +1,321 @@
+// composite.cu -- front-to-back alpha compositing of packed samples, forward and backward (training), and the
+// incremental inference variant.
+//
+// Replaces raymarching.cu:501-726 and :851-958 of the reference.  The reference walks each ray with ONE thread
+// (serial loop, 4-byte strided loads).  Here a WARP owns a ray: 32 consecutive samples are loaded with one
+// coalesced request per array, transmittance is a warp product-scan of (1-alpha), depth time and the
+// per-channel partial sums are warp sum-scans, and early termination is a ballot.  Results differ from the
+// serial loop only by fp32 re-association (the test tolerance is 1e-4 relative).
+#include "common.cuh"
+
+namespace snerf {
+
+constexpr int kCompThreads = 256;  // 8 rays per block
+constexpr float kNegLog2e = -1.4426950408889634f;
+
+// alpha = 1 - __expf(-sigma*delta): same formula and the same ex2.approx path as raymarching.cu:549
+__device__ __forceinline__ float alpha_of(float sigma, float delta) { return 1.0f - __expf(-sigma * delta); }
+
+template <int C>
+__device__ __forceinline__ void load_rgb(const float* __restrict__ rgbs, size_t i, float (&c)[C]) {
+  if constexpr (C == 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(rgbs) + i);
+    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+  } else if constexpr (C == 2) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(rgbs) + i);
+    c[0] = v.x; c[1] = v.y;
+  } else {
+#pragma unroll
+    for (int k = 0; k < C; k++) c[k] = __ldg(rgbs + i * C + k);
+  }
+}
+template <int C>
+__device__ __forceinline__ void store_rgb(float* __restrict__ out, size_t i, const float (&c)[C]) {
+  if constexpr (C == 4) {
+    reinterpret_cast<float4*>(out)[i] = make_float4(c[0], c[1], c[2], c[3]);
+  } else if constexpr (C == 2) {
+    reinterpret_cast<float2*>(out)[i] = make_float2(c[0], c[1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < C; k++) out[i * C + k] = c[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ train forward
+
+template <int C>
+__global__ void __launch_bounds__(kCompThreads) k_composite_train_fwd(const float* __restrict__ sigmas,
+                                                                      const float* __restrict__ rgbs,
+                                                                      const float* __restrict__ deltas,
+                                                                      const int32_t* __restrict__ rays, uint32_t M,
+                                                                      uint32_t N, float T_thresh,
+                                                                      float* __restrict__ weights_sum,
+                                                                      float* __restrict__ depth,
+                                                                      float* __restrict__ image) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+
+  float ws = 0.f, d = 0.f, ch[C];
+#pragma unroll
+  for (int k = 0; k < C; k++) ch[k] = 0.f;
+
+  if (num_steps != 0 && offset + num_steps <= M) {
+    float T_run = 1.f, t_run = 0.f;
+    for (uint32_t base = 0; base < num_steps; base += 32) {
+      const uint32_t i = base + lane;
+      const bool valid = i < num_steps;
+      float alpha = 0.f, dz = 0.f, c[C];
+#pragma unroll
+      for (int k = 0; k < C; k++) c[k] = 0.f;
+      if (valid) {
+        const float2 dl = __ldg(reinterpret_cast<const float2*>(deltas) + offset + i);
+        alpha = alpha_of(__ldg(sigmas + offset + i), dl.x);
+        dz = dl.y;
+        load_rgb<C>(rgbs, (size_t)offset + i, c);
+      }
+      const float p_incl = warp_incl_prod(1.0f - alpha, lane);
+      float p_excl = __shfl_up_sync(kFull, p_incl, 1);
+      if (lane == 0) p_excl = 1.0f;
+      const float T_after = T_run * p_incl;
+      // the reference accumulates the sample, then breaks when T < T_thresh (raymarching.cu:565-566)
+      const unsigned term = __ballot_sync(kFull, valid && (T_after < T_thresh));
+      const int last = term ? (__ffs(term) - 1) : 31;
+      const float w = (valid && lane <= last) ? alpha * (T_run * p_excl) : 0.f;
+      const float t_i = t_run + warp_incl_sum(dz, lane);
+      ws += w;
+      d += w * t_i;
+#pragma unroll
+      for (int k = 0; k < C; k++) ch[k] += w * c[k];
+      if (term) break;
+      T_run = __shfl_sync(kFull, T_after, 31);
+      t_run = __shfl_sync(kFull, t_i, 31);
+    }
+    ws = warp_sum(ws);
+    d = warp_sum(d);
+#pragma unroll
+    for (int k = 0; k < C; k++) ch[k] = warp_sum(ch[k]);
+  }
+  if (lane == 0) {
+    weights_sum[index] = ws;
+    depth[index] = d;
+    store_rgb<C>(image, index, ch);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ train backward
+
+// Every sample row owned by a ray is written (zeros after the termination point and for dropped rays), so the
+// caller does not have to memset the gradients the way raymarching.py:283-284 does.
+template <int C>
+__global__ void __launch_bounds__(kCompThreads) k_composite_train_bwd(
+    const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image, const float* __restrict__ sigmas,
+    const float* __restrict__ rgbs, const float* __restrict__ deltas, const int32_t* __restrict__ rays,
+    const float* __restrict__ weights_sum, const float* __restrict__ image, uint32_t M, uint32_t N, float T_thresh,
+    float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+  if (num_steps == 0 || offset >= M) return;
+  float zero[C];
+#pragma unroll
+  for (int k = 0; k < C; k++) zero[k] = 0.f;
+  if (offset + num_steps > M) {  // dropped ray: its rows inside [0,M) carry no gradient
+    for (uint32_t i = offset + lane; i < M; i += 32) {
+      grad_sigmas[i] = 0.f;
+      store_rgb<C>(grad_rgbs, i, zero);
+    }
+    return;
+  }
+  const float gws_term = __ldg(grad_weights_sum + index) * (1.0f - __ldg(weights_sum + index));
+  float gi[C], fin[C], acc_run[C];
+  load_rgb<C>(grad_image, index, gi);
+  load_rgb<C>(image, index, fin);
+#pragma unroll
+  for (int k = 0; k < C; k++) acc_run[k] = 0.f;
+
+  float T_run = 1.f;
+  bool done = false;
+  for (uint32_t base = 0; base < num_steps; base += 32) {
+    const uint32_t i = base + lane;
+    const bool valid = i < num_steps;
+    if (done) {  // past the termination point: zero gradients
+      if (valid) {
+        grad_sigmas[offset + i] = 0.f;
+        store_rgb<C>(grad_rgbs, (size_t)offset + i, zero);
+      }
+      continue;
+    }
+    float alpha = 0.f, d0 = 0.f, c[C];
+#pragma unroll
+    for (int k = 0; k < C; k++) c[k] = 0.f;
+    if (valid) {
+      d0 = __ldg(reinterpret_cast<const float2*>(deltas) + offset + i).x;
+      alpha = alpha_of(__ldg(sigmas + offset + i), d0);
+      load_rgb<C>(rgbs, (size_t)offset + i, c);
+    }
+    const float p_incl = warp_incl_prod(1.0f - alpha, lane);
+    float p_excl = __shfl_up_sync(kFull, p_incl, 1);
+    if (lane == 0) p_excl = 1.0f;
+    const float T_after = T_run * p_incl;
+    const unsigned term = __ballot_sync(kFull, valid && (T_after < T_thresh));
+    const int last = term ? (__ffs(term) - 1) : 31;
+    const bool inc = valid && lane <= last;
+    const float w = inc ? alpha * (T_run * p_excl) : 0.f;
+    float gs = gws_term, gr[C];
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+      const float acc = acc_run[k] + warp_incl_sum(w * c[k], lane);  // channels[] after this sample (:660-662)
+      gs += gi[k] * (T_after * c[k] - (fin[k] - acc));               // :680-686
+      gr[k] = gi[k] * w;                                             // :671-673
+      acc_run[k] = __shfl_sync(kFull, acc, 31);
+    }
+    if (valid) {
+      grad_sigmas[offset + i] = inc ? d0 * gs : 0.f;
+      if (!inc) {
+#pragma unroll
+        for (int k = 0; k < C; k++) gr[k] = 0.f;
+      }
+      store_rgb<C>(grad_rgbs, (size_t)offset + i, gr);
+    }
+    if (term) done = true;
+    T_run = __shfl_sync(kFull, T_after, 31);
+  }
+}
+
+// zero rows [*n_samples, M) of the gradients (alignment padding that no ray owns)
+template <int C>
+__global__ void __launch_bounds__(256) k_zero_tail(const int32_t* __restrict__ n_samples, uint32_t M,
+                                                   float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+  const uint32_t start = (uint32_t)max(0, *n_samples);
+  for (uint32_t i = start + blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+    grad_sigmas[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < C; k++) grad_rgbs[(size_t)i * C + k] = 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ inference
+//
+// n_step <= 8 samples per alive ray per call (nerf/renderer.py:146): a thread per ray is the right grain; the
+// loads are made contiguous per ray (n_step consecutive rows).
+
+template <int C>
+__global__ void __launch_bounds__(128) k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh,
+                                                        int32_t* __restrict__ rays_alive, float* __restrict__ rays_t,
+                                                        const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                        const float* __restrict__ deltas, float* __restrict__ weights_sum,
+                                                        float* __restrict__ depth, float* __restrict__ image) {
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_alive) return;
+  const int index = rays_alive[n];
+  if (index < 0) return;  // tolerate an uncompacted list
+  const size_t s0 = (size_t)n * n_step;
+  float t = rays_t[index], weight_sum = weights_sum[index], d = depth[index], ch[C];
+  load_rgb<C>(image, (size_t)index, ch);
+  uint32_t step = 0;
+  while (step < n_step) {
+    const float2 dl = __ldg(reinterpret_cast<const float2*>(deltas) + s0 + step);
+    if (dl.x == 0.f) break;  // terminator (raymarching.cu:885)
+    const float alpha = alpha_of(__ldg(sigmas + s0 + step), dl.x);
+    const float T = 1.0f - weight_sum;
+    const float weight = alpha * T;
+    weight_sum += weight;
+    t += dl.y;
+    d += weight * t;
+    float c[C];
+    load_rgb<C>(rgbs, s0 + step, c);
+#pragma unroll
+    for (int k = 0; k < C; k++) ch[k] += weight * c[k];
+    if (T < T_thresh) break;
+    step++;
+  }
+  if (step < n_step) rays_alive[n] = -1;
+  else rays_t[index] = t;
+  weights_sum[index] = weight_sum;
+  depth[index] = d;
+  store_rgb<C>(image, (size_t)index, ch);
+}
+
+}  // namespace snerf
+
+using namespace snerf;
+
+#define SNERF_DISPATCH_C(C, ...)                     \
+  switch (C) {                                       \
+    case 1: { constexpr int kC = 1; __VA_ARGS__; break; } \
+    case 2: { constexpr int kC = 2; __VA_ARGS__; break; } \
+    case 3: { constexpr int kC = 3; __VA_ARGS__; break; } \
+    case 4: { constexpr int kC = 4; __VA_ARGS__; break; } \
+    default: return SNERF_E_CHANNELS;                \
+  }
+
+extern "C" {
+
+int snerf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays,
+                                       uint32_t M, uint32_t N, float T_thresh, uint32_t channel_dim, float* weights_sum,
+                                       float* depth, float* image, snerf_stream_t stream) {
+  if (N == 0) return SNERF_OK;
+  if (!rays || !weights_sum || !depth || !image) return SNERF_E_BADARG;
+  if (M > 0 && (!sigmas || !rgbs || !deltas)) return SNERF_E_BADARG;
+  const uint32_t blocks = div_up(N, kCompThreads / 32);
+  SNERF_DISPATCH_C(channel_dim, (k_composite_train_fwd<kC><<<blocks, kCompThreads, 0, (cudaStream_t)stream>>>(
+                                    sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image)));
+  return finish_launch();
+}
+
+int snerf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                        const float* rgbs, const float* deltas, const int32_t* rays,
+                                        const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                        float T_thresh, uint32_t channel_dim, float* grad_sigmas, float* grad_rgbs,
+                                        snerf_stream_t stream) {
+  return snerf_composite_rays_train_backward_ex(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum,
+                                                image, M, N, T_thresh, channel_dim, grad_sigmas, grad_rgbs, nullptr,
+                                                stream);
+}
+
+int snerf_composite_rays_train_backward_ex(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                           const float* rgbs, const float* deltas, const int32_t* rays,
+                                           const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                           float T_thresh, uint32_t channel_dim, float* grad_sigmas, float* grad_rgbs,
+                                           const int32_t* n_samples, snerf_stream_t stream) {
+  if (M == 0) return SNERF_OK;
+  if (!grad_sigmas || !grad_rgbs) return SNERF_E_BADARG;
+  if (channel_dim < 1 || channel_dim > SNERF_MAX_CHANNELS) return SNERF_E_CHANNELS;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned launches = 0;
+  if (!n_samples) {
+    // rows not owned by any ray are unknown: clear everything first (what raymarching.py:283-284 does)
+    cudaError_t e = cudaMemsetAsync(grad_sigmas, 0, (size_t)M * sizeof(float), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(grad_rgbs, 0, (size_t)M * channel_dim * sizeof(float), s);
+    if (e != cudaSuccess) return (int)e;
+  } else {
+    SNERF_DISPATCH_C(channel_dim, (k_zero_tail<kC><<<8, 256, 0, s>>>(n_samples, M, grad_sigmas, grad_rgbs)));
+    launches++;
+  }
+  if (N > 0) {
+    if (!grad_weights_sum || !grad_image || !sigmas || !rgbs || !deltas || !rays || !weights_sum || !image)
+      return SNERF_E_BADARG;
+    const uint32_t blocks = div_up(N, kCompThreads / 32);
+    SNERF_DISPATCH_C(channel_dim, (k_composite_train_bwd<kC><<<blocks, kCompThreads, 0, s>>>(
+                                      grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N,
+                                      T_thresh, grad_sigmas, grad_rgbs)));
+    launches++;
+  }
+  return finish_launch(launches);
+}
+
+int snerf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, uint32_t channel_dim, int32_t* rays_alive,
+                         float* rays_t, const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
+                         float* depth, float* image, snerf_stream_t stream) {
+  if (n_alive == 0) return SNERF_OK;
+  if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image) return SNERF_E_BADARG;
+  SNERF_DISPATCH_C(channel_dim, (k_composite_rays<kC><<<div_up(n_alive, 128), 128, 0, (cudaStream_t)stream>>>(
+                                    n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum,
+                                    depth, image)));
+  return finish_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,258 @@
+// field_encode.cu -- multiresolution hash-grid encoding (forward gather, backward scatter-add) and the degree-4
+// spherical-harmonics direction encoding.
+//
+// Replaces the tiny-cuda-nn HashGrid / SphericalHarmonics encodings the reference instantiates in
+// nerf/network.py:23-32 from nerf/config.py:47-65 (16 levels x 2 features, T = 2^19, base 16, finest 2048).
+// tiny-cuda-nn is not vendored by the reference; the arithmetic is this repo's frozen restatement (oracle/
+// snerf_oracle.c, orc_hashgrid_*), fp32 table, fp32 interpolation.
+//
+// Layout: a CTA owns a tile of 128 consecutive samples.  Positions are staged in shared memory with one coalesced
+// read; a warp then works on 32 consecutive samples of ONE level, so its 8x32 gathers hit the same level slice
+// (consecutive samples of a ray are ~dt apart, i.e. mostly the same or neighbouring cells: L1/L2 hits).  Each
+// (sample, level) result is a float2; results are staged in an XOR-swizzled shared tile and written back as one
+// contiguous 16 KiB block.  The backward kernel mirrors this: coalesced read of the gradient tile, 8 float2
+// reductions (red.global.add.v2.f32) per (sample, level).
+#include "common.cuh"
+
+namespace snerf {
+
+constexpr int kEncTile = 128;    // samples per CTA
+constexpr int kEncThreads = 256;
+
+struct LevelInfo {
+  float scale;
+  uint32_t res, offset, size, hashed, pow2_mask;  // pow2_mask = size-1 if size is a power of two else 0
+};
+
+__device__ __forceinline__ LevelInfo level_info(const snerf_grid_desc& g, uint32_t l) {
+  LevelInfo li;
+  li.scale = g.scale[l];
+  li.res = g.resolution[l];
+  li.offset = g.offset[l];
+  li.size = g.size[l];
+  li.hashed = g.hashed[l];
+  li.pow2_mask = (li.size & (li.size - 1)) == 0 ? li.size - 1 : 0;
+  return li;
+}
+
+__device__ __forceinline__ uint32_t grid_index(const LevelInfo& li, uint32_t ix, uint32_t iy, uint32_t iz) {
+  uint32_t idx;
+  if (li.hashed) idx = ix ^ (iy * 2654435761u) ^ (iz * 805459861u);
+  else idx = ix + iy * li.res + iz * li.res * li.res;
+  if (li.pow2_mask) idx &= li.pow2_mask;
+  else if (idx >= li.size) idx %= li.size;
+  return li.offset + idx;
+}
+
+struct Cell {
+  uint32_t c[3];
+  float w[3];
+};
+__device__ __forceinline__ Cell grid_cell(float x, float y, float z, float scale) {
+  Cell r;
+  const float p[3] = {ffma(x, scale, 0.5f), ffma(y, scale, 0.5f), ffma(z, scale, 0.5f)};
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const float fl = floorf(p[d]);
+    r.c[d] = (uint32_t)(int32_t)fl;
+    r.w[d] = fadd(p[d], -fl);
+  }
+  return r;
+}
+__device__ __forceinline__ float corner_weight(const Cell& c, uint32_t corner) {
+  const float wx = (corner & 1u) ? c.w[0] : fadd(1.0f, -c.w[0]);
+  const float wy = (corner & 2u) ? c.w[1] : fadd(1.0f, -c.w[1]);
+  const float wz = (corner & 4u) ? c.w[2] : fadd(1.0f, -c.w[2]);
+  return fmul(fmul(wx, wy), wz);
+}
+
+// swizzled position of the float2 slot (sample s, level l) inside a [kEncTile][16] float2 tile
+__device__ __forceinline__ int tile_slot(int s, int l) { return s * 16 + (l ^ (s & 15)); }
+
+template <bool kNormalize>
+__global__ void __launch_bounds__(kEncThreads) k_hashgrid_fwd(snerf_grid_desc g, const float* __restrict__ x,
+                                                              float bound, const float2* __restrict__ table,
+                                                              uint32_t M, float* __restrict__ enc) {
+  __shared__ float xs[kEncTile * 3];
+  __shared__ float2 tile[kEncTile * 16];
+  const uint32_t m0 = blockIdx.x * kEncTile;
+  const uint32_t ns = min((uint32_t)kEncTile, M - m0);
+  for (uint32_t i = threadIdx.x; i < ns * 3; i += kEncThreads) {
+    float v = __ldg(x + (size_t)m0 * 3 + i);
+    if (kNormalize) v = __fdiv_rn(fadd(v, bound), fmul(2.0f, bound));  // nerf/network.py:43
+    xs[i] = v;
+  }
+  __syncthreads();
+  const uint32_t L = g.n_levels;
+  for (uint32_t item = threadIdx.x; item < kEncTile * L; item += kEncThreads) {
+    const uint32_t s = item % kEncTile, l = item / kEncTile;
+    if (s >= ns) continue;
+    const LevelInfo li = level_info(g, l);
+    const Cell c = grid_cell(xs[s * 3], xs[s * 3 + 1], xs[s * 3 + 2], li.scale);
+    float2 v[8];
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++)
+      v[k] = __ldg(table + grid_index(li, c.c[0] + (k & 1u), c.c[1] + ((k >> 1) & 1u), c.c[2] + (k >> 2)));
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) {
+      const float wt = corner_weight(c, k);
+      acc.x = ffma(wt, v[k].x, acc.x);
+      acc.y = ffma(wt, v[k].y, acc.y);
+    }
+    tile[tile_slot(s, l)] = acc;
+  }
+  __syncthreads();
+  float2* out = reinterpret_cast<float2*>(enc) + (size_t)m0 * L;
+  if (L == 16) {
+    for (uint32_t i = threadIdx.x; i < ns * 16; i += kEncThreads) out[i] = tile[tile_slot(i >> 4, i & 15)];
+  } else {
+    for (uint32_t i = threadIdx.x; i < ns * L; i += kEncThreads) out[i] = tile[tile_slot(i / L, i % L)];
+  }
+}
+
+template <bool kNormalize>
+__global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g, const float* __restrict__ x,
+                                                              float bound, const float* __restrict__ grad_enc,
+                                                              uint32_t M, float2* __restrict__ grad_table) {
+  __shared__ float xs[kEncTile * 3];
+  __shared__ float2 tile[kEncTile * 16];
+  const uint32_t m0 = blockIdx.x * kEncTile;
+  const uint32_t ns = min((uint32_t)kEncTile, M - m0);
+  const uint32_t L = g.n_levels;
+  for (uint32_t i = threadIdx.x; i < ns * 3; i += kEncThreads) {
+    float v = __ldg(x + (size_t)m0 * 3 + i);
+    if (kNormalize) v = __fdiv_rn(fadd(v, bound), fmul(2.0f, bound));
+    xs[i] = v;
+  }
+  const float2* gin = reinterpret_cast<const float2*>(grad_enc) + (size_t)m0 * L;
+  for (uint32_t i = threadIdx.x; i < ns * L; i += kEncThreads) tile[tile_slot(i / L, i % L)] = __ldg(gin + i);
+  __syncthreads();
+  for (uint32_t item = threadIdx.x; item < kEncTile * L; item += kEncThreads) {
+    const uint32_t s = item % kEncTile, l = item / kEncTile;
+    if (s >= ns) continue;
+    const float2 gv = tile[tile_slot(s, l)];
+    if (gv.x == 0.f && gv.y == 0.f) continue;  // padded / terminated samples carry exact zeros
+    const LevelInfo li = level_info(g, l);
+    const Cell c = grid_cell(xs[s * 3], xs[s * 3 + 1], xs[s * 3 + 2], li.scale);
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) {
+      const float wt = corner_weight(c, k);
+      const uint32_t idx = grid_index(li, c.c[0] + (k & 1u), c.c[1] + ((k >> 1) & 1u), c.c[2] + (k >> 2));
+      atomicAdd(grad_table + idx, make_float2(wt * gv.x, wt * gv.y));
+    }
+  }
+}
+
+// degree-4 real spherical harmonics of 2*d01-1 (SURVEY Appendix A constants)
+__device__ __forceinline__ void sh4_eval(float x01, float y01, float z01, float* o) {
+  const float x = x01 * 2.0f - 1.0f, y = y01 * 2.0f - 1.0f, z = z01 * 2.0f - 1.0f;
+  const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+  o[0] = 0.28209479177387814f;
+  o[1] = -0.48860251190291987f * y;
+  o[2] = 0.48860251190291987f * z;
+  o[3] = -0.48860251190291987f * x;
+  o[4] = 1.0925484305920792f * xy;
+  o[5] = -1.0925484305920792f * yz;
+  o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+  o[7] = -1.0925484305920792f * xz;
+  o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+  o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+  o[10] = 2.8906114426405538f * xy * z;
+  o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+  o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+  o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+  o[14] = 1.4453057213202769f * z * (x2 - y2);
+  o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+__global__ void __launch_bounds__(256) k_sh4(const float* __restrict__ d01, uint32_t M, float* __restrict__ sh) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float o[16];
+  sh4_eval(d01[m * 3], d01[m * 3 + 1], d01[m * 3 + 2], o);
+  float4* out = reinterpret_cast<float4*>(sh) + (size_t)m * 4;
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+}
+
+__global__ void __launch_bounds__(256) k_trunc_exp_fwd(const float* __restrict__ x, uint32_t n, float* __restrict__ y) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = expf(x[i]);
+}
+__global__ void __launch_bounds__(256) k_trunc_exp_bwd(const float* __restrict__ g, const float* __restrict__ x,
+                                                       uint32_t n, float* __restrict__ dx) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dx[i] = g[i] * expf(fminf(fmaxf(x[i], -15.0f), 15.0f));
+}
+
+int check_grid_desc(const snerf_grid_desc* g) {
+  if (!g) return SNERF_E_BADARG;
+  if (g->n_levels < 1 || g->n_levels > SNERF_MAX_LEVELS) return SNERF_E_UNSUPPORTED;
+  if (g->n_features != 2) return SNERF_E_UNSUPPORTED;
+  return SNERF_OK;
+}
+
+// launched by the field code too (field_fp32.cu): x is world-space, normalised in-kernel
+int launch_hashgrid_fwd(const snerf_grid_desc* g, const float* x, bool normalize, float bound, const float* table,
+                        uint32_t M, float* enc, cudaStream_t s) {
+  const uint32_t blocks = div_up(M, kEncTile);
+  if (normalize)
+    k_hashgrid_fwd<true><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, reinterpret_cast<const float2*>(table), M, enc);
+  else
+    k_hashgrid_fwd<false><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, reinterpret_cast<const float2*>(table), M, enc);
+  return finish_launch();
+}
+int launch_hashgrid_bwd(const snerf_grid_desc* g, const float* x, bool normalize, float bound, const float* grad_enc,
+                        uint32_t M, float* grad_table, cudaStream_t s) {
+  const uint32_t blocks = div_up(M, kEncTile);
+  if (normalize)
+    k_hashgrid_bwd<true><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, grad_enc, M, reinterpret_cast<float2*>(grad_table));
+  else
+    k_hashgrid_bwd<false><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, grad_enc, M, reinterpret_cast<float2*>(grad_table));
+  return finish_launch();
+}
+
+}  // namespace snerf
+
+using namespace snerf;
+
+extern "C" {
+
+int snerf_hashgrid_forward(const snerf_grid_desc* g, const float* x01, const float* table, uint32_t M, float* enc,
+                           snerf_stream_t stream) {
+  if (int e = check_grid_desc(g)) return e;
+  if (M == 0) return SNERF_OK;
+  if (!x01 || !table || !enc) return SNERF_E_BADARG;
+  return launch_hashgrid_fwd(g, x01, false, 1.0f, table, M, enc, (cudaStream_t)stream);
+}
+
+int snerf_hashgrid_backward(const snerf_grid_desc* g, const float* x01, const float* grad_enc, uint32_t M,
+                            float* grad_table, snerf_stream_t stream) {
+  if (int e = check_grid_desc(g)) return e;
+  if (M == 0) return SNERF_OK;
+  if (!x01 || !grad_enc || !grad_table) return SNERF_E_BADARG;
+  return launch_hashgrid_bwd(g, x01, false, 1.0f, grad_enc, M, grad_table, (cudaStream_t)stream);
+}
+
+int snerf_sh4_forward(const float* d01, uint32_t M, float* sh, snerf_stream_t stream) {
+  if (M == 0) return SNERF_OK;
+  if (!d01 || !sh) return SNERF_E_BADARG;
+  k_sh4<<<div_up(M, 256), 256, 0, (cudaStream_t)stream>>>(d01, M, sh);
+  return finish_launch();
+}
+
+int snerf_trunc_exp_forward(const float* x, uint32_t n, float* y, snerf_stream_t stream) {
+  if (n == 0) return SNERF_OK;
+  if (!x || !y) return SNERF_E_BADARG;
+  k_trunc_exp_fwd<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, y);
+  return finish_launch();
+}
+int snerf_trunc_exp_backward(const float* g, const float* x, uint32_t n, float* dx, snerf_stream_t stream) {
+  if (n == 0) return SNERF_OK;
+  if (!g || !x || !dx) return SNERF_E_BADARG;
+  k_trunc_exp_bwd<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(g, x, n, dx);
+  return finish_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,538 @@
+// raymarch.cu -- ray utilities, occupancy-grid marching (training + inference) and alive-ray compaction.
+//
+// Replaces the reference kernels of submodules/raymarching/src/raymarching.cu:92-491 and :733-848 plus the
+// torch boolean-mask compaction of nerf/renderer.py:158.  Marching results are bit-identical to the reference
+// (given the same bitfield) because every rounding step is pinned with an intrinsic at exactly the places
+// where nvcc fuses the reference's expressions (see oracle/snerf_oracle.c, "[FMA]" marks).  Unlike the
+// reference, sample offsets come from a deterministic ray-order scan, not from atomicAdd.
+#include "common.cuh"
+
+namespace snerf {
+
+// ------------------------------------------------------------------------------------------------ utils
+
+__global__ void __launch_bounds__(256) k_near_far_from_aabb(const float* __restrict__ rays_o,
+                                                            const float* __restrict__ rays_d,
+                                                            const float* __restrict__ aabb, uint32_t N, float min_near,
+                                                            float* __restrict__ nears, float* __restrict__ fars) {
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+  const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+  const float rdx = __frcp_rn(dx), rdy = __frcp_rn(dy), rdz = __frcp_rn(dz);
+  float near = fmul(fadd(aabb[0], -ox), rdx), far = fmul(fadd(aabb[3], -ox), rdx);
+  if (near > far) { float c = near; near = far; far = c; }
+  float near_y = fmul(fadd(aabb[1], -oy), rdy), far_y = fmul(fadd(aabb[4], -oy), rdy);
+  if (near_y > far_y) { float c = near_y; near_y = far_y; far_y = c; }
+  const float kMax = 3.402823466e+38f;
+  if (near > far_y || near_y > far) { nears[n] = kMax; fars[n] = kMax; return; }
+  if (near_y > near) near = near_y;
+  if (far_y < far) far = far_y;
+  float near_z = fmul(fadd(aabb[2], -oz), rdz), far_z = fmul(fadd(aabb[5], -oz), rdz);
+  if (near_z > far_z) { float c = near_z; near_z = far_z; far_z = c; }
+  if (near > far_z || near_z > far) { nears[n] = kMax; fars[n] = kMax; return; }
+  if (near_z > near) near = near_z;
+  if (far_z < far) far = far_z;
+  if (near < min_near) near = min_near;
+  nears[n] = near;
+  fars[n] = far;
+}
+
+__global__ void __launch_bounds__(256) k_sph_from_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                      float radius, uint32_t N, float* __restrict__ coords) {
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float RPI = 0.3183098861837907f;
+  const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+  const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+  const float A = dx * dx + dy * dy + dz * dz;
+  const float B = ox * dx + oy * dy + oz * dz;
+  const float Cc = ox * ox + oy * oy + oz * oz - radius * radius;
+  const float t = (-B + sqrtf(B * B - A * Cc)) / A;
+  const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+  const float theta = atan2f(sqrtf(x * x + z * z), y);
+  const float phi = atan2f(z, x);
+  reinterpret_cast<float2*>(coords)[n] = make_float2(2 * theta * RPI - 1, phi * RPI);
+}
+
+__global__ void __launch_bounds__(256) k_morton3D(const int32_t* __restrict__ coords, uint32_t N,
+                                                  int32_t* __restrict__ indices) {
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  indices[n] = (int32_t)morton3D((uint32_t)coords[n * 3], (uint32_t)coords[n * 3 + 1], (uint32_t)coords[n * 3 + 2]);
+}
+
+__global__ void __launch_bounds__(256) k_morton3D_invert(const int32_t* __restrict__ indices, uint32_t N,
+                                                         int32_t* __restrict__ coords) {
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int32_t ind = indices[n];
+  coords[n * 3] = (int32_t)morton3D_invert((uint32_t)(ind >> 0));
+  coords[n * 3 + 1] = (int32_t)morton3D_invert((uint32_t)(ind >> 1));
+  coords[n * 3 + 2] = (int32_t)morton3D_invert((uint32_t)(ind >> 2));
+}
+
+// One thread per output byte: two 16-byte loads in, one byte out; a warp reads 1 KiB contiguous and writes one
+// 32-byte sector.  4.125 B/cell, the algorithmic minimum.
+__global__ void __launch_bounds__(256) k_packbits(const float* __restrict__ grid, uint32_t N, float thresh,
+                                                  uint8_t* __restrict__ bitfield) {
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(grid) + 2 * (size_t)n);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(grid) + 2 * (size_t)n + 1);
+  uint32_t bits = 0;
+  bits |= (a.x > thresh) ? 1u : 0u;
+  bits |= (a.y > thresh) ? 2u : 0u;
+  bits |= (a.z > thresh) ? 4u : 0u;
+  bits |= (a.w > thresh) ? 8u : 0u;
+  bits |= (b.x > thresh) ? 16u : 0u;
+  bits |= (b.y > thresh) ? 32u : 0u;
+  bits |= (b.z > thresh) ? 64u : 0u;
+  bits |= (b.w > thresh) ? 128u : 0u;
+  bitfield[n] = (uint8_t)bits;
+}
+
+// ------------------------------------------------------------------------------------------------ march core
+
+struct MarchParams {
+  float bound, dt_gamma, dt_min, dt_max, rH, half_H, Hm1, Cm1;
+  uint32_t C, H, H3, max_steps;
+};
+
+static int make_march_params(MarchParams* p, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H) {
+  if (C < 1 || C > 8) return SNERF_E_GRID;
+  if (H < 2 || H > 1024 || (H & (H - 1))) return SNERF_E_GRID;
+  if (max_steps == 0) return SNERF_E_BADARG;
+  // host IEEE fp32 arithmetic == the device's (raymarching.cu:345-349); volatile pins single-precision rounding
+  volatile float two_sqrt3 = 2.0f * 1.7320508075688772f;
+  volatile float dt_min = two_sqrt3 / (float)max_steps;
+  volatile float num = two_sqrt3 * (float)(1u << (C - 1));
+  volatile float dt_max = num / (float)H;
+  volatile float rH = 1.0f / (float)H;
+  p->bound = bound; p->dt_gamma = dt_gamma; p->dt_min = dt_min; p->dt_max = dt_max; p->rH = rH;
+  p->half_H = 0.5f * (float)H; p->Hm1 = (float)(H - 1); p->Cm1 = (float)C - 1.0f;
+  p->C = C; p->H = H; p->H3 = H * H * H; p->max_steps = max_steps;
+  return SNERF_OK;
+}
+
+struct Ray {
+  float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz, hsx, hsy, hsz;  // hs* = 0.5*sign(d)
+  __device__ __forceinline__ void load(const float* __restrict__ o, const float* __restrict__ d) {
+    ox = o[0]; oy = o[1]; oz = o[2];
+    dx = d[0]; dy = d[1]; dz = d[2];
+    rdx = __frcp_rn(dx); rdy = __frcp_rn(dy); rdz = __frcp_rn(dz);
+    hsx = copysignf(0.5f, dx); hsy = copysignf(0.5f, dy); hsz = copysignf(0.5f, dz);
+  }
+};
+
+// exponent e of frexpf(|v|) clamped to [0, Cm1]: the cascade level (raymarching.cu:43-55)
+__device__ __forceinline__ int level_from(float v, float Cm1) {
+  const int e = (int)((__float_as_uint(v) >> 23) & 0xffu) - 126;  // zero/denormals give <= -126 -> clamp to 0
+  return (int)fminf(Cm1, fmaxf(0.0f, (float)e));
+}
+
+// One iteration of the reference's while-body (raymarching.cu:360-401).  Returns true if the cell at t is
+// occupied; (x,y,z,dt) is then the sample and the caller does t += dt.  Otherwise t is advanced past the voxel.
+__device__ __forceinline__ bool march_iter(const MarchParams& p, const Ray& r, const uint8_t* __restrict__ grid,
+                                           float& t, float& x, float& y, float& z, float& dt) {
+  x = clampf(ffma(t, r.dx, r.ox), -p.bound, p.bound);
+  y = clampf(ffma(t, r.dy, r.oy), -p.bound, p.bound);
+  z = clampf(ffma(t, r.dz, r.oz), -p.bound, p.bound);
+  dt = clampf(fmul(t, p.dt_gamma), p.dt_min, p.dt_max);
+  const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+  const int level = max(level_from(mx, p.Cm1), level_from(fmul(fmul(dt, (float)p.H), 0.5f), p.Cm1));
+  const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), p.bound);
+  const float mip_rbound = __frcp_rn(mip_bound);
+  // 0.5*(x*rb+1)*H goes through double in the reference; for H a power of two the fp32 product is identical
+  const int nx = (int)clampf(fmul(ffma(x, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);
+  const int ny = (int)clampf(fmul(ffma(y, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);
+  const int nz = (int)clampf(fmul(ffma(z, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);
+  const uint32_t index = (uint32_t)level * p.H3 + morton3D((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+  const bool occ = (__ldg(grid + (index >> 3)) >> (index & 7u)) & 1u;
+  if (occ) return true;
+  const float vx = fmul(fadd(fadd((float)nx, 0.5f), r.hsx), p.rH);
+  const float vy = fmul(fadd(fadd((float)ny, 0.5f), r.hsy), p.rH);
+  const float vz = fmul(fadd(fadd((float)nz, 0.5f), r.hsz), p.rH);
+  const float tx = fmul(ffma(ffma(vx, 2.0f, -1.0f), mip_bound, -x), r.rdx);
+  const float ty = fmul(ffma(ffma(vy, 2.0f, -1.0f), mip_bound, -y), r.rdy);
+  const float tz = fmul(ffma(ffma(vz, 2.0f, -1.0f), mip_bound, -z), r.rdz);
+  const float tt = fadd(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+  do {
+    t = fadd(t, clampf(fmul(t, p.dt_gamma), p.dt_min, p.dt_max));
+  } while (t < tt);
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------------ training march
+//
+// Three launches: count (per-ray sample counts + per-block totals) -> block-offset scan (one block) ->
+// write (re-march; each block rebuilds its rays' offsets with a block scan).  Offsets are therefore the
+// exclusive scan of the counts in ray order: deterministic, unlike raymarching.cu:406-407.
+
+constexpr int kMarchThreads = 128;
+
+__device__ __forceinline__ float ray_t0(const MarchParams& p, float near, float noise) {
+  return ffma(clampf(fmul(near, p.dt_gamma), p.dt_min, p.dt_max), noise, near);  // raymarching.cu:352
+}
+
+// block-wide exclusive scan of one uint32 per thread; returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* smem /*[32]*/, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  const uint32_t incl = warp_incl_sum_u32(v, lane);
+  if (lane == 31) smem[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = lane < nwarp ? smem[lane] : 0u;
+    const uint32_t wi = warp_incl_sum_u32(w, lane);
+    smem[lane] = wi;
+  }
+  __syncthreads();
+  const uint32_t warp_off = warp == 0 ? 0u : smem[warp - 1];
+  *total = smem[nwarp - 1];
+  return warp_off + incl - v;
+}
+
+__global__ void __launch_bounds__(kMarchThreads) k_march_train_count(MarchParams p, const float* __restrict__ rays_o,
+                                                                     const float* __restrict__ rays_d,
+                                                                     const uint8_t* __restrict__ grid, uint32_t N,
+                                                                     const float* __restrict__ nears,
+                                                                     const float* __restrict__ fars,
+                                                                     const float* __restrict__ noises,
+                                                                     uint32_t* __restrict__ counts,
+                                                                     uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t smem[32];
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t num_steps = 0;
+  if (n < N) {
+    Ray r;
+    r.load(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+    const float far = fars[n];
+    float t = ray_t0(p, nears[n], noises[n]);
+    float x, y, z, dt;
+    while (t < far && num_steps < p.max_steps) {
+      if (march_iter(p, r, grid, t, x, y, z, dt)) {
+        num_steps++;
+        t = fadd(t, dt);
+      }
+    }
+    counts[n] = num_steps;
+  }
+  uint32_t total;
+  block_excl_scan(num_steps, smem, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of block_sums in place; counter[0] += total, counter[1] += N
+__global__ void __launch_bounds__(1024) k_march_train_scan(uint32_t* __restrict__ block_sums, uint32_t nblocks,
+                                                           uint32_t N, int32_t* __restrict__ counter) {
+  __shared__ uint32_t smem[32];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nblocks; base += blockDim.x) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nblocks ? block_sums[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_excl_scan(v, smem, &total);
+    if (i < nblocks) block_sums[i] = carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    block_sums[nblocks] = carry;  // total number of samples, read back by the write pass
+    counter[0] += (int32_t)carry;
+    counter[1] += (int32_t)N;
+  }
+}
+
+__device__ __forceinline__ void zero_rows(float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+                                          uint32_t i) {
+  xyzs[(size_t)i * 3] = 0.f; xyzs[(size_t)i * 3 + 1] = 0.f; xyzs[(size_t)i * 3 + 2] = 0.f;
+  dirs[(size_t)i * 3] = 0.f; dirs[(size_t)i * 3 + 1] = 0.f; dirs[(size_t)i * 3 + 2] = 0.f;
+  reinterpret_cast<float2*>(deltas)[i] = make_float2(0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(kMarchThreads) k_march_train_write(
+    MarchParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
+    uint32_t N, uint32_t M, const float* __restrict__ nears, const float* __restrict__ fars,
+    const float* __restrict__ noises, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ block_offsets,
+    float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas, int32_t* __restrict__ rays,
+    int zero_unwritten, int32_t* __restrict__ n_samples_out) {
+  __shared__ uint32_t smem[32];
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n == 0 && n_samples_out) *n_samples_out = (int32_t)block_offsets[gridDim.x];
+  if (zero_unwritten) {  // alignment padding: rows [total, M)
+    const uint32_t total = block_offsets[gridDim.x];
+    for (uint32_t i = total + n; i < M; i += gridDim.x * blockDim.x) zero_rows(xyzs, dirs, deltas, i);
+  }
+  const uint32_t num_steps = n < N ? counts[n] : 0u;
+  uint32_t total;
+  const uint32_t point_index = block_offsets[blockIdx.x] + block_excl_scan(num_steps, smem, &total);
+  if (n >= N) return;
+  rays[n * 3] = (int32_t)n;
+  rays[n * 3 + 1] = (int32_t)point_index;
+  rays[n * 3 + 2] = (int32_t)num_steps;
+  if (num_steps == 0) return;
+  if (point_index + num_steps > M) {  // raymarching.cu:417: overflowing rays are dropped
+    if (zero_unwritten)
+      for (uint32_t i = point_index; i < M && i < point_index + num_steps; i++) zero_rows(xyzs, dirs, deltas, i);
+    return;
+  }
+
+  Ray r;
+  r.load(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+  const float far = fars[n];
+  float t = ray_t0(p, nears[n], noises[n]);
+  float last_t = t;
+  float* px = xyzs + (size_t)point_index * 3;
+  float* pd = dirs + (size_t)point_index * 3;
+  float2* pl = reinterpret_cast<float2*>(deltas) + point_index;
+  uint32_t step = 0;
+  float x, y, z, dt;
+  while (t < far && step < num_steps) {
+    if (march_iter(p, r, grid, t, x, y, z, dt)) {
+      px[0] = x; px[1] = y; px[2] = z;
+      pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+      t = fadd(t, dt);
+      *pl = make_float2(dt, fadd(t, -last_t));
+      last_t = t;
+      px += 3; pd += 3; pl += 1;
+      step++;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ inference march
+
+__global__ void __launch_bounds__(kMarchThreads) k_march_rays(MarchParams p, uint32_t n_alive, uint32_t n_step,
+                                                              const int32_t* __restrict__ rays_alive,
+                                                              const float* __restrict__ rays_t,
+                                                              const float* __restrict__ rays_o,
+                                                              const float* __restrict__ rays_d,
+                                                              const uint8_t* __restrict__ grid,
+                                                              const float* __restrict__ fars, float* __restrict__ xyzs,
+                                                              float* __restrict__ dirs, float* __restrict__ deltas,
+                                                              const float* __restrict__ noises, uint32_t n_rows) {
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  // n_rows != 0: the caller's buffers are uninitialised; zero the padding rows [n_alive*n_step, n_rows)
+  for (uint32_t i = n_alive * n_step + n; i < n_rows; i += gridDim.x * blockDim.x) zero_rows(xyzs, dirs, deltas, i);
+  if (n >= n_alive) return;
+  const int index = rays_alive[n];
+  Ray r;
+  r.load(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
+  float* px = xyzs + (size_t)n * n_step * 3;
+  float* pd = dirs + (size_t)n * n_step * 3;
+  float2* pl = reinterpret_cast<float2*>(deltas) + (size_t)n * n_step;
+  const float far = fars[index];
+  float t = ray_t0(p, rays_t[index], noises ? noises[n] : 0.0f);  // raymarching.cu:776
+  float last_t = t;
+  uint32_t step = 0;
+  float x, y, z, dt;
+  while (t < far && step < n_step) {
+    if (march_iter(p, r, grid, t, x, y, z, dt)) {
+      px[0] = x; px[1] = y; px[2] = z;
+      pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+      t = fadd(t, dt);
+      *pl = make_float2(dt, fadd(t, -last_t));
+      last_t = t;
+      px += 3; pd += 3; pl += 1;
+      step++;
+    }
+  }
+  if (n_rows)  // zero terminators for the unused slots of this ray (delta == 0 ends it, raymarching.cu:885)
+    for (; step < n_step; step++) zero_rows(xyzs, dirs, deltas, n * n_step + step);
+}
+
+// ------------------------------------------------------------------------------------------------ compaction
+//
+// Stable stream compaction of ids >= 0 (nerf/renderer.py:158).  Block-level ballot/popc scan + a single-block
+// scan of the per-block totals; two launches for any n, no host sync: the new length is written to *n_out.
+
+constexpr int kCompactThreads = 256;
+
+__global__ void __launch_bounds__(kCompactThreads) k_compact_count(const int32_t* __restrict__ in, uint32_t n,
+                                                                   uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t smem[32];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t keep = (i < n && in[i] >= 0) ? 1u : 0u;
+  uint32_t total;
+  block_excl_scan(keep, smem, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_compact_scan(uint32_t* __restrict__ block_sums, uint32_t nblocks,
+                                                       int32_t* __restrict__ n_out) {
+  __shared__ uint32_t smem[32];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nblocks; base += blockDim.x) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nblocks ? block_sums[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_excl_scan(v, smem, &total);
+    if (i < nblocks) block_sums[i] = carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_out = (int32_t)carry;
+}
+
+__global__ void __launch_bounds__(kCompactThreads) k_compact_write(const int32_t* __restrict__ in, uint32_t n,
+                                                                   const uint32_t* __restrict__ block_offsets,
+                                                                   int32_t* __restrict__ out) {
+  __shared__ uint32_t smem[32];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t v = i < n ? in[i] : -1;
+  const uint32_t keep = v >= 0 ? 1u : 0u;
+  uint32_t total;
+  const uint32_t pos = block_offsets[blockIdx.x] + block_excl_scan(keep, smem, &total);
+  if (keep) out[pos] = v;
+}
+
+}  // namespace snerf
+
+using namespace snerf;
+
+// ------------------------------------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+int snerf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
+                             float* nears, float* fars, snerf_stream_t stream) {
+  if (N == 0) return SNERF_OK;
+  if (!rays_o || !rays_d || !aabb || !nears || !fars) return SNERF_E_BADARG;
+  k_near_far_from_aabb<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+  return finish_launch();
+}
+
+int snerf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                       snerf_stream_t stream) {
+  if (N == 0) return SNERF_OK;
+  if (!rays_o || !rays_d || !coords) return SNERF_E_BADARG;
+  k_sph_from_ray<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, radius, N, coords);
+  return finish_launch();
+}
+
+int snerf_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, snerf_stream_t stream) {
+  if (N == 0) return SNERF_OK;
+  if (!coords || !indices) return SNERF_E_BADARG;
+  k_morton3D<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(coords, N, indices);
+  return finish_launch();
+}
+
+int snerf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, snerf_stream_t stream) {
+  if (N == 0) return SNERF_OK;
+  if (!coords || !indices) return SNERF_E_BADARG;
+  k_morton3D_invert<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(indices, N, coords);
+  return finish_launch();
+}
+
+int snerf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, snerf_stream_t stream) {
+  if (N == 0) return SNERF_OK;
+  if (!grid || !bitfield) return SNERF_E_BADARG;
+  if ((uintptr_t)grid & 15u) return SNERF_E_BADARG;  // float4 loads
+  k_packbits<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(grid, N, density_thresh, bitfield);
+  return finish_launch();
+}
+
+size_t snerf_march_rays_train_workspace_bytes(uint32_t N) {
+  const size_t nblocks = div_up(N ? N : 1, kMarchThreads);
+  return align_up((size_t)(N ? N : 1) * sizeof(uint32_t), 256) + align_up((nblocks + 1) * sizeof(uint32_t), 256);
+}
+
+static uint32_t* ws_block_sums(void* workspace, uint32_t N) {
+  return (uint32_t*)((char*)workspace + align_up((size_t)N * sizeof(uint32_t), 256));
+}
+
+int snerf_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                 const float* nears, const float* fars, int32_t* counter, const float* noises,
+                                 void* workspace, size_t workspace_bytes, snerf_stream_t stream) {
+  if (N == 0) return SNERF_OK;
+  if (!rays_o || !rays_d || !grid || !nears || !fars || !counter || !noises || !workspace) return SNERF_E_BADARG;
+  if (workspace_bytes < snerf_march_rays_train_workspace_bytes(N)) return SNERF_E_WORKSPACE;
+  MarchParams p;
+  if (int e = make_march_params(&p, bound, dt_gamma, max_steps, C, H)) return e;
+  uint32_t* counts = (uint32_t*)workspace;
+  uint32_t* block_sums = ws_block_sums(workspace, N);
+  const uint32_t nblocks = div_up(N, kMarchThreads);
+  cudaStream_t s = (cudaStream_t)stream;
+  k_march_train_count<<<nblocks, kMarchThreads, 0, s>>>(p, rays_o, rays_d, grid, N, nears, fars, noises, counts, block_sums);
+  k_march_train_scan<<<1, 1024, 0, s>>>(block_sums, nblocks, N, counter);
+  return finish_launch(2);
+}
+
+int snerf_march_rays_train_write(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                 const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                                 int32_t* rays, const float* noises, int zero_unwritten, int32_t* n_samples_out,
+                                 void* workspace, size_t workspace_bytes, snerf_stream_t stream) {
+  if (N == 0) return SNERF_OK;
+  if (!rays_o || !rays_d || !grid || !nears || !fars || !rays || !noises || !workspace) return SNERF_E_BADARG;
+  if (M > 0 && (!xyzs || !dirs || !deltas)) return SNERF_E_BADARG;
+  if (workspace_bytes < snerf_march_rays_train_workspace_bytes(N)) return SNERF_E_WORKSPACE;
+  if ((uintptr_t)deltas & 7u) return SNERF_E_BADARG;
+  MarchParams p;
+  if (int e = make_march_params(&p, bound, dt_gamma, max_steps, C, H)) return e;
+  const uint32_t nblocks = div_up(N, kMarchThreads);
+  k_march_train_write<<<nblocks, kMarchThreads, 0, (cudaStream_t)stream>>>(
+      p, rays_o, rays_d, grid, N, M, nears, fars, noises, (const uint32_t*)workspace, ws_block_sums(workspace, N), xyzs,
+      dirs, deltas, rays, zero_unwritten, n_samples_out);
+  return finish_launch();
+}
+
+int snerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                           uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                           const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
+                           const float* noises, void* workspace, size_t workspace_bytes, snerf_stream_t stream) {
+  if (int e = snerf_march_rays_train_count(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
+                                           counter, noises, workspace, workspace_bytes, stream))
+    return e;
+  return snerf_march_rays_train_write(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs,
+                                      dirs, deltas, rays, noises, 0, nullptr, workspace, workspace_bytes, stream);
+}
+
+int snerf_march_rays_ex(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                        const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                        uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
+                        float* dirs, float* deltas, const float* noises, uint32_t n_rows, snerf_stream_t stream) {
+  (void)nears;  // read by the reference kernel but never used (raymarching.cu:768)
+  if (n_alive == 0 || n_step == 0) return SNERF_OK;
+  if (!rays_alive || !rays_t || !rays_o || !rays_d || !grid || !fars || !xyzs || !dirs || !deltas) return SNERF_E_BADARG;
+  if ((uintptr_t)deltas & 7u) return SNERF_E_BADARG;
+  if (n_rows != 0 && n_rows < n_alive * n_step) return SNERF_E_BADARG;
+  MarchParams p;
+  if (int e = make_march_params(&p, bound, dt_gamma, max_steps, C, H)) return e;
+  k_march_rays<<<div_up(n_alive, kMarchThreads), kMarchThreads, 0, (cudaStream_t)stream>>>(
+      p, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, grid, fars, xyzs, dirs, deltas, noises, n_rows);
+  return finish_launch();
+}
+
+int snerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                     const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
+                     uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs, float* dirs,
+                     float* deltas, const float* noises, snerf_stream_t stream) {
+  return snerf_march_rays_ex(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
+                             nears, fars, xyzs, dirs, deltas, noises, 0, stream);
+}
+
+size_t snerf_compact_rays_workspace_bytes(uint32_t n_alive) {
+  return align_up((size_t)div_up(n_alive ? n_alive : 1, kCompactThreads) * sizeof(uint32_t), 256);
+}
+
+int snerf_compact_rays(const int32_t* rays_alive_in, uint32_t n_alive, int32_t* rays_alive_out, int32_t* n_out,
+                       void* workspace, size_t workspace_bytes, snerf_stream_t stream) {
+  if (!n_out) return SNERF_E_BADARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_alive == 0) {
+    cudaError_t e = cudaMemsetAsync(n_out, 0, sizeof(int32_t), s);
+    return e == cudaSuccess ? SNERF_OK : (int)e;
+  }
+  if (!rays_alive_in || !rays_alive_out || !workspace || rays_alive_in == rays_alive_out) return SNERF_E_BADARG;
+  if (workspace_bytes < snerf_compact_rays_workspace_bytes(n_alive)) return SNERF_E_WORKSPACE;
+  uint32_t* block_sums = (uint32_t*)workspace;
+  const uint32_t nblocks = div_up(n_alive, kCompactThreads);
+  k_compact_count<<<nblocks, kCompactThreads, 0, s>>>(rays_alive_in, n_alive, block_sums);
+  k_compact_scan<<<1, 1024, 0, s>>>(block_sums, nblocks, n_out);
+  k_compact_write<<<nblocks, kCompactThreads, 0, s>>>(rays_alive_in, n_alive, block_sums, rays_alive_out);
+  return finish_launch(3);
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+"""``NeRFRenderer`` with the reference's interface (nerf/renderer.py:8-334), driving libsnerf_b200 kernels.
+
+Same constructor arguments, buffers (``aabb_train``, ``aabb_infer``, ``density_grid``, ``density_bitfield``,
+``step_counter``), python-side state (``mean_density``, ``iter_density``, ``mean_count``, ``local_step``) and
+methods (``render``, ``run_cuda``, ``update_extra_state``, ``mark_untrained_grid``, ``reset_extra_state``), so a
+reference ``state_dict`` of these buffers loads unchanged.
+
+Differences that do not change results:
+* the occupancy sweep enumerates cells directly in Morton order (``morton3D_invert(arange)``) and writes the grid
+  contiguously, instead of building xyz meshgrids and scattering through ``morton3D`` indices;
+* the inference loop compacts the alive list on the device (``compact_rays``) and reads one int per iteration instead
+  of running ``rays_alive[rays_alive >= 0]`` (a nonzero + gather + sync);
+* the module does not force ``.cuda()`` in the constructor (nerf/renderer.py:30); buffers move with ``.to(device)``.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import raymarching
+
+
+class NeRFRenderer(nn.Module):
+    def __init__(self, bound=1, channel_dim=3, density_scale=1, min_near=0.2, density_thresh=0.01, bg_radius=-1):
+        super().__init__()
+        self.channel_dim = channel_dim
+        self.bound = bound
+        self.cascade = 1 + math.ceil(math.log2(bound))
+        self.grid_size = 128
+        self.density_scale = density_scale
+        self.min_near = min_near
+        self.density_thresh = density_thresh
+        self.bg_radius = bg_radius
+
+        aabb = torch.tensor([-bound, -bound, -bound, bound, bound, bound], dtype=torch.float32)
+        self.register_buffer('aabb_train', aabb)
+        self.register_buffer('aabb_infer', aabb.clone())
+        cells = self.cascade * self.grid_size ** 3
+        self.register_buffer('density_grid', torch.zeros(self.cascade, self.grid_size ** 3, dtype=torch.float32))
+        self.register_buffer('density_bitfield', torch.zeros(cells // 8, dtype=torch.uint8))
+        self.register_buffer('step_counter', torch.zeros(16, 2, dtype=torch.int32))  # 16 steps of history
+        self.mean_density = 0
+        self.iter_density = 0
+        self.mean_count = 0
+        self.local_step = 0
+        self.error_map = None
+
+    # ---- subclass interface (nerf/renderer.py:50-58)
+    def forward(self, x, d):
+        raise NotImplementedError()
+
+    def density(self, x):
+        raise NotImplementedError()
+
+    def color(self, x, d, mask=None, **kwargs):
+        raise NotImplementedError()
+
+    def reset_extra_state(self):
+        self.density_grid.zero_()
+        self.mean_density = 0
+        self.iter_density = 0
+        self.step_counter.zero_()
+        self.mean_count = 0
+        self.local_step = 0
+
+    # ---- rendering
+    def _finish(self, image, depth, weights_sum, nears, fars, bg_color, prefix):
+        # background blend and depth normalisation (nerf/renderer.py:111-114, :164-167)
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+        return image.view(*prefix, self.channel_dim), depth.view(*prefix)
+
+    def run_cuda(self, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False, max_steps=1024,
+                 T_thresh=1e-4, **kwargs):
+        """rays_o, rays_d [B,N,3] -> {'image' [B,N,C], 'depth' [B,N], 'weights_sum' [B*N] (training only)}."""
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        N = rays_o.shape[0]
+        device = rays_o.device
+
+        aabb = self.aabb_train if self.training else self.aabb_infer
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, aabb, self.min_near)
+
+        if self.bg_radius > 0:
+            # the reference calls an undefined self.background here (nerf/renderer.py:88)
+            raise NotImplementedError("bg_radius > 0 is a dead path in the reference (no background model exists)")
+        if bg_color is None:
+            bg_color = 1
+
+        results = {}
+        if self.training:
+            counter = self.step_counter[self.local_step % 16]
+            counter.zero_()
+            self.local_step += 1
+            xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+                rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
+                self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps)
+            sigmas, rgbs = self(xyzs, dirs)
+            sigmas = self.density_scale * sigmas
+            weights_sum, depth, image = raymarching.composite_rays_train(
+                sigmas.to(torch.float32), rgbs.to(torch.float32), deltas, rays, T_thresh, self.channel_dim)
+            results['weights_sum'] = weights_sum
+        else:
+            weights_sum = torch.zeros(N, dtype=torch.float32, device=device)
+            depth = torch.zeros(N, dtype=torch.float32, device=device)
+            image = torch.zeros(N, self.channel_dim, dtype=torch.float32, device=device)
+            rays_alive = torch.arange(N, dtype=torch.int32, device=device)
+            spare = torch.empty_like(rays_alive)
+            count = torch.empty(1, dtype=torch.int32, device=device)
+            rays_t = nears.clone()
+            n_alive, step = N, 0
+            while step < max_steps and n_alive > 0:
+                n_step = max(min(N // n_alive, 8), 1)
+                xyzs, dirs, deltas = raymarching.march_rays(
+                    n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound, self.density_bitfield, self.cascade,
+                    self.grid_size, nears, fars, 128, perturb if step == 0 else False, dt_gamma, max_steps)
+                sigmas, rgbs = self(xyzs, dirs)
+                sigmas = self.density_scale * sigmas
+                raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth,
+                                           image, T_thresh, self.channel_dim)
+                spare, count = raymarching.compact_rays(rays_alive, n_alive, out=spare, count=count)
+                rays_alive, spare = spare, rays_alive
+                n_alive = int(count.item())
+                step += n_step
+
+        image, depth = self._finish(image, depth, weights_sum, nears, fars, bg_color, prefix)
+        results['depth'] = depth
+        results['image'] = image
+        return results
+
+    def render(self, rays_o, rays_d, **kwargs):
+        return self.run_cuda(rays_o, rays_d, **kwargs)
+
+    # ---- occupancy grid maintenance
+    def _cell_coords(self, indices):
+        """int32 [n,3] grid coordinates of Morton indices."""
+        return raymarching.morton3D_invert(indices.to(torch.int32))
+
+    def _cell_centres(self, coords):
+        """cell coordinates -> [-1,1] positions (nerf/renderer.py:259)."""
+        return 2 * coords.float() / (self.grid_size - 1) - 1
+
+    @torch.no_grad()
+    def mark_untrained_grid(self, poses, intrinsic, S=64):
+        """Cells no camera sees get density -1 (nerf/renderer.py:174-234).  poses [B,4,4] cam2world; intrinsic
+        (fx, fy, cx, cy)."""
+        if isinstance(poses, np.ndarray):
+            poses = torch.from_numpy(poses)
+        device = self.density_grid.device
+        poses = poses.to(device=device, dtype=torch.float32)
+        B = poses.shape[0]
+        fx, fy, cx, cy = intrinsic
+        H3 = self.grid_size ** 3
+        count = torch.zeros_like(self.density_grid)
+        chunk = 64 ** 3
+        for start in range(0, H3, chunk):
+            idx = torch.arange(start, min(start + chunk, H3), dtype=torch.int32, device=device)
+            world = self._cell_centres(self._cell_coords(idx)).unsqueeze(0)  # [1,n,3]
+            for cas in range(self.cascade):
+                bound = min(2 ** cas, self.bound)
+                half = bound / self.grid_size
+                cas_world = world * (bound - half)
+                seen = torch.zeros(idx.shape[0], dtype=torch.float32, device=device)
+                for head in range(0, B, S):
+                    R = poses[head:head + S, :3, :3]
+                    cam = (cas_world - poses[head:head + S, :3, 3].unsqueeze(1)) @ R  # world -> camera
+                    z = cam[:, :, 2]
+                    vis = (z > 0) & (cam[:, :, 0].abs() < cx / fx * z + half * 2) & (cam[:, :, 1].abs() < cy / fy * z + half * 2)
+                    seen += vis.sum(0)
+                count[cas, start:start + idx.shape[0]] += seen
+        self.density_grid[count == 0] = -1
+        print(f'[mark untrained grid] {(count == 0).sum()} from {H3 * self.cascade}')
+
+    def _query_sigma(self, cas_xyzs):
+        return self.density(cas_xyzs)['sigma'].reshape(-1).detach().to(torch.float32) * self.density_scale
+
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128):
+        """EMA update of the occupancy grid + bitfield + running sample-count estimate (nerf/renderer.py:236-327)."""
+        device = self.density_grid.device
+        H3 = self.grid_size ** 3
+        tmp_grid = -torch.ones_like(self.density_grid)
+
+        def jittered(coords, cas):
+            bound = min(2 ** cas, self.bound)
+            half = bound / self.grid_size
+            xyzs = self._cell_centres(coords) * (bound - half)
+            return xyzs + (torch.rand_like(xyzs) * 2 - 1) * half
+
+        if self.iter_density < 16:  # full sweep
+            chunk = max(int(S), 1) ** 3
+            for start in range(0, H3, chunk):
+                idx = torch.arange(start, min(start + chunk, H3), dtype=torch.int32, device=device)
+                coords = self._cell_coords(idx)
+                for cas in range(self.cascade):
+                    tmp_grid[cas, start:start + idx.shape[0]] = self._query_sigma(jittered(coords, cas))
+        else:  # partial update: H^3/4 uniform cells + H^3/4 occupied cells per cascade
+            n = H3 // 4
+            for cas in range(self.cascade):
+                coords = torch.randint(0, self.grid_size, (n, 3), device=device)
+                indices = raymarching.morton3D(coords).long()
+                occ = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
+                if occ.shape[0] > 0:
+                    occ = occ[torch.randint(0, occ.shape[0], [n], dtype=torch.long, device=device)]
+                    indices = torch.cat([indices, occ], dim=0)
+                    coords = torch.cat([coords.int(), self._cell_coords(occ)], dim=0)
+                tmp_grid[cas, indices] = self._query_sigma(jittered(coords, cas))
+
+        valid = (self.density_grid >= 0) & (tmp_grid >= 0)
+        self.density_grid[valid] = torch.maximum(self.density_grid[valid] * decay, tmp_grid[valid])
+        self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()
+        self.iter_density += 1
+
+        density_thresh = min(self.mean_density, self.density_thresh)
+        self.density_bitfield = raymarching.packbits(self.density_grid, density_thresh, self.density_bitfield)
+
+        total_step = min(16, self.local_step)
+        if total_step > 0:
+            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        self.local_step = 0

@@ -1,0 +1,205 @@
+"""GPU parity of the field: hash-grid encode fwd/bwd, SH-4, sigma/colour MLP fwd/bwd
+against the CPU oracle.  tiny-cuda-nn is not available (un-vendored dependency of the reference), so the oracle is
+this repo's restatement: PARITY UNPINNED against the reference itself.
+
+Bars: fp32 path 1e-4 relative (north_star); bf16 tcgen05 path 2e-2 relative against the fp32 oracle and 2e-3 against
+the oracle run with bf16 rounding emulation (same rounding points, different accumulation order)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def dev_t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from oracle import oracle as orc
+    from stable_nerf_b200 import synthetic as syn
+    from stable_nerf_b200.config import BaseNeRFConfig
+    from stable_nerf_b200.field import make_field_desc, mlp_layer_shapes
+    out = {}
+    for C in (3, 4):
+        f = make_field_desc(BaseNeRFConfig().as_dict(), C, 15, 1.0)
+        ws, table, wc = syn.field_params(38912, f.grid.n_entries * 2, 55296, shapes_sigma=mlp_layer_shapes(32, 128, 3),
+                                         shapes_color=mlp_layer_shapes(32, 128, 4), table_scale=1.0, seed=1337 + C)
+        out[C] = (f, orc.copy_desc(f, orc.FieldDesc), ws, table, wc)
+    return out
+
+
+def sample_points(M, seed=0):
+    """march-like inputs: runs of nearby points along rays + a few exact corner cases (0, 1, cell boundaries)."""
+    rng = np.random.default_rng(seed)
+    n_rays = max(M // 64, 1)
+    o = rng.uniform(-0.9, 0.9, (n_rays, 3))
+    d = rng.standard_normal((n_rays, 3))
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    t = np.arange(64)[None, :, None] * 0.0034
+    x = np.clip(o[:, None] + t * d[:, None], -1, 1).reshape(-1, 3)[:M]
+    if x.shape[0] < M:
+        x = np.concatenate([x, rng.uniform(-1, 1, (M - x.shape[0], 3))])
+    dirs = np.repeat(d, 64, axis=0)[:M]
+    if dirs.shape[0] < M:
+        dirs = np.concatenate([dirs, np.tile(d[:1], (M - dirs.shape[0], 1))])
+    x = x.astype(np.float32)
+    x[0] = (-1, -1, -1)
+    x[1] = (1, 1, 1)
+    x[2] = (0, 0, 0)
+    x[3] = (1, -1, 0.5)
+    return x, dirs.astype(np.float32)
+
+
+@pytest.mark.parametrize("M", [1, 127, 128, 129, 5000])
+def test_hashgrid_forward_backward(M, setup, built_lib, cuda):
+    from oracle import oracle as orc
+    from stable_nerf_b200 import _lib
+    from stable_nerf_b200._lib import check, ptr, stream
+    lib = _lib.load()
+    f, of, ws, table, wc = setup[3]
+    x, _ = sample_points(M, seed=M)
+    x01 = ((x + 1) / 2).astype(np.float32)
+    enc_o = orc.hashgrid_forward(of.grid, x01, table)
+    t_x, t_tab = dev_t(x01, cuda), dev_t(table, cuda)
+    enc = torch.empty(M, 32, device=cuda)
+    check(lib.snerf_hashgrid_forward(f.grid, ptr(t_x), ptr(t_tab), M, ptr(enc), stream()), "enc fwd")
+    assert rel_err(enc.cpu().numpy(), enc_o) <= 1e-6, "hash-grid encode forward"
+    assert np.array_equal(enc.cpu().numpy(), enc_o), "encode forward is bit-identical to the oracle"
+    rng = np.random.default_rng(M)
+    g = rng.standard_normal((M, 32)).astype(np.float32)
+    gt_o = orc.hashgrid_backward(of.grid, x01, g)
+    gt = torch.zeros(f.grid.n_entries * 2, device=cuda)
+    check(lib.snerf_hashgrid_backward(f.grid, ptr(t_x), ptr(dev_t(g, cuda)), M, ptr(gt), stream()), "enc bwd")
+    assert rel_err(gt.cpu().numpy(), gt_o) <= 1e-4, "hash-grid scatter-add backward"
+    # linearity: backward of 2g is 2x
+    gt2 = torch.zeros_like(gt)
+    check(lib.snerf_hashgrid_backward(f.grid, ptr(t_x), ptr(dev_t(2 * g, cuda)), M, ptr(gt2), stream()), "enc bwd")
+    assert rel_err(gt2.cpu().numpy(), 2 * gt.cpu().numpy()) <= 1e-5
+
+
+def test_sh4_and_trunc_exp(built_lib, cuda):
+    from oracle import oracle as orc
+    from stable_nerf_b200 import trunc_exp
+    from stable_nerf_b200.field import DirEncoder
+    rng = np.random.default_rng(1)
+    d = rng.standard_normal((1000, 3))
+    d = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
+    d01 = ((d + 1) / 2).astype(np.float32)
+    sh = DirEncoder().to(cuda)(dev_t(d01, cuda))
+    assert rel_err(sh.cpu().numpy(), orc.sh4_forward(d01)) <= 1e-6
+    x = np.linspace(-20, 20, 999).astype(np.float32)
+    tx = dev_t(x, cuda).requires_grad_(True)
+    y = trunc_exp(tx)
+    assert rel_err(y.detach().cpu().numpy(), orc.trunc_exp_forward(x)) <= 1e-6
+    g = rng.standard_normal(999).astype(np.float32)
+    y.backward(dev_t(g, cuda))
+    assert rel_err(tx.grad.cpu().numpy(), orc.trunc_exp_backward(g, x)) <= 1e-6
+
+
+def run_cuda_field(f, x, dirs, ws, table, wc, precision, g_sig=None, g_rgb=None, dev=None):
+    from stable_nerf_b200 import _lib
+    from stable_nerf_b200._lib import check, ptr, stream
+    lib = _lib.load()
+    M = x.shape[0]
+    t = dict(x=dev_t(x, dev), d=dev_t(dirs, dev), ws=dev_t(ws, dev), tab=dev_t(table, dev), wc=dev_t(wc, dev))
+    sig = torch.empty(M, device=dev)
+    rgb = torch.empty(M, f.channel_dim, device=dev)
+    nb = lib.snerf_field_workspace_bytes(f, M, precision, 1)
+    wsb = torch.empty(max(nb, 256), dtype=torch.uint8, device=dev)
+    check(lib.snerf_field_forward(f, ptr(t["x"]), ptr(t["d"]), M, ptr(t["tab"]), ptr(t["ws"]), ptr(t["wc"]), precision,
+                                  ptr(sig), ptr(rgb), ptr(wsb), nb, stream()), "field fwd")
+    grads = None
+    if g_sig is not None:
+        gt = torch.zeros_like(t["tab"])
+        gws = torch.zeros_like(t["ws"])
+        gwc = torch.zeros_like(t["wc"])
+        check(lib.snerf_field_backward(f, ptr(t["x"]), ptr(t["d"]), M, ptr(t["tab"]), ptr(t["ws"]), ptr(t["wc"]),
+                                       ptr(dev_t(g_sig, dev)), ptr(dev_t(g_rgb, dev)), precision, ptr(gt), ptr(gws),
+                                       ptr(gwc), ptr(wsb), nb, stream()), "field bwd")
+        grads = (gt.cpu().numpy(), gws.cpu().numpy(), gwc.cpu().numpy())
+    torch.cuda.synchronize()
+    return sig.cpu().numpy(), rgb.cpu().numpy(), grads
+
+
+@pytest.mark.parametrize("C,M", [(3, 1), (3, 200), (4, 1000), (3, 4133)])
+def test_field_fp32_forward_backward(C, M, setup, built_lib, cuda):
+    from oracle import oracle as orc
+    f, of, ws, table, wc = setup[C]
+    x, dirs = sample_points(M, seed=C * 1000 + M)
+    rng = np.random.default_rng(M)
+    g_sig = rng.standard_normal(M).astype(np.float32)
+    g_rgb = rng.standard_normal((M, C)).astype(np.float32)
+    g_sig[M // 2:] = 0  # terminated samples carry exact zero gradients
+    g_rgb[M // 2:] = 0
+    sig_o, rgb_o = orc.field_forward(of, x, dirs, table, ws, wc)
+    gt_o, gws_o, gwc_o = orc.field_backward(of, x, dirs, table, ws, wc, g_sig, g_rgb)
+    sig, rgb, (gt, gws, gwc) = run_cuda_field(f, x, dirs, ws, table, wc, 0, g_sig, g_rgb, cuda)
+    assert rel_err(sig, sig_o) <= 1e-4, "sigma"
+    assert rel_err(rgb, rgb_o) <= 1e-4, "rgb"
+    assert rel_err(gws, gws_o) <= 1e-4, "grad w_sigma"
+    assert rel_err(gwc, gwc_o) <= 1e-4, "grad w_color"
+    assert rel_err(gt, gt_o) <= 1e-4, "grad table"
+
+
+@pytest.mark.parametrize("C,M", [(3, 1), (3, 300), (4, 2500), (3, 70001)])
+def test_field_bf16_forward_backward(C, M, setup, built_lib, cuda):
+    from oracle import oracle as orc
+    f, of, ws, table, wc = setup[C]
+    x, dirs = sample_points(M, seed=C * 77 + M)
+    rng = np.random.default_rng(M)
+    g_sig = rng.standard_normal(M).astype(np.float32)
+    g_rgb = rng.standard_normal((M, C)).astype(np.float32)
+    g_sig[M // 2:] = 0
+    g_rgb[M // 2:] = 0
+    try:
+        sig, rgb, (gt, gws, gwc) = run_cuda_field(f, x, dirs, ws, table, wc, 1, g_sig, g_rgb, cuda)
+    except RuntimeError as e:
+        if "not supported" in str(e):
+            pytest.skip("tcgen05 path not built in this revision")
+        raise
+    Mo = min(M, 6000)  # the scalar oracle is slow; compare a prefix for the big case (grads only when M is small)
+    sig_e, rgb_e = orc.field_forward(of, x[:Mo], dirs[:Mo], table, ws, wc, emulate_bf16=True)
+    sig_o, rgb_o = orc.field_forward(of, x[:Mo], dirs[:Mo], table, ws, wc)
+    assert rel_err(sig[:Mo], sig_e) <= 2e-3 and rel_err(rgb[:Mo], rgb_e) <= 2e-3, "vs bf16-emulating oracle"
+    assert rel_err(sig[:Mo], sig_o) <= 2e-2 and rel_err(rgb[:Mo], rgb_o) <= 2e-2, "vs fp32 oracle (stated bf16 tolerance)"
+    if M <= 6000:
+        gt_e, gws_e, gwc_e = orc.field_backward(of, x, dirs, table, ws, wc, g_sig, g_rgb, emulate_bf16=True)
+        gt_o, gws_o, gwc_o = orc.field_backward(of, x, dirs, table, ws, wc, g_sig, g_rgb)
+        for name, a, e, o in (("w_sigma", gws, gws_e, gws_o), ("w_color", gwc, gwc_e, gwc_o), ("table", gt, gt_e, gt_o)):
+            assert rel_err(a, e) <= 5e-3, f"grad {name} vs bf16-emulating oracle"
+            assert rel_err(a, o) <= 3e-2, f"grad {name} vs fp32 oracle (stated bf16 tolerance)"
+
+
+def test_network_module_autograd(setup, built_lib, cuda):
+    """NeRFNetwork.forward/density through torch autograd (nerf/network.py:39-76 surface)."""
+    from oracle import oracle as orc
+    from stable_nerf_b200 import NeRFNetwork
+    model = NeRFNetwork(channel_dim=4, precision="fp32").to(cuda)
+    with torch.no_grad():
+        model.sigma_net.params[model.sigma_net.n_mlp:] *= 1e4
+    x, dirs = sample_points(777, seed=3)
+    sigma, color = model(dev_t(x, cuda), dev_t(dirs, cuda))
+    assert sigma.shape == (777,) and color.shape == (777, 4) and sigma.dtype == torch.float32
+    of = orc.copy_desc(model.fdesc, orc.FieldDesc)
+    sp, cp = model.sigma_net.params.detach().cpu().numpy(), model.color_net.params.detach().cpu().numpy()
+    nm = model.sigma_net.n_mlp
+    sig_o, rgb_o, geo_o = orc.field_forward(of, x, dirs, sp[nm:], sp[:nm], cp, want_geo=True)
+    assert rel_err(sigma.detach().cpu().numpy(), sig_o) <= 1e-4 and rel_err(color.detach().cpu().numpy(), rgb_o) <= 1e-4
+    den = model.density(dev_t(x, cuda))
+    assert rel_err(den["sigma"].cpu().numpy(), sig_o) <= 1e-4 and rel_err(den["geo_feat"].cpu().numpy(), geo_o) <= 1e-4
+    (sigma.sum() + (color ** 2).sum()).backward()
+    gt, gws, gwc = orc.field_backward(of, x, dirs, sp[nm:], sp[:nm], cp, np.ones(777, np.float32),
+                                      2 * color.detach().cpu().numpy())
+    gp = model.sigma_net.params.grad.cpu().numpy()
+    assert rel_err(gp[:nm], gws) <= 1e-4 and rel_err(gp[nm:], gt) <= 1e-4
+    assert rel_err(model.color_net.params.grad.cpu().numpy(), gwc) <= 1e-4
+    names = [n for n, _ in model.named_parameters()]
+    assert names == ["sigma_net.params", "encoder_dir.params", "color_net.params"]
+    assert len(model.get_params(1e-3)) == 3
