@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path: train rays/s (fwd+bwd) on the cfg2 workload of BASELINE.json
+("Blender-shaped synthetic scene 800x800, hash-grid + cuda_ray occupancy marching, 4096-ray train step on 1 B200").
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                      (CPU arm: the oracle port timed on the host cores)
+
+A step = near/far -> occupancy march -> hash-grid encode + sigma/colour MLP -> alpha compositing -> L1 loss ->
+backward of all of it (composite bwd, MLP dgrad/wgrad, hash-grid scatter-add) [-> NCCL all-reduce of the gradients
+when N>1].  Weak scaling: every rank marches its own 4096-ray shard.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAYS_PER_GPU = 4096
+MAX_STEPS = 1024
+CHANNELS = 3
+TABLE_SCALE = 1e4  # hash table U(-1e-4,1e-4) * 1e4: non-degenerate densities
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]), tf_sust=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 8 and r[4 + k].lower().startswith("active") for r in self.rows)]
+        busy = [x for x in sm if x >= 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def workload(n_rays, seed):
+    from stable_nerf_b200 import synthetic as syn
+    grid = syn.occupancy_grid(lego_like=True, seed=0)
+    bitfield = syn.pack_bitfield(grid)
+    rays_o, rays_d = syn.train_batch(n_rays, seed=seed)
+    target = np.random.default_rng(seed + 1).random((n_rays, CHANNELS), dtype=np.float32)  # torch.rand-like targets
+    return bitfield, rays_o, rays_d, target
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+
+def oracle_step(orc, fd, bitfield, rays_o, rays_d, target, sp, cp, n_mlp):
+    """The same step as the GPU arm, on the CPU oracle.  Returns (n_samples, loss)."""
+    aabb = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    nears, fars = orc.near_far_from_aabb(rays_o, rays_d, aabb, 0.2)
+    xyzs, dirs, deltas, rays, counter = orc.march_rays_train(rays_o, rays_d, 1.0, bitfield, 1, 128, nears, fars,
+                                                             max_steps=MAX_STEPS)
+    sig, rgb = orc.field_forward(fd, xyzs, dirs, sp[n_mlp:], sp[:n_mlp], cp)
+    ws, depth, image = orc.composite_rays_train_forward(sig, rgb, deltas, rays, 1e-4)
+    pred = image + (1 - ws)[:, None]
+    loss = float(np.abs(pred - target).mean())
+    g_img = (np.sign(pred - target) / pred.size).astype(np.float32)
+    gs, gr = orc.composite_rays_train_backward(-g_img.sum(-1), g_img, sig, rgb, deltas, rays, ws, image, 1e-4)
+    orc.field_backward(fd, xyzs, dirs, sp[n_mlp:], sp[:n_mlp], cp, gs, gr)
+    return int(counter[0]), loss
+
+
+def cpu_setup():
+    from oracle import oracle as orc
+    from stable_nerf_b200 import NeRFNetwork
+    orc.set_threads(0)
+    model = NeRFNetwork(channel_dim=CHANNELS)
+    sp = model.sigma_net.params.detach().numpy().copy()
+    n_mlp = model.sigma_net.n_mlp
+    sp[n_mlp:] *= TABLE_SCALE
+    cp = model.color_net.params.detach().numpy().copy()
+    fd = orc.copy_desc(model.fdesc, orc.FieldDesc)
+    return orc, fd, sp, cp, n_mlp
+
+
+def cpu_baseline(budget_s=20.0):
+    """oracle port on the host cores over a bounded sample of the cfg2 batch (reported baseline only)."""
+    orc, fd, sp, cp, n_mlp = cpu_setup()
+    bitfield, rays_o, rays_d, target = workload(RAYS_PER_GPU, 0)
+    t0 = time.perf_counter()
+    oracle_step(orc, fd, bitfield, rays_o[:32], rays_d[:32], target[:32], sp, cp, n_mlp)
+    t32 = time.perf_counter() - t0
+    n = int(min(RAYS_PER_GPU, max(32, 32 * budget_s / max(t32, 1e-3) // 32 * 32)))
+    t0 = time.perf_counter()
+    ns, _ = oracle_step(orc, fd, bitfield, rays_o[:n], rays_d[:n], target[:n], sp, cp, n_mlp)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "rays/s", "cores": orc.get_threads(), "kind": "port",
+            "sample": f"first {n} of the {RAYS_PER_GPU} cfg2 rays ({ns} samples), one fwd+bwd step in {dt:.1f} s on "
+                      f"the C oracle (OpenMP); the reference ships no CPU path (SURVEY R2)"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference has no CPU implementation of this path (nerf/renderer.py:330-334 is CUDA only)
+    and its tiny-cuda-nn dependency is absent, so the timed thing is the oracle port on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    orc, fd, sp, cp, n_mlp = cpu_setup()
+    bitfield, rays_o, rays_d, target = workload(RAYS_PER_GPU, 0)
+    t0 = time.perf_counter()
+    oracle_step(orc, fd, bitfield, rays_o[:32], rays_d[:32], target[:32], sp, cp, n_mlp)
+    t32 = time.perf_counter() - t0
+    budget = 150.0 / (args.steps + args.warmup)
+    n = int(min(RAYS_PER_GPU, max(32, 32 * budget / max(t32, 1e-3) // 32 * 32)))
+    for w in range(args.warmup):
+        oracle_step(orc, fd, bitfield, rays_o[:n], rays_d[:n], target[:n], sp, cp, n_mlp)
+    t0 = time.perf_counter()
+    ns = 0
+    for k in range(args.steps):
+        lo = (k * n) % (RAYS_PER_GPU - n + 1)
+        s, _ = oracle_step(orc, fd, bitfield, rays_o[lo:lo + n], rays_d[lo:lo + n], target[lo:lo + n], sp, cp, n_mlp)
+        ns += s
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    cb = {"value": value, "unit": "rays/s", "cores": orc.get_threads(), "kind": "port",
+          "sample": f"{n} of the {RAYS_PER_GPU} cfg2 rays per step ({ns // max(args.steps, 1)} samples/step)"}
+    print(json.dumps({
+        "impl": "reference", "metric": "train rays/s (fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: 4096-ray train step, 800x800 Blender-shaped synthetic scene, hash grid + occupancy "
+                               "marching, max_steps 1024 (CPU arm: bounded sample per step)"},
+        "cpu_baseline": cb, "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "samples_per_s": ns / dt}))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+
+def stage_times(model, ts, iters=10):
+    """Device time of each stage of one step (CUDA events on the launch stream), eager, steady-state sizes."""
+    import torch
+    from stable_nerf_b200 import raymarching as rm
+    m = model
+    dev = ts.rays_o.device
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    acc, n_samples, M = {}, 0, 0
+    aabb = m.aabb_train
+    for it in range(iters + 2):
+        marks = [("start", ev())]
+        marks[0][1].record()
+
+        def mark(name):
+            e = ev()
+            e.record()
+            marks.append((name, e))
+        nears, fars = rm.near_far_from_aabb(ts.rays_o, ts.rays_d, aabb, m.min_near)
+        mark("near_far")
+        counter = torch.zeros(2, dtype=torch.int32, device=dev)
+        xyzs, dirs, deltas, rays = rm.march_rays_train(ts.rays_o, ts.rays_d, m.bound, m.density_bitfield, m.cascade,
+                                                       m.grid_size, nears, fars, counter, m.mean_count, False, 128,
+                                                       False, 0, ts.max_steps)
+        mark("march")
+        sig, rgb = m(xyzs, dirs)
+        mark("field_fwd")
+        ws, depth, image = rm.composite_rays_train(sig, rgb, deltas, rays, ts.T_thresh, m.channel_dim)
+        mark("composite_fwd")
+        pred = image + (1 - ws).unsqueeze(-1)
+        loss = (pred - ts.target).abs().mean()
+        g_sig, g_rgb = torch.autograd.grad(loss, [sig, rgb], retain_graph=True)
+        mark("loss+composite_bwd")
+        torch.autograd.backward([sig, rgb], [g_sig, g_rgb])
+        mark("field_bwd")
+        torch.cuda.synchronize()
+        if it >= 2:
+            for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+                acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1) / iters
+        n_samples, M = int(counter[0].item()), xyzs.shape[0]
+    return acc, n_samples, M
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from stable_nerf_b200 import NeRFNetwork, _lib
+    from stable_nerf_b200.trainer import TrainStep, broadcast_occupancy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()  # fail loudly when the extension is missing
+
+    bitfield, rays_o, rays_d, target = workload(RAYS_PER_GPU, seed=rank)
+    model = NeRFNetwork(channel_dim=CHANNELS, precision=args.precision).to(dev)
+    with torch.no_grad():
+        model.sigma_net.params[model.sigma_net.n_mlp:] *= TABLE_SCALE
+    model.density_bitfield.copy_(torch.from_numpy(bitfield))
+    broadcast_occupancy(model)
+    model.train()
+
+    ts = TrainStep(model, RAYS_PER_GPU, max_steps=MAX_STEPS, use_graph=not args.no_graph, world_size=world,
+                   loss_scale=1.0 / world)
+    d_o, d_d, d_t = (torch.from_numpy(a).to(dev) for a in (rays_o, rays_d, target))
+    h_o, h_d, h_t = (torch.from_numpy(a).pin_memory() for a in (rays_o, rays_d, target))
+    ts.warmup(d_o, d_d, d_t)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing: inputs already in HBM, K steps, CUDA events, max over ranks
+    for _ in range(args.warmup):
+        ts.step()
+    barrier()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            ts.step()
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = (ts.launches_per_step if ts.graph is not None else (_lib.launch_count() - launches0) // args.steps)
+    n_samples = int(model.step_counter[(model.local_step - 1) % 16, 0].item())
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> loss D2H, wall clock between device-complete points
+    for _ in range(args.warmup):
+        ts.step_from_host(h_o, h_d, h_t)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss = ts.step_from_host(h_o, h_d, h_t)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+
+    total_rays = RAYS_PER_GPU * world
+    out = {
+        "metric": "train rays/s (fwd+bwd)", "value": total_rays * args.steps / (ms * 1e-3), "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: 4096-ray train step per GPU, 800x800 Blender-shaped synthetic scene (lego-like "
+                               "occupancy, C=1, H=128), hash grid 16x2 T=2^19 + occupancy marching, max_steps 1024, "
+                               "channel_dim 3, fwd + L1 + bwd",
+                   "rays_per_gpu": RAYS_PER_GPU, "samples_per_step_per_gpu": n_samples, "mlp_precision": args.precision,
+                   "cuda_graph": ts.graph is not None, "parallelism": f"ray-sharded dp{world}",
+                   "l2": "not flushed between steps: the step streams params 49 MB + grads 49 MB + samples and "
+                         "activations (> 126 MB L2 together); the hash table is meant to stay L2-resident across steps"},
+        "e2e": {"value": total_rays * args.steps / (e2e_ms * 1e-3), "unit": "rays/s",
+                "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in (h_o, h_d, h_t))), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
+        "samples_per_s": n_samples * world * args.steps / (ms * 1e-3), "loss": loss,
+        "clocks": clocks.summary(),
+    }
+
+    if rank == 0 and not args.no_stages:
+        pk = peaks()
+        st, ns, M = stage_times(model, ts)
+        out["stages_ms"] = {k: round(v, 4) for k, v in st.items()}
+        C = CHANNELS
+        alg = {  # algorithmic bytes / flops per launch (SURVEY section 8d figures)
+            "near_far": ("hbm", 32.0 * RAYS_PER_GPU),
+            "march": ("hbm", 48.0 * RAYS_PER_GPU + 32.0 * ns),
+            "composite_fwd": ("hbm", (12 + 4 * C) * ns + (20 + 4 * C) * RAYS_PER_GPU),
+            "loss+composite_bwd": ("hbm", (16 + 8 * C) * ns + (20 + 8 * C) * RAYS_PER_GPU),
+            "field_fwd": ("tensor", 188416.0 * M),
+            "field_bwd": ("tensor", 565248.0 * M),  # recompute + dgrad + wgrad
+        }
+        dom = max(st, key=st.get)
+        bound, work = alg[dom]
+        t = st[dom] * 1e-3
+        if bound == "hbm":
+            ach, peak, unit = work / t / 1e9, pk["hbm"], "GB/s"
+        else:
+            ach, peak, unit = work / t / 1e12, pk["tf_sust"], "TFLOP/s"
+        out["roofline"] = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                           "traffic": None, "peak_source": pk["src"]}
+        out["stage_rooflines"] = {}
+        for k, (b, w) in alg.items():
+            if k in st and st[k] > 0:
+                a = w / (st[k] * 1e-3) / (1e9 if b == "hbm" else 1e12)
+                out["stage_rooflines"][k] = {"bound": b, "achieved": round(a, 2), "frac": round(a / (pk["hbm"] if b == "hbm" else pk["tf_sust"]), 4)}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline()
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("SNERF_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-stages", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,10 +50,8 @@ def sample_points(M, seed=0):
     if dirs.shape[0] < M:
         dirs = np.concatenate([dirs, np.tile(d[:1], (M - dirs.shape[0], 1))])
     x = x.astype(np.float32)
-    x[0] = (-1, -1, -1)
-    x[1] = (1, 1, 1)
-    x[2] = (0, 0, 0)
-    x[3] = (1, -1, 0.5)
+    for i, v in enumerate([(-1, -1, -1), (1, 1, 1), (0, 0, 0), (1, -1, 0.5)][:M]):
+        x[i] = v
     return x, dirs.astype(np.float32)
 
 
@@ -76,11 +74,12 @@ def test_hashgrid_forward_backward(M, setup, built_lib, cuda):
     g = rng.standard_normal((M, 32)).astype(np.float32)
     gt_o = orc.hashgrid_backward(of.grid, x01, g)
     gt = torch.zeros(f.grid.n_entries * 2, device=cuda)
-    check(lib.snerf_hashgrid_backward(f.grid, ptr(t_x), ptr(dev_t(g, cuda)), M, ptr(gt), stream()), "enc bwd")
+    t_g, t_g2 = dev_t(g, cuda), dev_t(2 * g, cuda)  # keep alive: ptr() of a temporary would dangle
+    check(lib.snerf_hashgrid_backward(f.grid, ptr(t_x), ptr(t_g), M, ptr(gt), stream()), "enc bwd")
     assert rel_err(gt.cpu().numpy(), gt_o) <= 1e-4, "hash-grid scatter-add backward"
     # linearity: backward of 2g is 2x
     gt2 = torch.zeros_like(gt)
-    check(lib.snerf_hashgrid_backward(f.grid, ptr(t_x), ptr(dev_t(2 * g, cuda)), M, ptr(gt2), stream()), "enc bwd")
+    check(lib.snerf_hashgrid_backward(f.grid, ptr(t_x), ptr(t_g2), M, ptr(gt2), stream()), "enc bwd")
     assert rel_err(gt2.cpu().numpy(), 2 * gt.cpu().numpy()) <= 1e-5
 
 
@@ -120,8 +119,9 @@ def run_cuda_field(f, x, dirs, ws, table, wc, precision, g_sig=None, g_rgb=None,
         gt = torch.zeros_like(t["tab"])
         gws = torch.zeros_like(t["ws"])
         gwc = torch.zeros_like(t["wc"])
+        t["gs"], t["gr"] = dev_t(g_sig, dev), dev_t(g_rgb, dev)  # keep alive: ptr() of a temporary would dangle
         check(lib.snerf_field_backward(f, ptr(t["x"]), ptr(t["d"]), M, ptr(t["tab"]), ptr(t["ws"]), ptr(t["wc"]),
-                                       ptr(dev_t(g_sig, dev)), ptr(dev_t(g_rgb, dev)), precision, ptr(gt), ptr(gws),
+                                       ptr(t["gs"]), ptr(t["gr"]), precision, ptr(gt), ptr(gws),
                                        ptr(gwc), ptr(wsb), nb, stream()), "field bwd")
         grads = (gt.cpu().numpy(), gws.cpu().numpy(), gwc.cpu().numpy())
     torch.cuda.synchronize()

@@ -170,8 +170,9 @@ def test_composite_train_fwd_bwd(sc, built_lib, cuda):
     from stable_nerf_b200._lib import check, ptr, stream
     gs2 = torch.full((M,), float("nan"), device=cuda)
     gr2 = torch.full((M, sc.channels), float("nan"), device=cuda)
+    keep = [dev_t(g_ws, cuda), dev_t(g_img, cuda), dev_t(dl, cuda)]  # ptr() of a temporary would dangle
     check(_lib.load().snerf_composite_rays_train_backward(
-        ptr(dev_t(g_ws, cuda)), ptr(dev_t(g_img, cuda)), ptr(t_sig.detach()), ptr(t_rgb.detach()), ptr(dev_t(dl, cuda)),
+        ptr(keep[0]), ptr(keep[1]), ptr(t_sig.detach()), ptr(t_rgb.detach()), ptr(keep[2]),
         ptr(t_rays), ptr(c_ws.detach()), ptr(c_image.detach()), M, N, sc.t_thresh, sc.channels, ptr(gs2), ptr(gr2),
         stream()), "bwd")
     assert torch.equal(gs2, t_sig.grad) and torch.equal(gr2, t_rgb.grad)
@@ -219,9 +220,10 @@ def test_inference_march_composite_compact(sc, built_lib, cuda):
         xyzs = torch.full((M, 3), float("nan"), device=cuda)
         dirs = torch.full((M, 3), float("nan"), device=cuda)
         deltas = torch.full((M, 2), float("nan"), device=cuda)
+        t_noise = dev_t(noises, cuda)
         check(lib.snerf_march_rays_ex(n_alive, n_step, ptr(alive), ptr(rays_t), ptr(o), ptr(d), sc.bound, sc.dt_gamma,
                                       sc.max_steps, sc.cascades, sc.H, ptr(bf), ptr(nears), ptr(fars), ptr(xyzs),
-                                      ptr(dirs), ptr(deltas), ptr(dev_t(noises, cuda)), M, stream()), "march_rays")
+                                      ptr(dirs), ptr(deltas), ptr(t_noise), M, stream()), "march_rays")
         assert_bits_equal(xyzs.cpu().numpy(), ox, f"it{it} xyzs")
         assert_bits_equal(dirs.cpu().numpy(), od, f"it{it} dirs")
         assert_bits_equal(deltas.cpu().numpy(), odl, f"it{it} deltas")
