@@ -230,6 +230,11 @@ int snerf_field_backward(const snerf_field_desc* f, const float* xyzs, const flo
                          float* grad_w_sigma, float* grad_w_color, void* workspace, size_t workspace_bytes,
                          snerf_stream_t stream);
 
+/* Hardware self-test of the tcgen05 building blocks: D[128,N] = A[128,K] * B[N,K]^T (bf16 operands, fp32
+ * accumulate) for one tile, with either operand staged K-major or MN-major (a_mn / b_mn).  Not on the hot path. */
+int snerf_tc_selftest(const float* A, const float* B, float* D, uint32_t N, uint32_t K, int a_mn, int b_mn,
+                      snerf_stream_t stream);
+
 /* nerf/activation.py:6-18.  y = exp(x); dx = g * exp(clamp(x,-15,15)). */
 int snerf_trunc_exp_forward(const float* x, uint32_t n, float* y, snerf_stream_t stream);
 int snerf_trunc_exp_backward(const float* g, const float* x, uint32_t n, float* dx, snerf_stream_t stream);

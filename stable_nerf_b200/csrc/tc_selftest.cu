@@ -1,0 +1,75 @@
+// tc_selftest.cu -- single-tile tcgen05 GEMM through the same helpers (tile layout, descriptors, mbarrier, TMEM) the
+// fused field kernels use.  tests/test_gpu_tc.py compares it with torch.matmul for K-major and MN-major operands.
+#include "tc.cuh"
+
+namespace snerf {
+
+// D[128,N] = A[128,K] * B[N,K]^T with bf16-rounded operands.  a_mn / b_mn select how the operand is laid out in
+// shared memory (rows = K index) and read through an MN-major descriptor.
+__global__ void __launch_bounds__(128) k_tc_selftest(const float* __restrict__ A, const float* __restrict__ B,
+                                                     float* __restrict__ D, uint32_t N, uint32_t K, int a_mn, int b_mn) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 32768;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t a_rows = a_mn ? K : 128u, b_rows = b_mn ? K : N;
+  for (uint32_t i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  __syncthreads();
+  for (uint32_t i = tid; i < 128 * K; i += 128) {
+    const uint32_t m = i / K, k = i % K;
+    const __nv_bfloat16 v = __float2bfloat16_rn(A[i]);
+    *reinterpret_cast<__nv_bfloat16*>(sA + (a_mn ? tc::tile_off(a_rows, k, m) : tc::tile_off(a_rows, m, k))) = v;
+  }
+  for (uint32_t i = tid; i < N * K; i += 128) {
+    const uint32_t n = i / K, k = i % K;
+    const __nv_bfloat16 v = __float2bfloat16_rn(B[i]);
+    *reinterpret_cast<__nv_bfloat16*>(sB + (b_mn ? tc::tile_off(b_rows, k, n) : tc::tile_off(b_rows, n, k))) = v;
+  }
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc<128>(&tmem_base_s);
+  tc::fence_proxy_async();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = tc::make_idesc(128, N, a_mn != 0, b_mn != 0);
+    for (uint32_t s = 0; s < K / 16; s++) {
+      const uint64_t ad = a_mn ? tc::desc_mnmajor(tc::smem_u32(sA), a_rows, s) : tc::desc_kmajor(tc::smem_u32(sA), a_rows, s);
+      const uint64_t bd = b_mn ? tc::desc_mnmajor(tc::smem_u32(sB), b_rows, s) : tc::desc_kmajor(tc::smem_u32(sB), b_rows, s);
+      tc::mma_ss(tmem, ad, bd, idesc, s > 0);
+    }
+    tc::mma_commit(&bar);
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after();
+  const uint32_t row = tid;  // warp w reads TMEM lanes 32w..32w+31
+  for (uint32_t c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tc::tmem_ld16(tmem + ((warp * 32u) << 16) + c0, v);
+    for (int j = 0; j < 16; j++) D[row * N + c0 + j] = v[j];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<128>(tmem);
+}
+
+}  // namespace snerf
+
+extern "C" int snerf_tc_selftest(const float* A, const float* B, float* D, uint32_t N, uint32_t K, int a_mn, int b_mn,
+                                 snerf_stream_t stream) {
+  using namespace snerf;
+  if (!A || !B || !D) return SNERF_E_BADARG;
+  if (N < 16 || N > 128 || (N % 16) || K < 16 || K > 128 || (K % 16)) return SNERF_E_UNSUPPORTED;
+  const int smem = 65536 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  k_tc_selftest<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, a_mn, b_mn);
+  return finish_launch();
+}
