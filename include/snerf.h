@@ -208,13 +208,17 @@ uint32_t snerf_mlp_sigma_params(const snerf_field_desc* f);
 uint32_t snerf_mlp_color_params(const snerf_field_desc* f);
 
 size_t snerf_field_workspace_bytes(const snerf_field_desc* f, uint32_t M, int precision, int backward);
+/* bytes of the optional forward->backward hand-off buffer (0 when the precision has none) */
+size_t snerf_field_saved_bytes(const snerf_field_desc* f, uint32_t M, int precision);
 
 /* nerf/network.py:39-61 (NeRFNetwork.forward): xyzs [M,3] in [-bound,bound], dirs [M,3] unit ->
- * sigmas [M] (after ReLU), rgbs [M,channel_dim] (after sigmoid). */
+ * sigmas [M] (after ReLU), rgbs [M,channel_dim] (after sigmoid).
+ * saved (may be NULL): snerf_field_saved_bytes() bytes that the forward fills for the backward of the SAME inputs
+ * (the sigma net's geometry features, 32 B/sample); with it the backward does not re-run the sigma net first. */
 int snerf_field_forward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M,
                         const float* table, const float* w_sigma, const float* w_color, int precision,
-                        float* sigmas, float* rgbs, void* workspace, size_t workspace_bytes,
-                        snerf_stream_t stream);
+                        float* sigmas, float* rgbs, void* saved, size_t saved_bytes, void* workspace,
+                        size_t workspace_bytes, snerf_stream_t stream);
 
 /* nerf/network.py:63-76 (NeRFNetwork.density): sigma only; geo_feat [M,geo_feat_dim] optional (may be NULL). */
 int snerf_field_density(const snerf_field_desc* f, const float* xyzs, uint32_t M, const float* table,
@@ -227,8 +231,8 @@ int snerf_field_density(const snerf_field_desc* f, const float* xyzs, uint32_t M
 int snerf_field_backward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M,
                          const float* table, const float* w_sigma, const float* w_color,
                          const float* grad_sigmas, const float* grad_rgbs, int precision, float* grad_table,
-                         float* grad_w_sigma, float* grad_w_color, void* workspace, size_t workspace_bytes,
-                         snerf_stream_t stream);
+                         float* grad_w_sigma, float* grad_w_color, const void* saved, size_t saved_bytes,
+                         void* workspace, size_t workspace_bytes, snerf_stream_t stream);
 
 /* Hardware self-test of the tcgen05 building blocks: D[128,N] = A[128,K] * B[N,K]^T (bf16 operands, fp32
  * accumulate) for one tile, with either operand staged K-major or MN-major (a_mn / b_mn).  Not on the hot path. */

@@ -74,10 +74,12 @@ SIGNATURES = {
     "snerf_mlp_sigma_params": (c_uint32, [POINTER(FieldDesc)]),
     "snerf_mlp_color_params": (c_uint32, [POINTER(FieldDesc)]),
     "snerf_field_workspace_bytes": (c_size_t, [POINTER(FieldDesc), _U, c_int, c_int]),
-    "snerf_field_forward": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, c_int, _P, _P, _P, c_size_t, _S]),
+    "snerf_field_saved_bytes": (c_size_t, [POINTER(FieldDesc), _U, c_int]),
+    "snerf_field_forward": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, c_int, _P, _P, _P, c_size_t, _P, c_size_t,
+                                    _S]),
     "snerf_field_density": (c_int, [POINTER(FieldDesc), _P, _U, _P, _P, c_int, _P, _P, _P, c_size_t, _S]),
-    "snerf_field_backward": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P,
-                                     c_size_t, _S]),
+    "snerf_field_backward": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_size_t,
+                                     _P, c_size_t, _S]),
     "snerf_tc_selftest": (c_int, [_P, _P, _P, _U, _U, c_int, c_int, _S]),
     "snerf_trunc_exp_forward": (c_int, [_P, _U, _P, _S]),
     "snerf_trunc_exp_backward": (c_int, [_P, _P, _U, _P, _S]),

@@ -33,15 +33,21 @@ size_t snerf_field_workspace_bytes(const snerf_field_desc* f, uint32_t M, int pr
                                            : field_fp32_workspace_bytes(f, M, backward);
 }
 
+size_t snerf_field_saved_bytes(const snerf_field_desc* f, uint32_t M, int precision) {
+  if (check_field_desc(f) || precision != SNERF_PRECISION_BF16) return 0;
+  return field_tc_saved_bytes(M);
+}
+
 int snerf_field_forward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                         const float* w_sigma, const float* w_color, int precision, float* sigmas, float* rgbs,
-                        void* workspace, size_t workspace_bytes, snerf_stream_t stream) {
+                        void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes,
+                        snerf_stream_t stream) {
   if (int e = check_field_desc(f)) return e;
   if (M == 0) return SNERF_OK;
   if (!xyzs || !dirs || !table || !w_sigma || !w_color || !sigmas || !rgbs || !workspace) return SNERF_E_BADARG;
   if (precision == SNERF_PRECISION_BF16)
-    return field_tc_forward(f, xyzs, dirs, M, table, w_sigma, w_color, sigmas, rgbs, nullptr, false, workspace,
-                            workspace_bytes, (cudaStream_t)stream);
+    return field_tc_forward(f, xyzs, dirs, M, table, w_sigma, w_color, sigmas, rgbs, nullptr, false, saved, saved_bytes,
+                            workspace, workspace_bytes, (cudaStream_t)stream);
   if (precision != SNERF_PRECISION_FP32) return SNERF_E_UNSUPPORTED;
   return field_fp32_forward(f, xyzs, dirs, M, table, w_sigma, w_color, sigmas, rgbs, nullptr, false, workspace,
                             workspace_bytes, (cudaStream_t)stream);
@@ -54,8 +60,8 @@ int snerf_field_density(const snerf_field_desc* f, const float* xyzs, uint32_t M
   if (M == 0) return SNERF_OK;
   if (!xyzs || !table || !w_sigma || !sigmas || !workspace) return SNERF_E_BADARG;
   if (precision == SNERF_PRECISION_BF16)
-    return field_tc_forward(f, xyzs, nullptr, M, table, w_sigma, nullptr, sigmas, nullptr, geo_feat, true, workspace,
-                            workspace_bytes, (cudaStream_t)stream);
+    return field_tc_forward(f, xyzs, nullptr, M, table, w_sigma, nullptr, sigmas, nullptr, geo_feat, true, nullptr, 0,
+                            workspace, workspace_bytes, (cudaStream_t)stream);
   if (precision != SNERF_PRECISION_FP32) return SNERF_E_UNSUPPORTED;
   return field_fp32_forward(f, xyzs, nullptr, M, table, w_sigma, nullptr, sigmas, nullptr, geo_feat, true, workspace,
                             workspace_bytes, (cudaStream_t)stream);
@@ -63,8 +69,8 @@ int snerf_field_density(const snerf_field_desc* f, const float* xyzs, uint32_t M
 
 int snerf_field_backward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                          const float* w_sigma, const float* w_color, const float* grad_sigmas, const float* grad_rgbs,
-                         int precision, float* grad_table, float* grad_w_sigma, float* grad_w_color, void* workspace,
-                         size_t workspace_bytes, snerf_stream_t stream) {
+                         int precision, float* grad_table, float* grad_w_sigma, float* grad_w_color, const void* saved,
+                         size_t saved_bytes, void* workspace, size_t workspace_bytes, snerf_stream_t stream) {
   if (int e = check_field_desc(f)) return e;
   if (M == 0) return SNERF_OK;
   if (!xyzs || !dirs || !table || !w_sigma || !w_color || !grad_sigmas || !grad_rgbs || !grad_table || !grad_w_sigma ||
@@ -72,7 +78,7 @@ int snerf_field_backward(const snerf_field_desc* f, const float* xyzs, const flo
     return SNERF_E_BADARG;
   if (precision == SNERF_PRECISION_BF16)
     return field_tc_backward(f, xyzs, dirs, M, table, w_sigma, w_color, grad_sigmas, grad_rgbs, grad_table, grad_w_sigma,
-                             grad_w_color, workspace, workspace_bytes, (cudaStream_t)stream);
+                             grad_w_color, saved, saved_bytes, workspace, workspace_bytes, (cudaStream_t)stream);
   if (precision != SNERF_PRECISION_FP32) return SNERF_E_UNSUPPORTED;
   return field_fp32_backward(f, xyzs, dirs, M, table, w_sigma, w_color, grad_sigmas, grad_rgbs, grad_table, grad_w_sigma,
                              grad_w_color, workspace, workspace_bytes, (cudaStream_t)stream);

@@ -572,6 +572,7 @@ static size_t carve_tc(const snerf_field_desc* f, uint32_t M, int backward, char
 size_t field_tc_workspace_bytes(const snerf_field_desc* f, uint32_t M, int backward) {
   return carve_tc(f, M, backward, nullptr, nullptr);
 }
+size_t field_tc_saved_bytes(uint32_t M) { return (size_t)(M ? M : 1) * 16 * sizeof(__nv_bfloat16); }
 
 static int g_sm_count = 0;
 static int sm_count() {
@@ -608,11 +609,13 @@ static uint32_t grid_for(uint32_t M) { return min(div_up(M, kTile), (uint32_t)sm
 
 int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                      const float* w_sigma, const float* w_color, float* sigmas, float* rgbs, float* geo_feat,
-                     bool sigma_only, void* ws, size_t ws_bytes, cudaStream_t s) {
+                     bool sigma_only, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (ws_bytes < field_tc_workspace_bytes(f, M, 0)) return SNERF_E_WORKSPACE;
-  if ((uintptr_t)ws & 15u) return SNERF_E_BADARG;
+  if (((uintptr_t)ws & 15u) || ((uintptr_t)saved & 15u)) return SNERF_E_BADARG;
+  if (saved && saved_bytes < field_tc_saved_bytes(M)) return SNERF_E_WORKSPACE;
   TcWorkspace w;
   carve_tc(f, M, 0, (char*)ws, &w);
+  if (saved) w.geo = (__nv_bfloat16*)saved;  // the geometry features go straight into the hand-off buffer
   const PackedNet ps = make_packed(sigma_shape(f)), pc = make_packed(color_shape(f));
   k_pack_weights<<<div_up(ps.total_bytes / 16, 256), 256, 0, s>>>(w_sigma, ps, w.wimg_sigma);
   if (!sigma_only) k_pack_weights<<<div_up(pc.total_bytes / 16, 256), 256, 0, s>>>(w_color, pc, w.wimg_color);
@@ -638,9 +641,10 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
 
 int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                       const float* w_sigma, const float* w_color, const float* grad_sigmas, const float* grad_rgbs,
-                      float* grad_table, float* grad_w_sigma, float* grad_w_color, void* ws, size_t ws_bytes,
-                      cudaStream_t s) {
+                      float* grad_table, float* grad_w_sigma, float* grad_w_color, const void* saved, size_t saved_bytes,
+                      void* ws, size_t ws_bytes, cudaStream_t s) {
   if (ws_bytes < field_tc_workspace_bytes(f, M, 1)) return SNERF_E_WORKSPACE;
+  if (saved && (saved_bytes < field_tc_saved_bytes(M) || ((uintptr_t)saved & 15u))) return SNERF_E_BADARG;
   if (((uintptr_t)ws & 15u) || ((uintptr_t)grad_w_sigma & 15u) || ((uintptr_t)grad_w_color & 15u) ||
       ((uintptr_t)grad_table & 7u))
     return SNERF_E_BADARG;
@@ -650,15 +654,21 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   const PackedNet ps = make_packed(ss), pc = make_packed(sc);
   k_pack_weights<<<div_up(ps.total_bytes / 16, 256), 256, 0, s>>>(w_sigma, ps, w.wimg_sigma);
   k_pack_weights<<<div_up(pc.total_bytes / 16, 256), 256, 0, s>>>(w_color, pc, w.wimg_color);
-  // 1. sigma-net forward again: regenerates the geo features the colour net consumes
+  // 1. the geometry features the colour net consumes: handed over by the forward, or regenerated by running the
+  //    sigma net's forward again
   TcParams p;
-  fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
-  float* scratch_sigma = w.g_geo;  // any M floats: overwritten by step 2
-  p.sigmas = scratch_sigma;
-  p.geo = w.geo;
-  const size_t smem_f = ps.total_bytes + kActBytes + 1024;
-  if (int e = set_smem(k_field_fwd<0>, smem_f)) return e;
-  k_field_fwd<0><<<grid_for(M), kTcThreads, smem_f, s>>>(p);
+  unsigned launches = 4;
+  if (saved) {
+    w.geo = (__nv_bfloat16*)const_cast<void*>(saved);
+  } else {
+    fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
+    p.sigmas = w.g_geo;  // scratch: any M floats, overwritten by step 2
+    p.geo = w.geo;
+    const size_t smem_f = ps.total_bytes + kActBytes + 1024;
+    if (int e = set_smem(k_field_fwd<0>, smem_f)) return e;
+    k_field_fwd<0><<<grid_for(M), kTcThreads, smem_f, s>>>(p);
+    launches++;
+  }
   // 2. colour net: recompute + dgrad + wgrad; writes d loss / d geo
   fill_common(p, f, pc, M, xyzs, dirs, table, w.wimg_color);
   p.geo = w.geo;
@@ -677,7 +687,7 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   const size_t smem_s = kInBytes + (size_t)(ps.n_mats - 1) * kActBytes + kActBytes + kInBytes + kActBytes + 1024;
   if (int e = set_smem(k_field_bwd<0>, smem_s)) return e;
   k_field_bwd<0><<<grid_for(M), kTcThreads, smem_s, s>>>(p);
-  return finish_launch(5);
+  return finish_launch(launches);
 }
 
 }  // namespace snerf

@@ -152,7 +152,7 @@ class _FieldFunction(Function):
     """(xyzs, dirs, sigma_params, color_params) -> (sigmas [M], rgbs [M,C]); nerf/network.py:39-61."""
 
     @staticmethod
-    def forward(ctx, xyzs, dirs, sigma_params, color_params, fdesc, n_mlp_sigma, precision):
+    def forward(ctx, xyzs, dirs, sigma_params, color_params, fdesc, n_mlp_sigma, precision, grads_in_place):
         lib = _lib.load()
         _lib.require_cuda(xyzs, dirs, sigma_params, color_params)
         xyzs = xyzs.detach().to(torch.float32).contiguous().view(-1, 3)
@@ -164,35 +164,47 @@ class _FieldFunction(Function):
         rgbs = torch.empty(M, fdesc.channel_dim, dtype=torch.float32, device=dev)
         nbytes = lib.snerf_field_workspace_bytes(fdesc, M, precision, 0)
         ws = workspace.get("field", nbytes, dev)
+        # forward -> backward hand-off (the sigma net's geometry features): spares the backward a sigma-net pass
+        needs_grad = sigma_params.requires_grad or color_params.requires_grad
+        n_saved = lib.snerf_field_saved_bytes(fdesc, M, precision) if needs_grad else 0
+        saved = torch.empty(n_saved, dtype=torch.uint8, device=dev) if n_saved else None
         check(lib.snerf_field_forward(fdesc, ptr(xyzs), ptr(dirs), M, ptr(table), ptr(w_sigma), ptr(cp), precision,
-                                      ptr(sigmas), ptr(rgbs), ptr(ws), nbytes, stream()), "field forward")
-        ctx.save_for_backward(xyzs, dirs, sigma_params, color_params)
-        ctx.meta = (fdesc, n_mlp_sigma, precision)
+                                      ptr(sigmas), ptr(rgbs), ptr(saved), n_saved, ptr(ws), nbytes, stream()),
+              "field forward")
+        ctx.save_for_backward(xyzs, dirs, sigma_params, color_params, saved)
+        ctx.meta = (fdesc, n_mlp_sigma, precision, grads_in_place)
         return sigmas, rgbs
 
     @staticmethod
     def backward(ctx, grad_sigmas, grad_rgbs):
         lib = _lib.load()
-        xyzs, dirs, sigma_params, color_params = ctx.saved_tensors
-        fdesc, n_mlp_sigma, precision = ctx.meta
+        xyzs, dirs, sigma_params, color_params, saved = ctx.saved_tensors
+        fdesc, n_mlp_sigma, precision, grads_in_place = ctx.meta
         M, dev = xyzs.shape[0], xyzs.device
         grad_sigmas = grad_sigmas.to(torch.float32).contiguous()
         grad_rgbs = grad_rgbs.to(torch.float32).contiguous()
         sp, cp = sigma_params.detach(), color_params.detach()
-        g_sigma_params = torch.zeros_like(sp)
-        g_color_params = torch.zeros_like(cp)
+        # The kernels ACCUMULATE into the gradient buffers.  With grads_in_place (TrainStep) they add straight into
+        # the parameters' .grad (12.3 M floats): no zero-filled temporaries, no second add pass by autograd.
+        in_place = grads_in_place and sigma_params.grad is not None and color_params.grad is not None
+        g_sigma_params = sigma_params.grad if in_place else torch.zeros_like(sp)
+        g_color_params = color_params.grad if in_place else torch.zeros_like(cp)
         nbytes = lib.snerf_field_workspace_bytes(fdesc, M, precision, 1)
         ws = workspace.get("field", nbytes, dev)
+        n_saved = saved.numel() if saved is not None else 0
         check(lib.snerf_field_backward(fdesc, ptr(xyzs), ptr(dirs), M, ptr(sp[n_mlp_sigma:]), ptr(sp[:n_mlp_sigma]),
                                        ptr(cp), ptr(grad_sigmas), ptr(grad_rgbs), precision,
                                        ptr(g_sigma_params[n_mlp_sigma:]), ptr(g_sigma_params[:n_mlp_sigma]),
-                                       ptr(g_color_params), ptr(ws), nbytes, stream()), "field backward")
-        return None, None, g_sigma_params, g_color_params, None, None, None
+                                       ptr(g_color_params), ptr(saved), n_saved, ptr(ws), nbytes, stream()),
+              "field backward")
+        if in_place:
+            return None, None, None, None, None, None, None, None
+        return None, None, g_sigma_params, g_color_params, None, None, None, None
 
 
-def field_forward(xyzs, dirs, sigma_net, color_net, fdesc, precision):
+def field_forward(xyzs, dirs, sigma_net, color_net, fdesc, precision, grads_in_place=False):
     return _FieldFunction.apply(xyzs, dirs, sigma_net.params, color_net.params, fdesc, sigma_net.n_mlp,
-                                _precision_code(precision))
+                                _precision_code(precision), bool(grads_in_place))
 
 
 @torch.no_grad()

@@ -21,6 +21,7 @@ class NeRFNetwork(NeRFRenderer):
         self.config = config
         self.geo_feat_dim = geo_feat_dim
         self.precision = precision  # "fp32": CUDA-core reference-accuracy path; "bf16": tcgen05 path
+        self.grads_in_place = False  # set by trainer.TrainStep: backward adds straight into .grad
         self.fdesc = make_field_desc(config, channel_dim, geo_feat_dim, bound)
         self.sigma_net = SigmaNet(self.fdesc)
         self.encoder_dir = DirEncoder()
@@ -28,7 +29,7 @@ class NeRFNetwork(NeRFRenderer):
 
     def forward(self, x, d):
         """x [N,3] in [-bound,bound], d [N,3] unit -> sigma [N] (ReLU), colour [N,C] (sigmoid), both fp32."""
-        return field_forward(x, d, self.sigma_net, self.color_net, self.fdesc, self.precision)
+        return field_forward(x, d, self.sigma_net, self.color_net, self.fdesc, self.precision, self.grads_in_place)
 
     def density(self, x):
         sigma, geo_feat = field_density(x, self.sigma_net, self.fdesc, self.precision)

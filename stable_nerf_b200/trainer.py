@@ -79,6 +79,7 @@ class TrainStep:
         for p in self.params:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
+        model.grads_in_place = True  # the field backward accumulates straight into these .grad tensors
 
     def _body(self):
         m = self.model
