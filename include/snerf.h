@@ -239,6 +239,14 @@ int snerf_field_backward(const snerf_field_desc* f, const float* xyzs, const flo
 int snerf_tc_selftest(const float* A, const float* B, float* D, uint32_t N, uint32_t K, int a_mn, int b_mn,
                       snerf_stream_t stream);
 
+/* Timing probe of the tcgen05 building blocks (one CTA, clock64): out = 32 int64 on the device.  Not on the hot path. */
+int snerf_tc_probe(long long* out, int variant, snerf_stream_t stream);
+
+/* Debug aid, not on the hot path: registers a device buffer of 64 int64.  While set, the backward field kernels of
+ * the bf16 path (net 0: sigma, 1: colour) store clock64() marks of CTA 0's second tile at every phase boundary
+ * ([0] = number of marks).  NULL switches it off. */
+void snerf_debug_phase_buffer(void* dev_buffer, int net);
+
 /* nerf/activation.py:6-18.  y = exp(x); dx = g * exp(clamp(x,-15,15)). */
 int snerf_trunc_exp_forward(const float* x, uint32_t n, float* y, snerf_stream_t stream);
 int snerf_trunc_exp_backward(const float* g, const float* x, uint32_t n, float* dx, snerf_stream_t stream);

@@ -12,6 +12,8 @@ int snerf_version(void) { return 100; }  // round 1
 
 uint64_t snerf_launch_count(void) { return g_launch_count; }
 
+void snerf_debug_phase_buffer(void* dev_buffer, int net) { field_tc_set_phase_buffer(dev_buffer, net); }
+
 const char* snerf_error_string(int code) {
   switch (code) {
     case SNERF_OK: return "ok";

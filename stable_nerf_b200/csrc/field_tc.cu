@@ -20,6 +20,8 @@
 //
 // Numerics: weights, layer inputs and back-propagated gradients are rounded to bf16 (RNE) at exactly the points
 // the oracle's emulate_bf16 mode rounds them; accumulation is fp32.
+#include <algorithm>
+
 #include "encode.cuh"
 #include "field_common.cuh"
 #include "tc.cuh"
@@ -29,7 +31,6 @@ namespace snerf {
 using namespace tc;
 
 constexpr uint32_t kTile = 128;       // samples per tile (= UMMA M)
-constexpr uint32_t kTcThreads = 256;  // 8 warps: 2 per TMEM lane quadrant
 constexpr uint32_t kActBytes = 32768; // [128 x 128] bf16
 constexpr uint32_t kInBytes = 16384;  // [128 x 64]  bf16 (32 columns used)
 
@@ -96,27 +97,29 @@ struct TcParams {
   float* rgbs;
   float* geo_f32;        // optional [M,15] fp32 (density())
   __nv_bfloat16* geo;    // [M,16] bf16: (geo0..geo14, sigma_raw) written by the sigma net, read by the colour net
+  __nv_bfloat16* enc;    // [M,32] bf16 hash-grid features: written by the sigma forward, read by its backward
   // backward
   const float* grad_sigmas;
   const float* grad_rgbs;
   float* g_geo;          // [M,16] fp32: d loss / d geo (cols 0..14) written by the colour bwd, read by the sigma bwd
   float* grad_w;         // fp32 gradient of this net's flat matrices (accumulated)
   float2* grad_table;    // fp32 gradient of the hash table (accumulated)
+  long long* dbg;        // optional phase-timing buffer (snerf_debug_phase_buffer): clock64 marks of CTA 0, 2nd tile
 };
+
+// byte offset of row r inside a chunk (the 16-byte group g of the row sits at + ((g ^ (r & 7)) << 4))
+__device__ __forceinline__ uint32_t row_off(uint32_t r) { return (r >> 3) * kAtomBytes + (r & 7u) * 128u; }
 
 __device__ __forceinline__ void st_group(uint8_t* tile, uint32_t rows, uint32_t r, uint32_t c, uint32_t g, uint4 v) {
   *reinterpret_cast<uint4*>(tile + tile_off16(rows, r, c, g)) = v;
 }
-__device__ __forceinline__ uint4 ld_group(const uint8_t* tile, uint32_t rows, uint32_t r, uint32_t c, uint32_t g) {
-  return *reinterpret_cast<const uint4*>(tile + tile_off16(rows, r, c, g));
-}
 
-// sigma-net input: 8 levels (16 features = 2 column groups) of one sample
-__device__ __forceinline__ void encode_half(const snerf_grid_desc& g, const float2* __restrict__ table, float x, float y,
-                                            float z, uint32_t l0, uint4 (&out)[2]) {
-  uint32_t packed[8];
+// NL consecutive levels (l0 ..) of one sample -> NL bf16x2 words
+template <int NL>
+__device__ __forceinline__ void encode_levels(const snerf_grid_desc& g, const float2* __restrict__ table, float x, float y,
+                                              float z, uint32_t l0, uint32_t (&packed)[NL]) {
 #pragma unroll 2
-  for (uint32_t j = 0; j < 8; j++) {
+  for (uint32_t j = 0; j < (uint32_t)NL; j++) {
     const LevelInfo li = level_info(g, l0 + j);
     const Cell c = grid_cell(x, y, z, li.scale);
     float2 v[8];
@@ -132,77 +135,93 @@ __device__ __forceinline__ void encode_half(const snerf_grid_desc& g, const floa
     }
     packed[j] = pack_bf16(acc.x, acc.y);
   }
-  out[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-  out[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
 }
 
 __device__ __forceinline__ float norm01(float v, float bound) { return __fdiv_rn(fadd(v, bound), fmul(2.0f, bound)); }
 
-// writes the 32-column input operand of tile `t` into `a0` (chunk 0 of a [128 x 64] tile)
-template <int NET>
-__device__ __forceinline__ void load_input(const TcParams& p, uint32_t t, uint8_t* a0) {
-  const uint32_t s = threadIdx.x & 127u, h = threadIdx.x >> 7;
-  const uint32_t m = t * kTile + s;
-  uint4 out[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+// The 32-column input operand of sample m is 4 groups of 8 columns.  NET 0: group g = hash-grid levels 4g..4g+3;
+// NET 1: groups 0,1 = SH-4 of the direction, groups 2,3 = the 15 geometry features + a zero pad.
+// Writes groups [G0, G0+NG) of row `row` into chunk 0 of tile a0 (zeros for rows past M).
+template <int NET, int G0, int NG, bool kFromSaved>
+__device__ __forceinline__ void load_input(const TcParams& p, uint32_t m, uint32_t row, uint8_t* a0) {
+  uint4 out[NG];
+#pragma unroll
+  for (int g = 0; g < NG; g++) out[g] = make_uint4(0u, 0u, 0u, 0u);
   if (m < p.M) {
     if (NET == 0) {
-      const float x = norm01(__ldg(p.xyzs + (size_t)m * 3), p.bound), y = norm01(__ldg(p.xyzs + (size_t)m * 3 + 1), p.bound),
-                  z = norm01(__ldg(p.xyzs + (size_t)m * 3 + 2), p.bound);
-      encode_half(p.grid, p.table, x, y, z, h * 8u, out);
-    } else if (h == 0) {
-      float o[16];
-      sh4_eval(fmul(fadd(__ldg(p.dirs + (size_t)m * 3), 1.0f), 0.5f), fmul(fadd(__ldg(p.dirs + (size_t)m * 3 + 1), 1.0f), 0.5f),
-               fmul(fadd(__ldg(p.dirs + (size_t)m * 3 + 2), 1.0f), 0.5f), o);
-      out[0] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-      out[1] = make_uint4(pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]), pack_bf16(o[12], o[13]), pack_bf16(o[14], o[15]));
+      if (kFromSaved) {
+        const uint4* ep = reinterpret_cast<const uint4*>(p.enc + (size_t)m * 32) + G0;
+#pragma unroll
+        for (int g = 0; g < NG; g++) out[g] = __ldg(ep + g);
+      } else {
+        const float x = norm01(__ldg(p.xyzs + (size_t)m * 3), p.bound), y = norm01(__ldg(p.xyzs + (size_t)m * 3 + 1), p.bound),
+                    z = norm01(__ldg(p.xyzs + (size_t)m * 3 + 2), p.bound);
+        uint32_t packed[NG * 4];
+        encode_levels<NG * 4>(p.grid, p.table, x, y, z, G0 * 4u, packed);
+#pragma unroll
+        for (int g = 0; g < NG; g++) out[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+        if (p.enc) {
+          uint4* ep = reinterpret_cast<uint4*>(p.enc + (size_t)m * 32) + G0;
+#pragma unroll
+          for (int g = 0; g < NG; g++) ep[g] = out[g];
+        }
+      }
     } else {
-      const uint4* gp = reinterpret_cast<const uint4*>(p.geo + (size_t)m * 16);
-      out[0] = __ldg(gp);
-      out[1] = __ldg(gp + 1);
-      out[1].w &= 0x0000ffffu;  // column 31 is the zero pad (the slot holds sigma_raw in the geo buffer)
+      if (G0 == 0) {
+        float o[16];
+        sh4_eval(fmul(fadd(__ldg(p.dirs + (size_t)m * 3), 1.0f), 0.5f), fmul(fadd(__ldg(p.dirs + (size_t)m * 3 + 1), 1.0f), 0.5f),
+                 fmul(fadd(__ldg(p.dirs + (size_t)m * 3 + 2), 1.0f), 0.5f), o);
+        out[0] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        out[1] = make_uint4(pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]), pack_bf16(o[12], o[13]), pack_bf16(o[14], o[15]));
+      }
+      if (G0 + NG == 4) {
+        const uint4* gp = reinterpret_cast<const uint4*>(p.geo + (size_t)m * 16);
+        out[NG - 2] = __ldg(gp);
+        out[NG - 1] = __ldg(gp + 1);
+        out[NG - 1].w &= 0x0000ffffu;  // column 31 is the zero pad (the slot holds sigma_raw in the geo buffer)
+      }
     }
   }
-  st_group(a0, kTile, s, 0, 2 * h, out[0]);
-  st_group(a0, kTile, s, 0, 2 * h + 1, out[1]);
+  uint8_t* rp = a0 + row_off(row);
+  const uint32_t r7 = row & 7u;
+#pragma unroll
+  for (int g = 0; g < NG; g++) *reinterpret_cast<uint4*>(rp + (((uint32_t)(G0 + g) ^ r7) << 4)) = out[g];
 }
 
-// K-major A (tile rows = 128 samples, K = k_dim columns) x K-major B (weight image, rows = n_out): D = A . W^T
-__device__ __forceinline__ void mma_forward(uint32_t d, const uint8_t* a, const uint8_t* w, uint32_t n_out, uint32_t k_dim) {
-  const uint32_t idesc = make_idesc(kTile, n_out, false, false);
+// D[128 x N] (+)= A[128 x 16*KSTEPS] . W[N x 16*KSTEPS]^T : K-major A tile (rows = samples) x K-major weight image
+template <uint32_t N, uint32_t KSTEPS>
+__device__ __forceinline__ void mma_forward(uint32_t d, const uint8_t* a, const uint8_t* w) {
+  constexpr uint32_t idesc = make_idesc(kTile, N, false, false);
   const uint32_t sa = smem_u32(a), sw = smem_u32(w);
-  for (uint32_t s = 0; s < k_dim / 16u; s++) mma_ss(d, desc_kmajor(sa, kTile, s), desc_kmajor(sw, n_out, s), idesc, s > 0);
+#pragma unroll
+  for (uint32_t s = 0; s < KSTEPS; s++) mma_ss(d, desc_kmajor(sa, kTile, s), desc_kmajor(sw, N, s), idesc, s > 0);
 }
 
-// hidden-layer epilogue: D[128 x 128] fp32 -> (ReLU | mask) -> bf16 -> dst tile.  All 8 warps: quadrant q = warp%4
-// owns TMEM lanes 32q..32q+31 (rows), half hc = warp/4 owns columns 64hc..64hc+63 (= chunk hc of the tile).
+// Hidden-layer epilogue of one 64-column chunk of one row: D fp32 (TMEM) -> ReLU (or the ReLU mask taken from the
+// post-ReLU activations in mask_src) -> bf16 -> dst.  taddr = accumulator address incl. the warp's lane offset and
+// the chunk's first column.  2 LDTM.x32, then per 8 columns 4 F2FP(.RELU) [+ 4 HSET2 + 4 LOP3 + LDS.128] + STS.128.
 template <bool kMask>
-__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_d, uint8_t* dst, const uint8_t* mask_src) {
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, q = warp & 3u, hc = warp >> 2;
-  const uint32_t row = q * 32u + lane;
+__device__ __forceinline__ void epi_chunk(uint32_t taddr, uint8_t* dst, const uint8_t* mask_src, uint32_t row, uint32_t chunk) {
+  uint32_t v[64];
+  tmem_ld64(taddr, v);
+  const uint32_t base = chunk * kTile * 128u + row_off(row), r7 = row & 7u;
 #pragma unroll
-  for (uint32_t cc = 0; cc < 2; cc++) {
-    float v[32];
-    tmem_ld32(tmem_d + ((q * 32u) << 16) + hc * 64u + cc * 32u, v);
-#pragma unroll
-    for (uint32_t j = 0; j < 4; j++) {
-      float e[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) e[k] = v[j * 8 + k];
-      if (kMask) {
-        const uint4 mk = ld_group(mask_src, kTile, row, hc, cc * 4u + j);
-        const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {  // activations are post-ReLU: bf16 > 0  <=>  non-zero, sign bit clear
-          if (!((mw[k] & 0x7fffu) != 0u && (mw[k] & 0x8000u) == 0u)) e[2 * k] = 0.f;
-          if (!((mw[k] & 0x7fff0000u) != 0u && (mw[k] & 0x80000000u) == 0u)) e[2 * k + 1] = 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; k++) e[k] = fmaxf(e[k], 0.f);
-      }
-      st_group(dst, kTile, row, hc, cc * 4u + j,
-               make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7])));
+  for (uint32_t j = 0; j < 8; j++) {
+    const uint32_t off = base + ((j ^ r7) << 4);
+    uint4 o;
+    if (kMask) {
+      const uint4 mk = *reinterpret_cast<const uint4*>(mask_src + off);
+      o.x = pack_bf16(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])) & bf16x2_gt0(mk.x);
+      o.y = pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])) & bf16x2_gt0(mk.y);
+      o.z = pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])) & bf16x2_gt0(mk.z);
+      o.w = pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])) & bf16x2_gt0(mk.w);
+    } else {
+      o.x = pack_bf16_relu(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+      o.y = pack_bf16_relu(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+      o.z = pack_bf16_relu(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+      o.w = pack_bf16_relu(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
     }
+    *reinterpret_cast<uint4*>(dst + off) = o;
   }
 }
 
@@ -214,106 +233,147 @@ __device__ __forceinline__ void sync_generic_to_async() {
 
 // ------------------------------------------------------------------------------------------------ forward kernel
 // NET 0: sigma net (hash-grid input; outputs sigma, geo).  NET 1: colour net (SH + geo input; outputs rgb).
+//
+// A CTA is kFwdGroups independent tile workers (warpgroups of 128 threads: thread = sample row = TMEM lane) that
+// share the resident weight image and the tensor pipe.  Each worker runs the sequential program
+//   input tile -> [MMA -> epilogue] x layers -> outputs
+// on its own activation buffer, accumulator columns, mbarrier and named barrier; because the workers are out of
+// phase, one worker's gathers and epilogues overlap the others' MMAs.
+
+constexpr uint32_t kFwdGroups = 3;
+constexpr uint32_t kFwdThreads = 128 * kFwdGroups;
 
 template <int NET>
-__global__ void __launch_bounds__(kTcThreads, 1) k_field_fwd(const TcParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 1) k_field_fwd(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* wsm = smem;                       // all packed matrices of the net
-  uint8_t* act = smem + p.net.total_bytes;   // [128 x 128] activation tile (input tile aliases chunk 0)
-  __shared__ uint64_t wbar, mbar;
+  uint8_t* wsm = smem;  // all packed matrices of the net
+  __shared__ uint64_t wbar, mbar[kFwdGroups];
   __shared__ uint32_t tmem_base_s;
-  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u, q = warp & 3u, hc = warp >> 2;
+  const uint32_t tid = threadIdx.x, warp = warp_idx_uniform(), wg = warp >> 2, row = tid & 127u;
+  uint8_t* act = smem + p.net.total_bytes + wg * kActBytes;  // [128 x 128] activation tile (input = chunk 0)
   const uint32_t n_tiles = div_up(p.M, kTile);
 
   if (tid == 0) {
     mbar_init(&wbar, 1);
-    mbar_init(&mbar, 1);
+    for (uint32_t g = 0; g < kFwdGroups; g++) mbar_init(&mbar[g], 1);
     fence_barrier_init();
     mbar_expect_tx(&wbar, p.net.total_bytes);
     for (uint32_t off = 0; off < p.net.total_bytes; off += 16384u)
       bulk_g2s(wsm + off, p.wimg + off, min(16384u, p.net.total_bytes - off), &wbar);
   }
-  if (warp == 0) tmem_alloc<128>(&tmem_base_s);
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = tmem_base_s + wg * kTile;            // this worker's 128 accumulator columns
+  const uint32_t tlane = tmem + (((warp & 3u) * 32u) << 16);  // + this warp's TMEM lane quadrant
   uint32_t mph = 0;
-  bool weights_ready = false;
   const int L = p.net.n_mats - 1;
+  auto worker_sync = [&]() {  // generic-proxy writes of this worker -> visible to the tensor pipe
+    tc_fence_before();
+    fence_proxy_async();
+    bar_sync(1u + wg, 128u);
+  };
 
-  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    load_input<NET>(p, t, act);
-    sync_generic_to_async();
+  for (uint32_t t = blockIdx.x + gridDim.x * wg; t < n_tiles; t += gridDim.x * kFwdGroups) {
+    const uint32_t m = t * kTile + row;
+    load_input<NET, 0, 4, false>(p, m, row, act);
+    worker_sync();
     for (int i = 0; i <= L; i++) {
-      if (tid == 0) {
-        if (!weights_ready) { mbar_wait(&wbar, 0); weights_ready = true; }
+      if ((warp & 3u) == 0) {  // the worker's first warp issues (converged warp, elected lane, uniform operands)
+        if (t == blockIdx.x + gridDim.x * wg) mbar_wait(&wbar, 0);  // weights resident (first tile of the worker)
         tc_fence_after();
-        mma_forward(tmem, act, wsm + p.net.img_off[i], (uint32_t)p.net.out_dim[i], (uint32_t)p.net.in_dim[i]);
-        mma_commit(&mbar);
+        const uint8_t* w = wsm + p.net.img_off[i];
+        if (elect_one()) {
+          if (i == 0) mma_forward<kTile, 2>(tmem, act, w);
+          else if (i < L) mma_forward<kTile, 8>(tmem, act, w);
+          else mma_forward<16, 8>(tmem, act, w);
+          mma_commit(&mbar[wg]);
+        }
+        __syncwarp();
       }
-      mbar_wait(&mbar, mph);
+      mbar_wait(&mbar[wg], mph);
       mph ^= 1u;
       tc_fence_after();
       if (i < L) {
-        epilogue_hidden<false>(tmem, act, nullptr);
-        sync_generic_to_async();
+        epi_chunk<false>(tlane, act, nullptr, row, 0);
+        epi_chunk<false>(tlane + 64u, act, nullptr, row, 1);
+        worker_sync();
       } else {
-        if (hc == 0) {
-          float v[16];
-          tmem_ld16(tmem + ((q * 32u) << 16), v);
-          const uint32_t m = t * kTile + q * 32u + lane;
-          if (m < p.M) {
-            if (NET == 0) {
-              p.sigmas[m] = fmaxf(v[0], 0.f);  // F.relu, nerf/network.py:46
-              if (p.geo) {
-                uint4* gp = reinterpret_cast<uint4*>(p.geo + (size_t)m * 16);
-                gp[0] = make_uint4(pack_bf16(v[1], v[2]), pack_bf16(v[3], v[4]), pack_bf16(v[5], v[6]), pack_bf16(v[7], v[8]));
-                gp[1] = make_uint4(pack_bf16(v[9], v[10]), pack_bf16(v[11], v[12]), pack_bf16(v[13], v[14]), pack_bf16(v[15], v[0]));
-              }
-              if (p.geo_f32)
-                for (int k = 0; k < 15; k++) p.geo_f32[(size_t)m * 15 + k] = v[1 + k];
-            } else {
-              for (uint32_t c = 0; c < p.C; c++) p.rgbs[(size_t)m * p.C + c] = 1.0f / (1.0f + __expf(-v[c]));  // sigmoid, :59
+        float v[16];
+        tmem_ld16(tlane, v);
+        if (m < p.M) {
+          if (NET == 0) {
+            p.sigmas[m] = fmaxf(v[0], 0.f);  // F.relu, nerf/network.py:46
+            if (p.geo) {
+              uint4* gp = reinterpret_cast<uint4*>(p.geo + (size_t)m * 16);
+              gp[0] = make_uint4(pack_bf16(v[1], v[2]), pack_bf16(v[3], v[4]), pack_bf16(v[5], v[6]), pack_bf16(v[7], v[8]));
+              gp[1] = make_uint4(pack_bf16(v[9], v[10]), pack_bf16(v[11], v[12]), pack_bf16(v[13], v[14]), pack_bf16(v[15], v[0]));
             }
+            if (p.geo_f32)
+              for (int k = 0; k < 15; k++) p.geo_f32[(size_t)m * 15 + k] = v[1 + k];
+          } else {
+            for (uint32_t c = 0; c < p.C; c++) p.rgbs[(size_t)m * p.C + c] = 1.0f / (1.0f + __expf(-v[c]));  // sigmoid, :59
           }
         }
-        tc_fence_before();
-        __syncthreads();
+        // the next tile's worker_sync orders these TMEM reads before the MMA that overwrites the accumulator
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<128>(tmem);
+  if (warp == 0) tmem_dealloc<512>(tmem_base_s);
 }
 
 // ------------------------------------------------------------------------------------------------ backward kernel
 //
-// Shared memory (bytes): A0 16K | A1..AL L x 32K | E 32K | S 16K | W 32K.   TMEM columns: [0,128) work accumulator,
-// [128 + 128 j, ...) weight-gradient accumulator of hidden matrix W_{j+1} (j < L-1), kept across the CTA's tiles.
-// Gradient tiles alternate between E and A_L's buffer (dead after the last layer's wgrad/dgrad).
+// Shared memory (bytes): A0 16K | A1..AL L x 32K | E 32K | weight ring NS x 16K.   TMEM columns: [0,128) work
+// accumulator, [128 + 128 j, ...) weight-gradient accumulator of hidden matrix W_{j+1} (j < L-1), kept across the
+// CTA's tiles.  Gradient tiles alternate between E and A_L's buffer (dead after the last layer's wgrad/dgrad); the
+// gradient of the raw output (16 columns) borrows the first half of E until the last layer's dgrad has read it.
+//
+// Warp roles:
+//   warps 0-7  compute: input tiles, epilogues, scatter.  Quadrant q = warp%4 owns TMEM lanes 32q..32q+31 (rows),
+//              half hc = warp/4 owns columns 64hc..64hc+63.
+//   warp 8     MMA issuer: a converged warp whose elected lane issues every tcgen05.mma / commit of the static
+//              per-tile schedule.  All of its addresses derive from warp-uniform values, so descriptors sit in
+//              uniform registers (a thread-divergent `if (tid == 0)` issue path costs ~95 cycles per MMA in
+//              R2UR broadcast loops).  It meets the compute warps at named barrier 1 ("operands written / TMEM
+//              read") and answers through the `mbar` mbarrier ("accumulator ready").
+//   warp 9     weight producer: the activations of a tile leave no room for the weights, so they stream through a
+//              ring of 16 KiB slots (one 64-column chunk of a matrix each) that one thread keeps full with bulk
+//              copies, running ahead of the MMAs by the depth of the ring; tcgen05.commit hands a slot back when
+//              the MMAs that read it have finished.  Fill order per tile (static):
+//              W_0 | W_1 .. W_{L-1} (2 chunks each) | W_L | W_{L-1} .. W_1 | W_0.
 
-template <int NET>
-__global__ void __launch_bounds__(kTcThreads, 1) k_field_bwd(const TcParams p) {
+constexpr uint32_t kBwdComputeThreads = 256;
+constexpr uint32_t kBwdThreads = kBwdComputeThreads + 64;
+constexpr uint32_t kBwdSyncThreads = kBwdComputeThreads + 32;  // compute warps + issuer warp meet at barrier 1
+constexpr uint32_t kSlotBytes = 16384;
+
+template <int NET, uint32_t NS>
+__global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int L = p.net.n_mats - 1;  // hidden activations a_1..a_L ; matrices W_0..W_L
   uint8_t* a0 = smem;
   uint8_t* ahid = a0 + kInBytes;                  // a_i at ahid + (i-1)*32K
   uint8_t* ebuf = ahid + (uint32_t)L * kActBytes;
-  uint8_t* sbuf = ebuf + kActBytes;               // [128 x 64] tile, 16 columns used: gradient of the net's raw output
-  uint8_t* wbuf = sbuf + kInBytes;
-  __shared__ uint64_t wbar, mbar;
+  uint8_t* sbuf = ebuf;                           // [128 x 64] tile, 16 columns used: gradient of the net's raw output
+  uint8_t* ring = ebuf + kActBytes;
+  __shared__ uint64_t mbar, full[NS], empty[NS];
   __shared__ uint32_t tmem_base_s;
-  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u, q = warp & 3u, hc = warp >> 2;
+  const uint32_t tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31u, q = warp & 3u, hc = (warp >> 2) & 1u;
   const uint32_t row = q * 32u + lane;
   const uint32_t n_tiles = div_up(p.M, kTile);
 
   if (tid == 0) {
-    mbar_init(&wbar, 1);
     mbar_init(&mbar, 1);
+    for (uint32_t i = 0; i < NS; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
@@ -321,219 +381,341 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_bwd(const TcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  uint32_t mph = 0, wph = 0;  // wph is only used by thread 0
-
   auto a_hid = [&](int i) { return ahid + (uint32_t)(i - 1) * kActBytes; };
-  auto fetch_w = [&](int i) {  // thread 0: start the bulk copy of matrix i into wbuf
-    mbar_expect_tx(&wbar, p.net.img_bytes[i]);
-    for (uint32_t off = 0; off < p.net.img_bytes[i]; off += 16384u)
-      bulk_g2s(wbuf + off, p.wimg + p.net.img_off[i] + off, min(16384u, p.net.img_bytes[i] - off), &wbar);
-  };
-  auto wait_w = [&]() {  // thread 0
-    mbar_wait(&wbar, wph);
-    wph ^= 1u;
-    tc_fence_after();
-  };
-  auto wait_mma = [&]() {
-    mbar_wait(&mbar, mph);
-    mph ^= 1u;
-    tc_fence_after();
-  };
 
-  float acc_first[32];  // dW_0[n = row][k < 32]     (warps with hc == 0)
-  float acc_last[16];   // dW_L[n < 16][k = row]
+  if (warp == kBwdComputeThreads / 32 + 1) {
+    // ======================================================================================== weight producer
+    if (lane == 0) {
+      uint32_t slot = 0, par = 1;  // first pass: waiting for parity 1 falls through on the fresh barriers
+      auto fill = [&](uint32_t src_off, uint32_t bytes) {
+        mbar_wait(&empty[slot], par);
+        mbar_expect_tx(&full[slot], bytes);
+        bulk_g2s(ring + slot * kSlotBytes, p.wimg + src_off, bytes, &full[slot]);
+        if (++slot == NS) { slot = 0; par ^= 1u; }
+      };
+      for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        fill(p.net.img_off[0], p.net.img_bytes[0]);
+        for (int i = 1; i < L; i++) {
+          fill(p.net.img_off[i], kSlotBytes);
+          fill(p.net.img_off[i] + kSlotBytes, kSlotBytes);
+        }
+        fill(p.net.img_off[L], p.net.img_bytes[L]);
+        for (int i = L - 1; i >= 1; i--) {
+          fill(p.net.img_off[i], kSlotBytes);
+          fill(p.net.img_off[i] + kSlotBytes, kSlotBytes);
+        }
+        fill(p.net.img_off[0], p.net.img_bytes[0]);
+      }
+    }
+  } else if (warp == kBwdComputeThreads / 32) {
+    // ======================================================================================== MMA issuer
+    uint32_t slot = 0, par = 0;
+    auto next_slot = [&]() -> uint32_t {  // wait for the next chunk of the static fill order; returns its address
+      mbar_wait(&full[slot], par);
+      const uint32_t addr = smem_u32(ring + slot * kSlotBytes);
+      if (++slot == NS) { slot = 0; par ^= 1u; }
+      tc_fence_after();
+      return addr;
+    };
+    auto slot_empty_bar = [&](uint32_t addr) { return &empty[(addr - smem_u32(ring)) / kSlotBytes]; };
+    auto meet = [&]() {  // the compute warps have written the operands / read the accumulator
+      bar_sync(1u, kBwdSyncThreads);
+      tc_fence_after();
+    };
+    const uint32_t s_a0 = smem_u32(a0), s_e = smem_u32(ebuf);
+    uint32_t iter = 0;
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, iter++) {
+      // ---- forward recompute
+      meet();
+      {
+        const uint32_t sw = next_slot();
+        if (elect_one()) {
+          constexpr uint32_t idesc = make_idesc(kTile, kTile, false, false);
 #pragma unroll
-  for (int k = 0; k < 32; k++) acc_first[k] = 0.f;
+          for (uint32_t s = 0; s < 2; s++) mma_ss(tmem, desc_kmajor(s_a0, kTile, s), desc_kmajor(sw, kTile, s), idesc, s > 0);
+          mma_commit(slot_empty_bar(sw));
+          mma_commit(&mbar);
+        }
+        __syncwarp();
+      }
+      for (int i = 1; i < L; i++) {
+        meet();
+        const uint32_t sa = smem_u32(a_hid(i));
+        constexpr uint32_t idesc = make_idesc(kTile, kTile, false, false);
 #pragma unroll
-  for (int k = 0; k < 16; k++) acc_last[k] = 0.f;
-
-  uint32_t iter = 0;
-  if (tid == 0 && blockIdx.x < n_tiles) fetch_w(0);
-  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, iter++) {
-    const uint32_t m = t * kTile + row;
-    // ---------------- forward recompute
-    load_input<NET>(p, t, a0);
-    sync_generic_to_async();
-    for (int i = 0; i < L; i++) {
-      if (tid == 0) {
-        wait_w();
-        mma_forward(tmem, i == 0 ? a0 : a_hid(i), wbuf, kTile, (uint32_t)p.net.in_dim[i]);
+        for (uint32_t c = 0; c < 2; c++) {  // K-steps 0-3 read chunk 0 (first slot), 4-7 chunk 1 (second slot)
+          const uint32_t sw = next_slot();
+          if (elect_one()) {
+#pragma unroll
+            for (uint32_t s = 0; s < 4; s++)
+              mma_ss(tmem, desc_kmajor(sa, kTile, c * 4u + s), desc_kmajor(sw, kTile, s), idesc, (c | s) > 0);
+            mma_commit(slot_empty_bar(sw));
+            if (c == 1) mma_commit(&mbar);
+          }
+          __syncwarp();
+        }
+      }
+      meet();
+      const uint32_t s_aL = smem_u32(a_hid(L));
+      const uint32_t sw_last = next_slot();  // W_L stays in its slot until the last layer's dgrad has read it
+      if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc(kTile, 16u, false, false);
+#pragma unroll
+        for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_kmajor(s_aL, kTile, s), desc_kmajor(sw_last, 16u, s), idesc, s > 0);
         mma_commit(&mbar);
       }
+      __syncwarp();
+      // ---- last matrix W_L [16 x 128]
+      meet();  // gradient of the raw output written to S
+      if (elect_one()) {  // wgrad (transposed): D[k, n] = sum_j a_L[j,k] g_out[j,n]
+        constexpr uint32_t idesc = make_idesc(kTile, 16u, true, true);
+#pragma unroll
+        for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_mnmajor(s_aL, kTile, s), desc_mnmajor(s_e, kTile, s), idesc, s > 0);
+        mma_commit(&mbar);
+      }
+      __syncwarp();
+      meet();  // accumulator read
+      if (elect_one()) {  // dgrad: D[m, k] = sum_n g_out[m,n] W_L[n,k]   (B = the W_L image read MN-major, rows = n)
+        mma_ss(tmem, desc_kmajor(s_e, kTile, 0), desc_mnmajor(sw_last, 16u, 0), make_idesc(kTile, kTile, false, true), false);
+        mma_commit(slot_empty_bar(sw_last));
+        mma_commit(&mbar);
+      }
+      __syncwarp();
+      // ---- hidden matrices W_{L-1} .. W_1 [128 x 128]
+      uint32_t sg = s_e, sgn = s_aL;
+      for (int i = L - 1; i >= 1; i--) {
+        meet();  // gradient tile written
+        const uint32_t sa = smem_u32(a_hid(i));
+        constexpr uint32_t id_d = make_idesc(kTile, 64u, false, true), id_w = make_idesc(kTile, kTile, true, true);
+        // dgrad: D[m,k] = sum_n g[m,n] W_i[n,k]; chunk c of the image holds columns k in [64c, 64c+64)
+#pragma unroll
+        for (uint32_t c = 0; c < 2; c++) {
+          const uint32_t sw = next_slot();
+          if (elect_one()) {
+#pragma unroll
+            for (uint32_t s = 0; s < 8; s++)
+              mma_ss(tmem + c * 64u, desc_kmajor(sg, kTile, s), desc_mnmajor(sw, kTile, s), id_d, s > 0);
+            mma_commit(slot_empty_bar(sw));
+            if (c == 1) mma_commit(&mbar);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          // wgrad: dW_i[n,k] += sum_j g[j,n] a_i[j,k]   (accumulates across tiles in TMEM; runs under the epilogue)
+          const uint32_t dw = tmem + 128u * (uint32_t)i;
+#pragma unroll
+          for (uint32_t s = 0; s < 8; s++)
+            mma_ss(dw, desc_mnmajor(sg, kTile, s), desc_mnmajor(sa, kTile, s), id_w, iter > 0 || s > 0);
+        }
+        __syncwarp();
+        const uint32_t tmp = sg; sg = sgn; sgn = tmp;
+      }
+      // ---- first matrix W_0 [128 x 32]
+      meet();
+      if (elect_one()) {  // wgrad: D[n, k] = sum_j g_1[j,n] a_0[j,k]
+        constexpr uint32_t idesc = make_idesc(kTile, 32u, true, true);
+#pragma unroll
+        for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_mnmajor(sg, kTile, s), desc_mnmajor(s_a0, kTile, s), idesc, s > 0);
+        mma_commit(&mbar);
+      }
+      __syncwarp();
+      meet();  // accumulator read
+      {
+        const uint32_t sw = next_slot();
+        if (elect_one()) {  // dgrad: D[m, k] = sum_n g_1[m,n] W_0[n,k],  k < 32
+          constexpr uint32_t idesc = make_idesc(kTile, 32u, false, true);
+#pragma unroll
+          for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_kmajor(sg, kTile, s), desc_mnmajor(sw, kTile, s), idesc, s > 0);
+          mma_commit(slot_empty_bar(sw));
+          mma_commit(&mbar);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ======================================================================================== compute warps
+    const uint32_t tlane = tmem + ((q * 32u) << 16);
+    uint32_t mph = 0;
+    auto hand_over = [&]() {  // generic-proxy writes of the compute warps -> visible to the tensor pipe; issuer may go
+      tc_fence_before();
+      fence_proxy_async();
+      bar_sync(1u, kBwdSyncThreads);
+    };
+    auto hand_over_tmem = [&]() {  // accumulator has been read; issuer may overwrite it
+      tc_fence_before();
+      bar_sync(1u, kBwdSyncThreads);
+    };
+    auto wait_mma = [&]() {
+      mbar_wait(&mbar, mph);
+      mph ^= 1u;
+      tc_fence_after();
+    };
+    uint32_t n_marks = 0;
+    uint32_t iter = 0;
+    auto mark = [&](int id) {  // phase timing of CTA 0's second tile (debug aid, off unless a buffer is registered)
+      if (p.dbg && tid == 0 && blockIdx.x == 0 && iter == 1 && n_marks < 63)
+        p.dbg[1 + n_marks++] = (clock64() << 8) | (long long)id;
+    };
+
+    float acc_first[32];  // dW_0[n = row][k < 32]     (warps with hc == 0)
+    float acc_last[16];   // dW_L[n < 16][k = row]
+#pragma unroll
+    for (int k = 0; k < 32; k++) acc_first[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc_last[k] = 0.f;
+
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, iter++) {
+      const uint32_t m = t * kTile + row;
+      mark(0);
+      // ---------------- forward recompute
+      if (NET == 0 && p.enc) {
+        if (hc == 0) load_input<NET, 0, 2, true>(p, m, row, a0);
+        else load_input<NET, 2, 2, true>(p, m, row, a0);
+      } else {
+        if (hc == 0) load_input<NET, 0, 2, false>(p, m, row, a0);
+        else load_input<NET, 2, 2, false>(p, m, row, a0);
+      }
+      hand_over();
+      mark(1);
+      for (int i = 0; i < L; i++) {
+        wait_mma();
+        mark(2);
+        epi_chunk<false>(tlane + hc * 64u, a_hid(i + 1), nullptr, row, hc);
+        mark(3);
+        hand_over();
+        mark(4);
+      }
       wait_mma();
-      if (tid == 0) fetch_w(i + 1);
-      epilogue_hidden<false>(tmem, a_hid(i + 1), nullptr);
-      sync_generic_to_async();
-    }
-    if (tid == 0) {
-      wait_w();
-      mma_forward(tmem, a_hid(L), wbuf, 16u, kTile);
-      mma_commit(&mbar);
-    }
-    wait_mma();
-    {  // gradient of the raw output (16 columns) -> S
-      uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0;
+      mark(5);
+      {  // gradient of the raw output (16 columns) -> S
+        uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0;
+        if (hc == 0) {
+          float v[16], go[16];
+          tmem_ld16(tlane, v);
+#pragma unroll
+          for (int k = 0; k < 16; k++) go[k] = 0.f;
+          if (m < p.M) {
+            if (NET == 0) {
+              go[0] = v[0] > 0.f ? __ldg(p.grad_sigmas + m) : 0.f;
+              const float4* gg = reinterpret_cast<const float4*>(p.g_geo + (size_t)m * 16);
+              const float4 x0 = __ldg(gg), x1 = __ldg(gg + 1), x2 = __ldg(gg + 2), x3 = __ldg(gg + 3);
+              const float gv[16] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z, x3.w};
+#pragma unroll
+              for (int k = 0; k < 15; k++) go[1 + k] = gv[k];
+            } else {
+              for (uint32_t c = 0; c < p.C; c++) {
+                const float y = 1.0f / (1.0f + __expf(-v[c]));
+                go[c] = __ldg(p.grad_rgbs + (size_t)m * p.C + c) * y * (1.0f - y);
+              }
+            }
+          }
+          g0 = make_uint4(pack_bf16(go[0], go[1]), pack_bf16(go[2], go[3]), pack_bf16(go[4], go[5]), pack_bf16(go[6], go[7]));
+          g1 = make_uint4(pack_bf16(go[8], go[9]), pack_bf16(go[10], go[11]), pack_bf16(go[12], go[13]), pack_bf16(go[14], go[15]));
+          st_group(sbuf, kTile, row, 0, 0, g0);
+          st_group(sbuf, kTile, row, 0, 1, g1);
+        }
+      }
+      hand_over();
+      mark(6);
+
+      // ---------------- last matrix W_L [16 x 128]
+      wait_mma();  // wgrad
+      mark(7);
       if (hc == 0) {
-        float v[16], go[16];
-        tmem_ld16(tmem + ((q * 32u) << 16), v);
+        float v[16];
+        tmem_ld16(tlane, v);
 #pragma unroll
-        for (int k = 0; k < 16; k++) go[k] = 0.f;
-        if (m < p.M) {
-          if (NET == 0) {
-            go[0] = v[0] > 0.f ? __ldg(p.grad_sigmas + m) : 0.f;
-            const float4* gg = reinterpret_cast<const float4*>(p.g_geo + (size_t)m * 16);
-            const float4 x0 = __ldg(gg), x1 = __ldg(gg + 1), x2 = __ldg(gg + 2), x3 = __ldg(gg + 3);
-            const float gv[16] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z, x3.w};
-#pragma unroll
-            for (int k = 0; k < 15; k++) go[1 + k] = gv[k];
-          } else {
-            for (uint32_t c = 0; c < p.C; c++) {
-              const float y = 1.0f / (1.0f + __expf(-v[c]));
-              go[c] = __ldg(p.grad_rgbs + (size_t)m * p.C + c) * y * (1.0f - y);
-            }
-          }
-        }
-        g0 = make_uint4(pack_bf16(go[0], go[1]), pack_bf16(go[2], go[3]), pack_bf16(go[4], go[5]), pack_bf16(go[6], go[7]));
-        g1 = make_uint4(pack_bf16(go[8], go[9]), pack_bf16(go[10], go[11]), pack_bf16(go[12], go[13]), pack_bf16(go[14], go[15]));
-        st_group(sbuf, kTile, row, 0, 0, g0);
-        st_group(sbuf, kTile, row, 0, 1, g1);
+        for (int k = 0; k < 16; k++) acc_last[k] += v[k];
       }
-    }
-    sync_generic_to_async();
+      hand_over_tmem();
+      wait_mma();  // dgrad
+      mark(8);
+      epi_chunk<true>(tlane + hc * 64u, ebuf, a_hid(L), row, hc);
+      hand_over();
+      mark(9);
 
-    // ---------------- last matrix W_L [16 x 128]
-    if (tid == 0) {  // wgrad (transposed): D[k, n] = sum_j a_L[j,k] g_out[j,n]
-      tc_fence_after();
-      const uint32_t idesc = make_idesc(kTile, 16u, true, true);
-      const uint32_t sa = smem_u32(a_hid(L)), sb = smem_u32(sbuf);
-      for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_mnmajor(sa, kTile, s), desc_mnmajor(sb, kTile, s), idesc, s > 0);
-      mma_commit(&mbar);
-    }
-    wait_mma();
-    if (hc == 0) {
-      float v[16];
-      tmem_ld16(tmem + ((q * 32u) << 16), v);
-#pragma unroll
-      for (int k = 0; k < 16; k++) acc_last[k] += v[k];
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {  // dgrad: D[m, k] = sum_n g_out[m,n] W_L[n,k]   (B = the W_L image read MN-major, rows = n)
-      tc_fence_after();
-      mma_ss(tmem, desc_kmajor(smem_u32(sbuf), kTile, 0), desc_mnmajor(smem_u32(wbuf), 16u, 0), make_idesc(kTile, kTile, false, true),
-             false);
-      mma_commit(&mbar);
-    }
-    wait_mma();
-    if (tid == 0) fetch_w(L - 1);
-    epilogue_hidden<true>(tmem, ebuf, a_hid(L));
-    sync_generic_to_async();
-
-    // ---------------- hidden matrices W_{L-1} .. W_1 [128 x 128]
-    uint8_t* gcur = ebuf;
-    uint8_t* gnext = a_hid(L);
-    for (int i = L - 1; i >= 1; i--) {
-      if (tid == 0) {
-        wait_w();
-        const uint32_t sg = smem_u32(gcur), sw = smem_u32(wbuf), sa = smem_u32(a_hid(i));
-        const uint32_t id_d = make_idesc(kTile, kTile, false, true), id_w = make_idesc(kTile, kTile, true, true);
-        // dgrad: D[m,k] = sum_n g[m,n] W_i[n,k]
-        for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_kmajor(sg, kTile, s), desc_mnmajor(sw, kTile, s), id_d, s > 0);
-        mma_commit(&mbar);
-        // wgrad: dW_i[n,k] += sum_j g[j,n] a_i[j,k]   (accumulates across tiles in TMEM)
-        const uint32_t dw = tmem + 128u * (uint32_t)i;
-        for (uint32_t s = 0; s < 8; s++)
-          mma_ss(dw, desc_mnmajor(sg, kTile, s), desc_mnmajor(sa, kTile, s), id_w, iter > 0 || s > 0);
+      // ---------------- hidden matrices W_{L-1} .. W_1 [128 x 128]
+      uint8_t* gcur = ebuf;
+      uint8_t* gnext = a_hid(L);
+      for (int i = L - 1; i >= 1; i--) {
+        wait_mma();  // dgrad (the wgrad runs under the epilogue)
+        mark(10);
+        epi_chunk<true>(tlane + hc * 64u, gnext, a_hid(i), row, hc);
+        hand_over();
+        mark(11);
+        uint8_t* tmp = gcur; gcur = gnext; gnext = tmp;
       }
-      wait_mma();
-      if (tid == 0) fetch_w(i - 1);
-      epilogue_hidden<true>(tmem, gnext, a_hid(i));
-      sync_generic_to_async();
-      uint8_t* tmp = gcur; gcur = gnext; gnext = tmp;
-    }
 
-    // ---------------- first matrix W_0 [128 x 32]
-    if (tid == 0) {  // wgrad: D[n, k] = sum_j g_1[j,n] a_0[j,k]
-      wait_w();
-      const uint32_t idesc = make_idesc(kTile, 32u, true, true);
-      const uint32_t sg = smem_u32(gcur), sa = smem_u32(a0);
-      for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_mnmajor(sg, kTile, s), desc_mnmajor(sa, kTile, s), idesc, s > 0);
-      mma_commit(&mbar);
-    }
-    wait_mma();
-    if (hc == 0) {
-      float v[32];
-      tmem_ld32(tmem + ((q * 32u) << 16), v);
-#pragma unroll
-      for (int k = 0; k < 32; k++) acc_first[k] += v[k];
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {  // dgrad: D[m, k] = sum_n g_1[m,n] W_0[n,k],  k < 32
-      tc_fence_after();
-      const uint32_t idesc = make_idesc(kTile, 32u, false, true);
-      const uint32_t sg = smem_u32(gcur), sw = smem_u32(wbuf);
-      for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_kmajor(sg, kTile, s), desc_mnmajor(sw, kTile, s), idesc, s > 0);
-      mma_commit(&mbar);
-    }
-    wait_mma();
-    if (tid == 0 && t + gridDim.x < n_tiles) fetch_w(0);  // next tile's first matrix
-    {
-      float v[16];
-      tmem_ld16(tmem + ((q * 32u) << 16) + hc * 16u, v);  // input-gradient columns 16hc .. 16hc+15 of row `row`
-      if (m < p.M) {
-        if (NET == 1) {
-          if (hc == 1) {  // columns 16..30 = d loss / d geo
-            float4* gg = reinterpret_cast<float4*>(p.g_geo + (size_t)m * 16);
-            gg[0] = make_float4(v[0], v[1], v[2], v[3]);
-            gg[1] = make_float4(v[4], v[5], v[6], v[7]);
-            gg[2] = make_float4(v[8], v[9], v[10], v[11]);
-            gg[3] = make_float4(v[12], v[13], v[14], 0.f);
-          }
-        } else {  // scatter-add of levels 8hc .. 8hc+7 into the table gradient
-          const float x = norm01(__ldg(p.xyzs + (size_t)m * 3), p.bound), y = norm01(__ldg(p.xyzs + (size_t)m * 3 + 1), p.bound),
-                      z = norm01(__ldg(p.xyzs + (size_t)m * 3 + 2), p.bound);
-#pragma unroll 2
-          for (uint32_t j = 0; j < 8; j++) {
-            const float gx = v[2 * j], gy = v[2 * j + 1];
-            if (gx == 0.f && gy == 0.f) continue;
-            const LevelInfo li = level_info(p.grid, hc * 8u + j);
-            const Cell c = grid_cell(x, y, z, li.scale);
-#pragma unroll
-            for (uint32_t k = 0; k < 8; k++) {
-              const float wt = corner_weight(c, k);
-              atomicAdd(p.grad_table + grid_index(li, c.c[0] + (k & 1u), c.c[1] + ((k >> 1) & 1u), c.c[2] + (k >> 2)),
-                        make_float2(wt * gx, wt * gy));
-            }
-          }
-        }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();
-  }
-
-  // ---------------- flush the weight gradients of this CTA
-  if (iter > 0) {
-    tc_fence_after();
-    if (hc == 0) {
-      float* g0 = p.grad_w + p.net.src_off[0] + (size_t)row * 32;
-#pragma unroll
-      for (int k = 0; k < 32; k += 4)
-        atomicAdd(reinterpret_cast<float4*>(g0 + k), make_float4(acc_first[k], acc_first[k + 1], acc_first[k + 2], acc_first[k + 3]));
-      float* gl = p.grad_w + p.net.src_off[L];
-#pragma unroll
-      for (int n = 0; n < 16; n++) atomicAdd(gl + (size_t)n * kTile + row, acc_last[n]);
-    }
-    for (int i = 1; i < L; i++) {
-      float* gw = p.grad_w + p.net.src_off[i] + (size_t)row * kTile + hc * 64u;
-#pragma unroll
-      for (uint32_t cc = 0; cc < 2; cc++) {
+      // ---------------- first matrix W_0 [128 x 32]
+      wait_mma();  // wgrad
+      mark(12);
+      if (hc == 0) {
         float v[32];
-        tmem_ld32(tmem + ((q * 32u) << 16) + 128u * (uint32_t)i + hc * 64u + cc * 32u, v);
+        tmem_ld32(tlane, v);
+#pragma unroll
+        for (int k = 0; k < 32; k++) acc_first[k] += v[k];
+      }
+      hand_over_tmem();
+      wait_mma();  // dgrad
+      mark(13);
+      {
+        float v[16];
+        tmem_ld16(tlane + hc * 16u, v);  // input-gradient columns 16hc .. 16hc+15 of row `row`
+        if (m < p.M) {
+          if (NET == 1) {
+            if (hc == 1) {  // columns 16..30 = d loss / d geo
+              float4* gg = reinterpret_cast<float4*>(p.g_geo + (size_t)m * 16);
+              gg[0] = make_float4(v[0], v[1], v[2], v[3]);
+              gg[1] = make_float4(v[4], v[5], v[6], v[7]);
+              gg[2] = make_float4(v[8], v[9], v[10], v[11]);
+              gg[3] = make_float4(v[12], v[13], v[14], 0.f);
+            }
+          } else {  // scatter-add of levels 8hc .. 8hc+7 into the table gradient
+            const float x = norm01(__ldg(p.xyzs + (size_t)m * 3), p.bound), y = norm01(__ldg(p.xyzs + (size_t)m * 3 + 1), p.bound),
+                        z = norm01(__ldg(p.xyzs + (size_t)m * 3 + 2), p.bound);
+#pragma unroll 2
+            for (uint32_t j = 0; j < 8; j++) {
+              const float gx = v[2 * j], gy = v[2 * j + 1];
+              if (gx == 0.f && gy == 0.f) continue;
+              const LevelInfo li = level_info(p.grid, hc * 8u + j);
+              const Cell c = grid_cell(x, y, z, li.scale);
+#pragma unroll
+              for (uint32_t k = 0; k < 8; k++) {
+                const float wt = corner_weight(c, k);
+                atomicAdd(p.grad_table + grid_index(li, c.c[0] + (k & 1u), c.c[1] + ((k >> 1) & 1u), c.c[2] + (k >> 2)),
+                          make_float2(wt * gx, wt * gy));
+              }
+            }
+          }
+        }
+      }
+      mark(14);
+      // the next tile's hand_over (after its input tile is written) orders these TMEM reads before the next MMA
+    }
+    if (p.dbg && tid == 0 && blockIdx.x == 0) p.dbg[0] = n_marks;
+
+    // ---------------- flush the weight gradients of this CTA
+    if (iter > 0) {
+      tc_fence_after();
+      if (hc == 0) {
+        float* g0 = p.grad_w + p.net.src_off[0] + (size_t)row * 32;
 #pragma unroll
         for (int k = 0; k < 32; k += 4)
-          atomicAdd(reinterpret_cast<float4*>(gw + cc * 32u + k), make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]));
+          atomicAdd(reinterpret_cast<float4*>(g0 + k), make_float4(acc_first[k], acc_first[k + 1], acc_first[k + 2], acc_first[k + 3]));
+        float* gl = p.grad_w + p.net.src_off[L];
+#pragma unroll
+        for (int n = 0; n < 16; n++) atomicAdd(gl + (size_t)n * kTile + row, acc_last[n]);
+      }
+      for (int i = 1; i < L; i++) {
+        float* gw = p.grad_w + p.net.src_off[i] + (size_t)row * kTile + hc * 64u;
+#pragma unroll
+        for (uint32_t cc = 0; cc < 2; cc++) {
+          float v[32];
+          tmem_ld32(tlane + 128u * (uint32_t)i + hc * 64u + cc * 32u, v);
+#pragma unroll
+          for (int k = 0; k < 32; k += 4)
+            atomicAdd(reinterpret_cast<float4*>(gw + cc * 32u + k), make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]));
+        }
       }
     }
   }
@@ -548,8 +730,13 @@ struct TcWorkspace {
   uint8_t* wimg_sigma;
   uint8_t* wimg_color;
   __nv_bfloat16* geo;
+  __nv_bfloat16* enc;
   float* g_geo;
 };
+
+// forward -> backward hand-off buffer: [geo: M x 16 bf16][pad to 1 KiB][enc: M x 32 bf16]
+static size_t saved_geo_bytes(uint32_t M) { return align_up((size_t)(M ? M : 1) * 16 * sizeof(__nv_bfloat16), 1024); }
+size_t field_tc_saved_bytes(uint32_t M) { return saved_geo_bytes(M) + (size_t)(M ? M : 1) * 32 * sizeof(__nv_bfloat16); }
 
 static size_t carve_tc(const snerf_field_desc* f, uint32_t M, int backward, char* base, TcWorkspace* w) {
   const PackedNet ps = make_packed(sigma_shape(f)), pc = make_packed(color_shape(f));
@@ -564,7 +751,9 @@ static size_t carve_tc(const snerf_field_desc* f, uint32_t M, int backward, char
   TcWorkspace& o = w ? *w : tmp;
   o.wimg_sigma = (uint8_t*)take(ps.total_bytes);
   o.wimg_color = (uint8_t*)take(pc.total_bytes);
-  o.geo = (__nv_bfloat16*)take((size_t)(M ? M : 1) * 16 * sizeof(__nv_bfloat16));
+  char* hand = take(field_tc_saved_bytes(M));  // used when the caller passes no hand-off buffer
+  o.geo = (__nv_bfloat16*)hand;
+  o.enc = (__nv_bfloat16*)(hand ? hand + saved_geo_bytes(M) : nullptr);
   o.g_geo = backward ? (float*)take((size_t)(M ? M : 1) * 16 * sizeof(float)) : nullptr;
   return off;
 }
@@ -572,7 +761,10 @@ static size_t carve_tc(const snerf_field_desc* f, uint32_t M, int backward, char
 size_t field_tc_workspace_bytes(const snerf_field_desc* f, uint32_t M, int backward) {
   return carve_tc(f, M, backward, nullptr, nullptr);
 }
-size_t field_tc_saved_bytes(uint32_t M) { return (size_t)(M ? M : 1) * 16 * sizeof(__nv_bfloat16); }
+
+static long long* g_phase_dbg = nullptr;
+static int g_phase_net = 0;
+void field_tc_set_phase_buffer(void* p, int net) { g_phase_dbg = (long long*)p; g_phase_net = net; }
 
 static int g_sm_count = 0;
 static int sm_count() {
@@ -603,9 +795,35 @@ static void fill_common(TcParams& p, const snerf_field_desc* f, const PackedNet&
   p.dirs = dirs;
   p.table = reinterpret_cast<const float2*>(table);
   p.wimg = wimg;
+  p.dbg = nullptr;
 }
 
 static uint32_t grid_for(uint32_t M) { return min(div_up(M, kTile), (uint32_t)sm_count()); }
+static size_t fwd_smem(const PackedNet& n) { return n.total_bytes + (size_t)kFwdGroups * kActBytes + 1024; }
+// ring depth of the backward's weight stream: whatever the 227 KiB of shared memory leave after the activations
+static uint32_t bwd_slots(const PackedNet& n) {
+  const size_t fixed = kInBytes + (size_t)(n.n_mats - 1) * kActBytes + kActBytes + 1024 + 512 /* static */;
+  const size_t room = 227 * 1024 > fixed ? 227 * 1024 - fixed : 0;
+  return room / kSlotBytes >= 5 ? 5u : (room / kSlotBytes >= 3 ? 3u : 0u);
+}
+static size_t bwd_smem(const PackedNet& n) {
+  return kInBytes + (size_t)(n.n_mats - 1) * kActBytes + kActBytes + (size_t)bwd_slots(n) * kSlotBytes + 1024;
+}
+
+template <int NET>
+static int launch_bwd(const TcParams& p, const PackedNet& n, uint32_t M, cudaStream_t s) {
+  const uint32_t slots = bwd_slots(n);
+  if (slots == 5) {
+    if (int e = set_smem(k_field_bwd<NET, 5>, bwd_smem(n))) return e;
+    k_field_bwd<NET, 5><<<grid_for(M), kBwdThreads, bwd_smem(n), s>>>(p);
+  } else if (slots == 3) {
+    if (int e = set_smem(k_field_bwd<NET, 3>, bwd_smem(n))) return e;
+    k_field_bwd<NET, 3><<<grid_for(M), kBwdThreads, bwd_smem(n), s>>>(p);
+  } else {
+    return SNERF_E_UNSUPPORTED;  // the activations of a tile leave no room for the weight ring
+  }
+  return SNERF_OK;
+}
 
 int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                      const float* w_sigma, const float* w_color, float* sigmas, float* rgbs, float* geo_feat,
@@ -615,7 +833,10 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
   if (saved && saved_bytes < field_tc_saved_bytes(M)) return SNERF_E_WORKSPACE;
   TcWorkspace w;
   carve_tc(f, M, 0, (char*)ws, &w);
-  if (saved) w.geo = (__nv_bfloat16*)saved;  // the geometry features go straight into the hand-off buffer
+  if (saved) {  // the geometry features and the encoded inputs go straight into the hand-off buffer
+    w.geo = (__nv_bfloat16*)saved;
+    w.enc = (__nv_bfloat16*)((char*)saved + saved_geo_bytes(M));
+  }
   const PackedNet ps = make_packed(sigma_shape(f)), pc = make_packed(color_shape(f));
   k_pack_weights<<<div_up(ps.total_bytes / 16, 256), 256, 0, s>>>(w_sigma, ps, w.wimg_sigma);
   if (!sigma_only) k_pack_weights<<<div_up(pc.total_bytes / 16, 256), 256, 0, s>>>(w_color, pc, w.wimg_color);
@@ -623,17 +844,17 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
   fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
   p.sigmas = sigmas;
   p.geo = sigma_only ? nullptr : w.geo;
+  p.enc = saved ? w.enc : nullptr;  // only worth writing when a backward will read it
   p.geo_f32 = geo_feat;
-  const size_t smem_s = ps.total_bytes + kActBytes + 1024, smem_c = pc.total_bytes + kActBytes + 1024;
-  if (int e = set_smem(k_field_fwd<0>, smem_s)) return e;
-  k_field_fwd<0><<<grid_for(M), kTcThreads, smem_s, s>>>(p);
+  if (int e = set_smem(k_field_fwd<0>, fwd_smem(ps))) return e;
+  k_field_fwd<0><<<grid_for(M), kFwdThreads, fwd_smem(ps), s>>>(p);
   unsigned launches = 2;
   if (!sigma_only) {
     fill_common(p, f, pc, M, xyzs, dirs, table, w.wimg_color);
     p.geo = w.geo;
     p.rgbs = rgbs;
-    if (int e = set_smem(k_field_fwd<1>, smem_c)) return e;
-    k_field_fwd<1><<<grid_for(M), kTcThreads, smem_c, s>>>(p);
+    if (int e = set_smem(k_field_fwd<1>, fwd_smem(pc))) return e;
+    k_field_fwd<1><<<grid_for(M), kFwdThreads, fwd_smem(pc), s>>>(p);
     launches += 2;
   }
   return finish_launch(launches);
@@ -654,19 +875,20 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   const PackedNet ps = make_packed(ss), pc = make_packed(sc);
   k_pack_weights<<<div_up(ps.total_bytes / 16, 256), 256, 0, s>>>(w_sigma, ps, w.wimg_sigma);
   k_pack_weights<<<div_up(pc.total_bytes / 16, 256), 256, 0, s>>>(w_color, pc, w.wimg_color);
-  // 1. the geometry features the colour net consumes: handed over by the forward, or regenerated by running the
-  //    sigma net's forward again
+  // 1. the geometry features the colour net consumes and the encoded inputs of the sigma net: handed over by the
+  //    forward, or regenerated by running the sigma net's forward again
   TcParams p;
   unsigned launches = 4;
   if (saved) {
     w.geo = (__nv_bfloat16*)const_cast<void*>(saved);
+    w.enc = (__nv_bfloat16*)((char*)const_cast<void*>(saved) + saved_geo_bytes(M));
   } else {
     fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
     p.sigmas = w.g_geo;  // scratch: any M floats, overwritten by step 2
     p.geo = w.geo;
-    const size_t smem_f = ps.total_bytes + kActBytes + 1024;
-    if (int e = set_smem(k_field_fwd<0>, smem_f)) return e;
-    k_field_fwd<0><<<grid_for(M), kTcThreads, smem_f, s>>>(p);
+    p.enc = w.enc;
+    if (int e = set_smem(k_field_fwd<0>, fwd_smem(ps))) return e;
+    k_field_fwd<0><<<grid_for(M), kFwdThreads, fwd_smem(ps), s>>>(p);
     launches++;
   }
   // 2. colour net: recompute + dgrad + wgrad; writes d loss / d geo
@@ -675,18 +897,17 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   p.grad_rgbs = grad_rgbs;
   p.g_geo = w.g_geo;
   p.grad_w = grad_w_color;
-  const size_t smem_c = kInBytes + (size_t)(pc.n_mats - 1) * kActBytes + kActBytes + kInBytes + kActBytes + 1024;
-  if (int e = set_smem(k_field_bwd<1>, smem_c)) return e;
-  k_field_bwd<1><<<grid_for(M), kTcThreads, smem_c, s>>>(p);
-  // 3. sigma net: recompute (incl. encode) + dgrad + wgrad + table scatter-add
+  p.dbg = g_phase_net == 1 ? g_phase_dbg : nullptr;
+  if (int e = launch_bwd<1>(p, pc, M, s)) return e;
+  // 3. sigma net: recompute from the saved encoding + dgrad + wgrad + table scatter-add
   fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
+  p.enc = w.enc;
   p.grad_sigmas = grad_sigmas;
   p.g_geo = w.g_geo;
   p.grad_w = grad_w_sigma;
   p.grad_table = reinterpret_cast<float2*>(grad_table);
-  const size_t smem_s = kInBytes + (size_t)(ps.n_mats - 1) * kActBytes + kActBytes + kInBytes + kActBytes + 1024;
-  if (int e = set_smem(k_field_bwd<0>, smem_s)) return e;
-  k_field_bwd<0><<<grid_for(M), kTcThreads, smem_s, s>>>(p);
+  p.dbg = g_phase_net == 0 ? g_phase_dbg : nullptr;
+  if (int e = launch_bwd<0>(p, ps, M, s)) return e;
   return finish_launch(launches);
 }
 

@@ -73,3 +73,101 @@ extern "C" int snerf_tc_selftest(const float* A, const float* B, float* D, uint3
   k_tc_selftest<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, a_mn, b_mn);
   return finish_launch();
 }
+
+// ------------------------------------------------------------------------------------------------ timing probe
+// Cycle counts (clock64, one CTA) of the building blocks the fused kernels are scheduled around.  Not on the hot path.
+namespace snerf {
+
+__global__ void __launch_bounds__(256) k_tc_probe(long long* __restrict__ out, int variant) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 32768;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  for (uint32_t i = tid; i < 65536 / 4; i += 256) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc<256>(&tmem_base_s);
+  tc::fence_proxy_async();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  uint32_t ph = 0;
+  int slot = 0;
+  // experiments: n MMAs (M128 N128 K16, SS, K-major) + commit, everybody waits; repeated 4x, last repetition recorded
+  const int counts[8] = {0, 1, 2, 4, 8, 16, 32, 64};
+  for (int e = 0; e < 8; e++) {
+    long long t0 = 0, t_issue = 0, t1 = 0;
+    for (int rep = 0; rep < 4; rep++) {
+      __syncthreads();
+      t0 = clock64();
+      if (tid == 0) {
+        tc::tc_fence_after();
+        const uint32_t N = variant == 1 ? 64u : 128u;
+        const uint32_t idesc = tc::make_idesc(128, N, false, false);
+        for (int s = 0; s < counts[e]; s++)
+          tc::mma_ss(tmem, tc::desc_kmajor(tc::smem_u32(sA), 128, s & 7), tc::desc_kmajor(tc::smem_u32(sB), 128, s & 7), idesc, s > 0);
+        tc::mma_commit(&bar);
+        t_issue = clock64();
+      }
+      tc::mbar_wait(&bar, ph);
+      ph ^= 1u;
+      tc::tc_fence_after();
+      t1 = clock64();
+    }
+    if (tid == 0) { out[slot] = t_issue - t0; out[slot + 1] = t1 - t0; }
+    if (tid == 255) out[slot + 2] = t1 - t0;
+    slot += 3;
+  }
+  // fence + barrier cost
+  for (int rep = 0; rep < 4; rep++) {
+    __syncthreads();
+    const long long t0 = clock64();
+    tc::tc_fence_before();
+    tc::fence_proxy_async();
+    __syncthreads();
+    const long long t1 = clock64();
+    if (tid == 0) out[slot] = t1 - t0;
+  }
+  slot++;
+  // epilogue-like: LDTM.x64 + 32 F2FP + 8 STS.128
+  for (int rep = 0; rep < 4; rep++) {
+    __syncthreads();
+    const long long t0 = clock64();
+    uint32_t v[64];
+    tc::tmem_ld64(tmem + (((warp & 3u) * 32u) << 16) + (warp >> 2) * 64u, v);
+    const long long t1 = clock64();
+    const uint32_t row = (warp & 3u) * 32u + (tid & 31u);
+    for (uint32_t j = 0; j < 8; j++) {
+      uint4 o;
+      o.x = tc::pack_bf16_relu(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]));
+      o.y = tc::pack_bf16_relu(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+      o.z = tc::pack_bf16_relu(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+      o.w = tc::pack_bf16_relu(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+      *reinterpret_cast<uint4*>(sA + tc::tile_off16(128, row, warp >> 2, j)) = o;
+    }
+    __syncthreads();
+    const long long t2 = clock64();
+    if (tid == 0) { out[slot] = t1 - t0; out[slot + 1] = t2 - t0; }
+  }
+  slot += 2;
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<256>(tmem);
+}
+
+}  // namespace snerf
+
+extern "C" int snerf_tc_probe(long long* out, int variant, snerf_stream_t stream) {
+  using namespace snerf;
+  const int smem = 65536 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(k_tc_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  k_tc_probe<<<1, 256, smem, (cudaStream_t)stream>>>(out, variant);
+  return finish_launch();
+}
