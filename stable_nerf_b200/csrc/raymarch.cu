@@ -165,11 +165,22 @@ __device__ __forceinline__ bool march_iter(const MarchParams& p, const Ray& r, c
 
 // ------------------------------------------------------------------------------------------------ training march
 //
-// Three launches: count (per-ray sample counts + per-block totals) -> block-offset scan (one block) ->
-// write (re-march; each block rebuilds its rays' offsets with a block scan).  Offsets are therefore the
-// exclusive scan of the counts in ray order: deterministic, unlike raymarching.cu:406-407.
+// Warp per ray.  The reference's loop (raymarching.cu:355-401) walks ONE chain of candidate positions
+//     t_0 = near + clamp(near*dt_gamma)*noise,   t_{k+1} = t_k + clamp(t_k*dt_gamma, dt_min, dt_max)
+// whether a cell is occupied or not: an occupied cell emits a sample and moves to t_{k+1}; an empty cell moves along
+// the same chain until t >= tt (the exit of the voxel), at least one element.  Occupancy therefore only selects WHICH
+// chain elements are tested and emitted, so a warp can test 32 consecutive elements at once (one coalesced round of
+// bitfield lookups instead of 32 dependent ones) and then replay the serial skip logic on ballots:
+//   * every lane runs the 32-step chain (the rounding sequence must be the reference's) and keeps its own element;
+//   * every lane tests its element (cascade level, Morton index, bit test, voxel exit tt);
+//   * the warp walks the lanes in order: runs of occupied lanes are emitted wholesale, an empty lane jumps to the
+//     first later lane with t >= tt (or carries tt into the next round).
+// Three launches: count (per-ray sample counts) -> scan (one block: exclusive offsets in ray order, counter update)
+// -> write (re-march, coalesced sample stores).  Offsets are the exclusive scan of the counts in ray order:
+// deterministic, unlike raymarching.cu:406-407.
 
-constexpr int kMarchThreads = 128;
+constexpr int kMarchThreads = 128;   // 4 rays per block
+constexpr int kMarchRaysPerBlock = kMarchThreads / 32;
 
 __device__ __forceinline__ float ray_t0(const MarchParams& p, float near, float noise) {
   return ffma(clampf(fmul(near, p.dt_gamma), p.dt_min, p.dt_max), noise, near);  // raymarching.cu:352
@@ -192,52 +203,154 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* smem /
   return warp_off + incl - v;
 }
 
+// The occupancy test of one chain element (the reference's while-body up to the branch, raymarching.cu:360-392).
+// Returns true if the cell at t is occupied; (x,y,z,dt) is then the sample.  Otherwise tt = exit of the voxel.
+__device__ __forceinline__ bool march_test(const MarchParams& p, const Ray& r, const uint8_t* __restrict__ grid, float t,
+                                           float& x, float& y, float& z, float& dt, float& tt) {
+  x = clampf(ffma(t, r.dx, r.ox), -p.bound, p.bound);
+  y = clampf(ffma(t, r.dy, r.oy), -p.bound, p.bound);
+  z = clampf(ffma(t, r.dz, r.oz), -p.bound, p.bound);
+  dt = clampf(fmul(t, p.dt_gamma), p.dt_min, p.dt_max);
+  const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+  const int level = max(level_from(mx, p.Cm1), level_from(fmul(fmul(dt, (float)p.H), 0.5f), p.Cm1));
+  const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), p.bound);
+  const float mip_rbound = __frcp_rn(mip_bound);
+  const int nx = (int)clampf(fmul(ffma(x, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);
+  const int ny = (int)clampf(fmul(ffma(y, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);
+  const int nz = (int)clampf(fmul(ffma(z, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);
+  const uint32_t index = (uint32_t)level * p.H3 + morton3D((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+  const bool occ = (__ldg(grid + (index >> 3)) >> (index & 7u)) & 1u;
+  const float vx = fmul(fadd(fadd((float)nx, 0.5f), r.hsx), p.rH);
+  const float vy = fmul(fadd(fadd((float)ny, 0.5f), r.hsy), p.rH);
+  const float vz = fmul(fadd(fadd((float)nz, 0.5f), r.hsz), p.rH);
+  const float tx = fmul(ffma(ffma(vx, 2.0f, -1.0f), mip_bound, -x), r.rdx);
+  const float ty = fmul(ffma(ffma(vy, 2.0f, -1.0f), mip_bound, -y), r.rdy);
+  const float tz = fmul(ffma(ffma(vz, 2.0f, -1.0f), mip_bound, -z), r.rdz);
+  tt = fadd(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+  return occ;
+}
+
+// State of one ray's march, identical in every lane of the warp (all control flow below is warp-uniform).
+struct WarpMarch {
+  float t_base;    // chain element of lane 0 in the next round
+  float resume_t;  // elements with t < resume_t are skipped (an empty cell's voxel exit), -FLT_MAX = none pending
+  float last_t;    // t after the step of the last emitted sample (raymarching.cu:470-472)
+  uint32_t count;  // samples emitted so far
+};
+
+// One round = 32 chain elements.  Returns false when the ray is finished.  emitted = lanes whose element is a sample
+// (in order); my_* describe this lane's element; my_last = last_t seen by this lane's sample.
+__device__ __forceinline__ bool march_round(const MarchParams& p, const Ray& r, const uint8_t* __restrict__ grid, float far,
+                                            uint32_t budget, int lane, WarpMarch& st, uint32_t& emitted, float& x, float& y,
+                                            float& z, float& dt, float& my_next, float& my_last) {
+  // the chain: every lane steps through all 32 elements and keeps its own (t, t_next)
+  float t = st.t_base, my_t = 0.f;
+  my_next = 0.f;
+  if (p.dt_gamma == 0.0f) {  // dt == dt_min: clamp(0, dt_min, dt_max)
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      const float tn = fadd(t, p.dt_min);
+      if (j == lane) { my_t = t; my_next = tn; }
+      t = tn;
+    }
+  } else {
+#pragma unroll 8
+    for (int j = 0; j < 32; j++) {
+      const float tn = fadd(t, clampf(fmul(t, p.dt_gamma), p.dt_min, p.dt_max));
+      if (j == lane) { my_t = t; my_next = tn; }
+      t = tn;
+    }
+  }
+  st.t_base = t;
+  const bool valid = my_t < far;
+  const uint32_t valid_mask = __ballot_sync(kFull, valid);
+  emitted = 0u;
+  if (valid_mask == 0u) return false;
+  float tt = 0.f;
+  bool occ = false;
+  if (valid && my_t >= st.resume_t) occ = march_test(p, r, grid, my_t, x, y, z, dt, tt);
+  const uint32_t occ_mask = __ballot_sync(kFull, occ);
+  // serial replay over the lanes
+  const uint32_t ge0 = __ballot_sync(kFull, valid && my_t >= st.resume_t);
+  uint32_t cur = ge0 ? (uint32_t)__ffs((int)ge0) - 1u : 32u;
+  bool done = false;
+  if (ge0) st.resume_t = -3.402823466e+38f;
+  while (cur < 32u) {
+    if (!((valid_mask >> cur) & 1u)) { done = true; break; }  // t >= far: the reference's loop condition fails
+    if ((occ_mask >> cur) & 1u) {
+      uint32_t run = (uint32_t)__ffs((int)~(occ_mask >> cur)) - 1u;  // consecutive occupied lanes from cur (<= 32-cur)
+      if (run == 0xffffffffu || run > 32u - cur) run = 32u - cur;
+      const uint32_t left = budget - st.count - (uint32_t)__popc(emitted);
+      if (run >= left) { run = left; done = true; }
+      emitted |= (run >= 32u ? 0xffffffffu : ((1u << run) - 1u)) << cur;
+      cur += run;
+      if (done) break;
+    } else {
+      const float tt_cur = __shfl_sync(kFull, tt, (int)cur);
+      const uint32_t later = cur >= 31u ? 0u : (0xffffffffu << (cur + 1u));
+      const uint32_t ge = __ballot_sync(kFull, my_t >= tt_cur) & later;  // lanes past far count: they end the ray
+      if (ge == 0u) { st.resume_t = tt_cur; cur = 32u; }
+      else cur = (uint32_t)__ffs((int)ge) - 1u;
+    }
+  }
+  // last_t bookkeeping: each emitted lane sees the t after the previous emitted sample's step
+  const uint32_t before = emitted & ((1u << lane) - 1u);
+  const int src = before ? 31 - __clz((int)before) : lane;
+  const float prev_next = __shfl_sync(kFull, my_next, src);
+  my_last = before ? prev_next : st.last_t;
+  if (emitted) st.last_t = __shfl_sync(kFull, my_next, 31 - __clz((int)emitted));
+  st.count += (uint32_t)__popc(emitted);
+  return !done && st.count < budget;
+}
+
 __global__ void __launch_bounds__(kMarchThreads) k_march_train_count(MarchParams p, const float* __restrict__ rays_o,
                                                                      const float* __restrict__ rays_d,
                                                                      const uint8_t* __restrict__ grid, uint32_t N,
                                                                      const float* __restrict__ nears,
                                                                      const float* __restrict__ fars,
                                                                      const float* __restrict__ noises,
-                                                                     uint32_t* __restrict__ counts,
-                                                                     uint32_t* __restrict__ block_sums) {
-  __shared__ uint32_t smem[32];
-  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t num_steps = 0;
-  if (n < N) {
-    Ray r;
-    r.load(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
-    const float far = fars[n];
-    float t = ray_t0(p, nears[n], noises[n]);
-    float x, y, z, dt;
-    while (t < far && num_steps < p.max_steps) {
-      if (march_iter(p, r, grid, t, x, y, z, dt)) {
-        num_steps++;
-        t = fadd(t, dt);
-      }
-    }
-    counts[n] = num_steps;
+                                                                     uint32_t* __restrict__ counts) {
+  const uint32_t n = blockIdx.x * kMarchRaysPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  Ray r;
+  r.load(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+  const float far = __ldg(fars + n);
+  WarpMarch st;
+  st.t_base = ray_t0(p, __ldg(nears + n), __ldg(noises + n));
+  st.resume_t = -3.402823466e+38f;
+  st.last_t = st.t_base;
+  st.count = 0;
+  uint32_t emitted;
+  float x, y, z, dt, my_next, my_last;
+  while (march_round(p, r, grid, far, p.max_steps, lane, st, emitted, x, y, z, dt, my_next, my_last)) {
   }
-  uint32_t total;
-  block_excl_scan(num_steps, smem, &total);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+  if (lane == 0) counts[n] = st.count;
 }
 
-// single block: exclusive scan of block_sums in place; counter[0] += total, counter[1] += N
-__global__ void __launch_bounds__(1024) k_march_train_scan(uint32_t* __restrict__ block_sums, uint32_t nblocks,
-                                                           uint32_t N, int32_t* __restrict__ counter) {
+// single block: offsets[n] = exclusive scan of counts (ray order), offsets[N] = total; counter[0] += total,
+// counter[1] += N (what the reference's atomics leave, raymarching.cu:406-407)
+__global__ void __launch_bounds__(1024) k_march_train_scan(const uint32_t* __restrict__ counts, uint32_t N,
+                                                           uint32_t* __restrict__ offsets, int32_t* __restrict__ counter) {
   __shared__ uint32_t smem[32];
   uint32_t carry = 0;
-  for (uint32_t base = 0; base < nblocks; base += blockDim.x) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < nblocks ? block_sums[i] : 0u;
+  for (uint32_t base = 0; base < N; base += blockDim.x * 4u) {
+    const uint32_t i = base + threadIdx.x * 4u;
+    uint32_t c[4];
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) c[k] = i + k < N ? counts[i + k] : 0u;
     uint32_t total;
-    const uint32_t ex = block_excl_scan(v, smem, &total);
-    if (i < nblocks) block_sums[i] = carry + ex;
+    uint32_t ex = carry + block_excl_scan(c[0] + c[1] + c[2] + c[3], smem, &total);
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+      if (i + k < N) offsets[i + k] = ex;
+      ex += c[k];
+    }
     carry += total;
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    block_sums[nblocks] = carry;  // total number of samples, read back by the write pass
+    offsets[N] = carry;  // total number of samples, read back by the write pass
     counter[0] += (int32_t)carry;
     counter[1] += (int32_t)N;
   }
@@ -253,49 +366,50 @@ __device__ __forceinline__ void zero_rows(float* __restrict__ xyzs, float* __res
 __global__ void __launch_bounds__(kMarchThreads) k_march_train_write(
     MarchParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
     uint32_t N, uint32_t M, const float* __restrict__ nears, const float* __restrict__ fars,
-    const float* __restrict__ noises, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ block_offsets,
+    const float* __restrict__ noises, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
     float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas, int32_t* __restrict__ rays,
     int zero_unwritten, int32_t* __restrict__ n_samples_out) {
-  __shared__ uint32_t smem[32];
-  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n == 0 && n_samples_out) *n_samples_out = (int32_t)block_offsets[gridDim.x];
-  if (zero_unwritten) {  // alignment padding: rows [total, M)
-    const uint32_t total = block_offsets[gridDim.x];
-    for (uint32_t i = total + n; i < M; i += gridDim.x * blockDim.x) zero_rows(xyzs, dirs, deltas, i);
-  }
-  const uint32_t num_steps = n < N ? counts[n] : 0u;
-  uint32_t total;
-  const uint32_t point_index = block_offsets[blockIdx.x] + block_excl_scan(num_steps, smem, &total);
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t total = offsets[N];
+  if (gtid == 0 && n_samples_out) *n_samples_out = (int32_t)total;
+  if (zero_unwritten)  // alignment padding: rows [total, M)
+    for (uint32_t i = total + gtid; i < M; i += gridDim.x * blockDim.x) zero_rows(xyzs, dirs, deltas, i);
+  const uint32_t n = blockIdx.x * kMarchRaysPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (n >= N) return;
-  rays[n * 3] = (int32_t)n;
-  rays[n * 3 + 1] = (int32_t)point_index;
-  rays[n * 3 + 2] = (int32_t)num_steps;
+  const uint32_t num_steps = counts[n], point_index = offsets[n];
+  if (lane == 0) {
+    rays[n * 3] = (int32_t)n;
+    rays[n * 3 + 1] = (int32_t)point_index;
+    rays[n * 3 + 2] = (int32_t)num_steps;
+  }
   if (num_steps == 0) return;
   if (point_index + num_steps > M) {  // raymarching.cu:417: overflowing rays are dropped
     if (zero_unwritten)
-      for (uint32_t i = point_index; i < M && i < point_index + num_steps; i++) zero_rows(xyzs, dirs, deltas, i);
+      for (uint32_t i = point_index + lane; i < M && i < point_index + num_steps; i += 32) zero_rows(xyzs, dirs, deltas, i);
     return;
   }
-
   Ray r;
   r.load(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
-  const float far = fars[n];
-  float t = ray_t0(p, nears[n], noises[n]);
-  float last_t = t;
-  float* px = xyzs + (size_t)point_index * 3;
-  float* pd = dirs + (size_t)point_index * 3;
-  float2* pl = reinterpret_cast<float2*>(deltas) + point_index;
-  uint32_t step = 0;
-  float x, y, z, dt;
-  while (t < far && step < num_steps) {
-    if (march_iter(p, r, grid, t, x, y, z, dt)) {
+  const float far = __ldg(fars + n);
+  WarpMarch st;
+  st.t_base = ray_t0(p, __ldg(nears + n), __ldg(noises + n));
+  st.resume_t = -3.402823466e+38f;
+  st.last_t = st.t_base;
+  st.count = 0;
+  bool more = true;
+  while (more) {
+    const uint32_t before_count = st.count;
+    uint32_t emitted;
+    float x, y, z, dt, my_next, my_last;
+    more = march_round(p, r, grid, far, num_steps, lane, st, emitted, x, y, z, dt, my_next, my_last);
+    if ((emitted >> lane) & 1u) {
+      const size_t row = (size_t)point_index + before_count + (uint32_t)__popc(emitted & ((1u << lane) - 1u));
+      float* px = xyzs + row * 3;
+      float* pd = dirs + row * 3;
       px[0] = x; px[1] = y; px[2] = z;
       pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
-      t = fadd(t, dt);
-      *pl = make_float2(dt, fadd(t, -last_t));
-      last_t = t;
-      px += 3; pd += 3; pl += 1;
-      step++;
+      reinterpret_cast<float2*>(deltas)[row] = make_float2(dt, fadd(my_next, -my_last));
     }
   }
 }
@@ -432,12 +546,12 @@ int snerf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t*
   return finish_launch();
 }
 
-size_t snerf_march_rays_train_workspace_bytes(uint32_t N) {
-  const size_t nblocks = div_up(N ? N : 1, kMarchThreads);
-  return align_up((size_t)(N ? N : 1) * sizeof(uint32_t), 256) + align_up((nblocks + 1) * sizeof(uint32_t), 256);
+size_t snerf_march_rays_train_workspace_bytes(uint32_t N) {  // counts [N] | offsets [N+1]
+  const size_t n = N ? N : 1;
+  return align_up(n * sizeof(uint32_t), 256) + align_up((n + 1) * sizeof(uint32_t), 256);
 }
 
-static uint32_t* ws_block_sums(void* workspace, uint32_t N) {
+static uint32_t* ws_offsets(void* workspace, uint32_t N) {
   return (uint32_t*)((char*)workspace + align_up((size_t)N * sizeof(uint32_t), 256));
 }
 
@@ -451,11 +565,10 @@ int snerf_march_rays_train_count(const float* rays_o, const float* rays_d, const
   MarchParams p;
   if (int e = make_march_params(&p, bound, dt_gamma, max_steps, C, H)) return e;
   uint32_t* counts = (uint32_t*)workspace;
-  uint32_t* block_sums = ws_block_sums(workspace, N);
-  const uint32_t nblocks = div_up(N, kMarchThreads);
+  const uint32_t nblocks = div_up(N, kMarchRaysPerBlock);
   cudaStream_t s = (cudaStream_t)stream;
-  k_march_train_count<<<nblocks, kMarchThreads, 0, s>>>(p, rays_o, rays_d, grid, N, nears, fars, noises, counts, block_sums);
-  k_march_train_scan<<<1, 1024, 0, s>>>(block_sums, nblocks, N, counter);
+  k_march_train_count<<<nblocks, kMarchThreads, 0, s>>>(p, rays_o, rays_d, grid, N, nears, fars, noises, counts);
+  k_march_train_scan<<<1, 1024, 0, s>>>(counts, N, ws_offsets(workspace, N), counter);
   return finish_launch(2);
 }
 
@@ -471,9 +584,9 @@ int snerf_march_rays_train_write(const float* rays_o, const float* rays_d, const
   if ((uintptr_t)deltas & 7u) return SNERF_E_BADARG;
   MarchParams p;
   if (int e = make_march_params(&p, bound, dt_gamma, max_steps, C, H)) return e;
-  const uint32_t nblocks = div_up(N, kMarchThreads);
+  const uint32_t nblocks = div_up(N, kMarchRaysPerBlock);
   k_march_train_write<<<nblocks, kMarchThreads, 0, (cudaStream_t)stream>>>(
-      p, rays_o, rays_d, grid, N, M, nears, fars, noises, (const uint32_t*)workspace, ws_block_sums(workspace, N), xyzs,
+      p, rays_o, rays_d, grid, N, M, nears, fars, noises, (const uint32_t*)workspace, ws_offsets(workspace, N), xyzs,
       dirs, deltas, rays, zero_unwritten, n_samples_out);
   return finish_launch();
 }
