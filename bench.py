@@ -302,18 +302,21 @@ def run_gpu_arm(args):
 
     if rank == 0 and not args.no_stages:
         pk = peaks()
-        st, ns, M = stage_times(model, ts)
+        local_step = model.local_step
+        st, ns, M = ts.profile_stages() if ts.fused else stage_times(model, ts)
+        model.local_step = local_step
         out["stages_ms"] = {k: round(v, 4) for k, v in st.items()}
         C = CHANNELS
         alg = {  # algorithmic bytes / flops per launch (SURVEY section 8d figures)
             "near_far": ("hbm", 32.0 * RAYS_PER_GPU),
             "march": ("hbm", 48.0 * RAYS_PER_GPU + 32.0 * ns),
             "composite_fwd": ("hbm", (12 + 4 * C) * ns + (20 + 4 * C) * RAYS_PER_GPU),
+            "composite_bwd": ("hbm", (16 + 8 * C) * ns + (20 + 8 * C) * RAYS_PER_GPU),
             "loss+composite_bwd": ("hbm", (16 + 8 * C) * ns + (20 + 8 * C) * RAYS_PER_GPU),
             "field_fwd": ("tensor", 188416.0 * M),
             "field_bwd": ("tensor", 565248.0 * M),  # recompute + dgrad + wgrad
         }
-        dom = max(st, key=st.get)
+        dom = max((k for k in st if k in alg), key=st.get)
         bound, work = alg[dom]
         t = st[dom] * 1e-3
         if bound == "hbm":

@@ -132,6 +132,17 @@ int snerf_composite_rays_train_backward_ex(const float* grad_weights_sum, const 
                                            float* grad_sigmas, float* grad_rgbs, const int32_t* n_samples,
                                            snerf_stream_t stream);
 
+/* The step right after the path in training (train.py:61-70 -> utils/loss_utils.py:9-10 l1_loss -> backward), as one
+ * launch: pred = image + (1 - weights_sum) * bg (nerf/renderer.py:111), *loss = mean |pred - target|,
+ * grad_image = grad_scale * sign(pred - target), grad_weights_sum = -sum_c grad_image_c * bg_c  -- the inputs of
+ * snerf_composite_rays_train_backward.  bg_color: C device floats, or NULL for the scalar bg_scalar.
+ * grad_scale = loss_scale / (N * channel_dim) for the mean.  Optional outputs (NULL to skip): pred_image [N,C] (the
+ * blended image render() returns) and depth_norm [N] = clamp(depth - nears, 0) / (fars - nears) (nerf/renderer.py:112). */
+int snerf_l1_loss_backward(const float* image, const float* weights_sum, const float* target, const float* bg_color,
+                           float bg_scalar, uint32_t N, uint32_t channel_dim, float grad_scale, float* loss,
+                           float* grad_image, float* grad_weights_sum, float* pred_image, const float* depth,
+                           const float* nears, const float* fars, float* depth_norm, snerf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Inference march + compositing + compaction  (reference: raymarching.h:17-18, nerf/renderer.py:158)
  * ---------------------------------------------------------------------------------------------- */

@@ -64,6 +64,7 @@ SIGNATURES = {
     "snerf_composite_rays_train_forward": (c_int, [_P, _P, _P, _P, _U, _U, _F, _U, _P, _P, _P, _S]),
     "snerf_composite_rays_train_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _F, _U, _P, _P, _S]),
     "snerf_composite_rays_train_backward_ex": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _F, _U, _P, _P, _P, _S]),
+    "snerf_l1_loss_backward": (c_int, [_P, _P, _P, _P, _F, _U, _U, _F, _P, _P, _P, _P, _P, _P, _P, _P, _S]),
     "snerf_march_rays": (c_int, [_U, _U, _P, _P, _P, _P, _F, _F, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _S]),
     "snerf_composite_rays": (c_int, [_U, _U, _F, _U, _P, _P, _P, _P, _P, _P, _P, _P, _S]),
     "snerf_compact_rays_workspace_bytes": (c_size_t, [_U]),

@@ -197,6 +197,61 @@ __global__ void __launch_bounds__(256) k_zero_tail(const int32_t* __restrict__ n
   }
 }
 
+// ------------------------------------------------------------------------------------------------ L1 loss + its gradient
+//
+// The step right after the path in training (train.py:61-70 forward_iteration -> utils/loss_utils.py:9-10 l1_loss ->
+// backward): pred = image + (1 - weights_sum) * bg (nerf/renderer.py:111), loss = mean |pred - target|, and the
+// gradients the compositing backward consumes.  One block, fixed summation order: the loss is reproducible.
+template <int C>
+__global__ void __launch_bounds__(1024) k_l1_loss_backward(const float* __restrict__ image,
+                                                           const float* __restrict__ weights_sum,
+                                                           const float* __restrict__ target,
+                                                           const float* __restrict__ bg_color, float bg_scalar, uint32_t N,
+                                                           float grad_scale, float* __restrict__ loss,
+                                                           float* __restrict__ grad_image,
+                                                           float* __restrict__ grad_weights_sum,
+                                                           float* __restrict__ pred_image,
+                                                           const float* __restrict__ depth,
+                                                           const float* __restrict__ nears,
+                                                           const float* __restrict__ fars,
+                                                           float* __restrict__ depth_norm) {
+  __shared__ float part[32];
+  float bg[C];
+#pragma unroll
+  for (int k = 0; k < C; k++) bg[k] = bg_color ? __ldg(bg_color + k) : bg_scalar;
+  float acc = 0.f;
+  for (uint32_t n = threadIdx.x; n < N; n += blockDim.x) {
+    const float om = 1.0f - __ldg(weights_sum + n);
+    float img[C], tgt[C], g[C], gws = 0.f;
+    load_rgb<C>(image, n, img);
+    load_rgb<C>(target, n, tgt);
+#pragma unroll
+    for (int k = 0; k < C; k++) img[k] += om * bg[k];  // nerf/renderer.py:111
+    if (pred_image) store_rgb<C>(pred_image, n, img);
+    if (depth_norm) {  // nerf/renderer.py:112
+      const float nr = __ldg(nears + n);
+      depth_norm[n] = fmaxf(__ldg(depth + n) - nr, 0.f) / (__ldg(fars + n) - nr);
+    }
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+      const float d = img[k] - tgt[k];
+      acc += fabsf(d);
+      g[k] = d > 0.f ? grad_scale : (d < 0.f ? -grad_scale : 0.f);
+      gws -= g[k] * bg[k];
+    }
+    store_rgb<C>(grad_image, n, g);
+    grad_weights_sum[n] = gws;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) *loss = v / ((float)N * (float)C);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ inference
 //
 // n_step <= 8 samples per alive ray per call (nerf/renderer.py:146): a thread per ray is the right grain; the
@@ -315,6 +370,19 @@ int snerf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, uint
   SNERF_DISPATCH_C(channel_dim, (k_composite_rays<kC><<<div_up(n_alive, 128), 128, 0, (cudaStream_t)stream>>>(
                                     n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum,
                                     depth, image)));
+  return finish_launch();
+}
+
+int snerf_l1_loss_backward(const float* image, const float* weights_sum, const float* target, const float* bg_color,
+                           float bg_scalar, uint32_t N, uint32_t channel_dim, float grad_scale, float* loss,
+                           float* grad_image, float* grad_weights_sum, float* pred_image, const float* depth,
+                           const float* nears, const float* fars, float* depth_norm, snerf_stream_t stream) {
+  if (N == 0) return SNERF_OK;
+  if (!image || !weights_sum || !target || !loss || !grad_image || !grad_weights_sum) return SNERF_E_BADARG;
+  if (depth_norm && (!depth || !nears || !fars)) return SNERF_E_BADARG;
+  SNERF_DISPATCH_C(channel_dim, (k_l1_loss_backward<kC><<<1, 1024, 0, (cudaStream_t)stream>>>(
+                                    image, weights_sum, target, bg_color, bg_scalar, N, grad_scale, loss, grad_image,
+                                    grad_weights_sum, pred_image, depth, nears, fars, depth_norm)));
   return finish_launch();
 }
 

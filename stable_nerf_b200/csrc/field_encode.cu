@@ -65,6 +65,25 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_fwd(snerf_grid_desc g,
   }
 }
 
+// Backward: scatter-add of (sample, level) gradients into the table.  The SM retires about one reduction LANE per
+// cycle (REDG, measured), so the kernel is organised to issue fewer lanes, not fewer bytes:
+//   * a warp works on 32 consecutive samples of one level; consecutive samples of a ray fall into the same cell at the
+//     coarse levels, so runs of lanes with equal (index0, index1) are summed with a segmented warp scan first and only
+//     the last lane of a run issues the reduction (levels with resolution <= kDedupeMaxRes);
+//   * the two corners that differ in x are adjacent entries whenever index0 is even (always for a hashed level with
+//     even x: x ^ h and (x+1) ^ h differ in bit 0 only): one 16-byte red.global.add.v4.f32 instead of two v2's;
+//   * samples whose gradient is exactly zero (padding, terminated rays) issue nothing.
+constexpr uint32_t kDedupeMaxRes = 600;
+
+__device__ __forceinline__ void red_pair(float2* __restrict__ grad_table, uint32_t i0, uint32_t i1, float4 v) {
+  if (i1 == i0 + 1u && (i0 & 1u) == 0u) {
+    atomicAdd(reinterpret_cast<float4*>(grad_table + i0), v);
+  } else {
+    atomicAdd(grad_table + i0, make_float2(v.x, v.y));
+    atomicAdd(grad_table + i1, make_float2(v.z, v.w));
+  }
+}
+
 template <bool kNormalize>
 __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g, const float* __restrict__ x,
                                                               float bound, const float* __restrict__ grad_enc,
@@ -74,6 +93,7 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g,
   const uint32_t m0 = blockIdx.x * kEncTile;
   const uint32_t ns = min((uint32_t)kEncTile, M - m0);
   const uint32_t L = g.n_levels;
+  const int lane = threadIdx.x & 31;
   for (uint32_t i = threadIdx.x; i < ns * 3; i += kEncThreads) {
     float v = __ldg(x + (size_t)m0 * 3 + i);
     if (kNormalize) v = __fdiv_rn(fadd(v, bound), fmul(2.0f, bound));
@@ -82,18 +102,41 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g,
   const float2* gin = reinterpret_cast<const float2*>(grad_enc) + (size_t)m0 * L;
   for (uint32_t i = threadIdx.x; i < ns * L; i += kEncThreads) tile[tile_slot(i / L, i % L)] = __ldg(gin + i);
   __syncthreads();
+  // kEncTile is a multiple of 32: a warp's 32 items share the level, so everything below is warp-uniform control flow
   for (uint32_t item = threadIdx.x; item < kEncTile * L; item += kEncThreads) {
     const uint32_t s = item % kEncTile, l = item / kEncTile;
-    if (s >= ns) continue;
-    const float2 gv = tile[tile_slot(s, l)];
-    if (gv.x == 0.f && gv.y == 0.f) continue;  // padded / terminated samples carry exact zeros
+    float2 gv = make_float2(0.f, 0.f);
+    if (s < ns) gv = tile[tile_slot(s, l)];
+    const bool active = gv.x != 0.f || gv.y != 0.f;  // padded / terminated samples carry exact zeros
+    if (__ballot_sync(kFull, active) == 0u) continue;
     const LevelInfo li = level_info(g, l);
-    const Cell c = grid_cell(xs[s * 3], xs[s * 3 + 1], xs[s * 3 + 2], li.scale);
+    const uint32_t sc = s < ns ? s : 0u;
+    const Cell c = grid_cell(xs[sc * 3], xs[sc * 3 + 1], xs[sc * 3 + 2], li.scale);
+    const bool dedupe = li.res <= kDedupeMaxRes;
 #pragma unroll
-    for (uint32_t k = 0; k < 8; k++) {
-      const float wt = corner_weight(c, k);
-      const uint32_t idx = grid_index(li, c.c[0] + (k & 1u), c.c[1] + ((k >> 1) & 1u), c.c[2] + (k >> 2));
-      atomicAdd(grad_table + idx, make_float2(wt * gv.x, wt * gv.y));
+    for (uint32_t kp = 0; kp < 4; kp++) {  // corner pair (x, x+1) at (y + kp&1, z + kp>>1)
+      const uint32_t cy = c.c[1] + (kp & 1u), cz = c.c[2] + (kp >> 1);
+      uint32_t i0 = grid_index(li, c.c[0], cy, cz), i1 = grid_index(li, c.c[0] + 1u, cy, cz);
+      const float w0 = corner_weight(c, kp * 2u), w1 = corner_weight(c, kp * 2u + 1u);
+      float4 v = make_float4(w0 * gv.x, w0 * gv.y, w1 * gv.x, w1 * gv.y);
+      if (!dedupe) {
+        if (active) red_pair(grad_table, i0, i1, v);
+        continue;
+      }
+      if (!active) { i0 = 0xffffffffu - (uint32_t)lane; i1 = i0; }  // a run of its own, value zero
+      const uint32_t p0 = __shfl_up_sync(kFull, i0, 1), p1 = __shfl_up_sync(kFull, i1, 1);
+      const bool head = lane == 0 || p0 != i0 || p1 != i1;
+      bool f = head;  // a run head lies inside the span summed so far
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float ux = __shfl_up_sync(kFull, v.x, d), uy = __shfl_up_sync(kFull, v.y, d);
+        const float uz = __shfl_up_sync(kFull, v.z, d), uw = __shfl_up_sync(kFull, v.w, d);
+        const bool uf = __shfl_up_sync(kFull, (int)f, d) != 0;
+        if (lane >= d && !f) { v.x += ux; v.y += uy; v.z += uz; v.w += uw; f = uf; }
+      }
+      const bool next_head = __shfl_down_sync(kFull, (int)head, 1) != 0;
+      const bool tail = lane == 31 || next_head;
+      if (tail && active) red_pair(grad_table, i0, i1, v);
     }
   }
 }

@@ -103,7 +103,7 @@ struct TcParams {
   const float* grad_rgbs;
   float* g_geo;          // [M,16] fp32: d loss / d geo (cols 0..14) written by the colour bwd, read by the sigma bwd
   float* grad_w;         // fp32 gradient of this net's flat matrices (accumulated)
-  float2* grad_table;    // fp32 gradient of the hash table (accumulated)
+  float* d_enc;          // [M,32] fp32: d loss / d encoding, written by the sigma bwd, scattered by k_hashgrid_bwd
   long long* dbg;        // optional phase-timing buffer (snerf_debug_phase_buffer): clock64 marks of CTA 0, 2nd tile
 };
 
@@ -670,22 +670,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
               gg[2] = make_float4(v[8], v[9], v[10], v[11]);
               gg[3] = make_float4(v[12], v[13], v[14], 0.f);
             }
-          } else {  // scatter-add of levels 8hc .. 8hc+7 into the table gradient
-            const float x = norm01(__ldg(p.xyzs + (size_t)m * 3), p.bound), y = norm01(__ldg(p.xyzs + (size_t)m * 3 + 1), p.bound),
-                        z = norm01(__ldg(p.xyzs + (size_t)m * 3 + 2), p.bound);
-#pragma unroll 2
-            for (uint32_t j = 0; j < 8; j++) {
-              const float gx = v[2 * j], gy = v[2 * j + 1];
-              if (gx == 0.f && gy == 0.f) continue;
-              const LevelInfo li = level_info(p.grid, hc * 8u + j);
-              const Cell c = grid_cell(x, y, z, li.scale);
-#pragma unroll
-              for (uint32_t k = 0; k < 8; k++) {
-                const float wt = corner_weight(c, k);
-                atomicAdd(p.grad_table + grid_index(li, c.c[0] + (k & 1u), c.c[1] + ((k >> 1) & 1u), c.c[2] + (k >> 2)),
-                          make_float2(wt * gx, wt * gy));
-              }
-            }
+          } else {  // d loss / d encoding, columns 16hc .. 16hc+15: scattered into the table by k_hashgrid_bwd
+            float4* ge = reinterpret_cast<float4*>(p.d_enc + (size_t)m * 32 + hc * 16u);
+            ge[0] = make_float4(v[0], v[1], v[2], v[3]);
+            ge[1] = make_float4(v[4], v[5], v[6], v[7]);
+            ge[2] = make_float4(v[8], v[9], v[10], v[11]);
+            ge[3] = make_float4(v[12], v[13], v[14], v[15]);
           }
         }
       }
@@ -732,6 +722,7 @@ struct TcWorkspace {
   __nv_bfloat16* geo;
   __nv_bfloat16* enc;
   float* g_geo;
+  float* d_enc;
 };
 
 // forward -> backward hand-off buffer: [geo: M x 16 bf16][pad to 1 KiB][enc: M x 32 bf16]
@@ -755,6 +746,7 @@ static size_t carve_tc(const snerf_field_desc* f, uint32_t M, int backward, char
   o.geo = (__nv_bfloat16*)hand;
   o.enc = (__nv_bfloat16*)(hand ? hand + saved_geo_bytes(M) : nullptr);
   o.g_geo = backward ? (float*)take((size_t)(M ? M : 1) * 16 * sizeof(float)) : nullptr;
+  o.d_enc = backward ? (float*)take((size_t)(M ? M : 1) * 32 * sizeof(float)) : nullptr;
   return off;
 }
 
@@ -905,9 +897,11 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   p.grad_sigmas = grad_sigmas;
   p.g_geo = w.g_geo;
   p.grad_w = grad_w_sigma;
-  p.grad_table = reinterpret_cast<float2*>(grad_table);
+  p.d_enc = w.d_enc;
   p.dbg = g_phase_net == 0 ? g_phase_dbg : nullptr;
   if (int e = launch_bwd<0>(p, ps, M, s)) return e;
+  // 4. table scatter-add of d loss / d encoding (its own kernel: full occupancy, warp-level merging of equal cells)
+  if (int e = launch_hashgrid_bwd(&f->grid, xyzs, true, f->bound, w.d_enc, M, grad_table, s)) return e;
   return finish_launch(launches);
 }
 

@@ -15,6 +15,8 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from .field import _precision_code
+from .raymarching import _pad_up
 
 
 def shard_range(n, rank, world):
@@ -62,10 +64,13 @@ class TrainStep:
     """
 
     def __init__(self, model, n_rays, max_steps=1024, bg_color=1, T_thresh=1e-4, use_graph=True, world_size=1,
-                 loss_scale=1.0):
+                 loss_scale=1.0, fused=True, perturb=False, dt_gamma=0):
         self.model, self.n_rays, self.max_steps = model, int(n_rays), int(max_steps)
         self.bg_color, self.T_thresh, self.world_size = bg_color, T_thresh, world_size
         self.loss_scale = loss_scale
+        self.fused, self.perturb, self.dt_gamma = bool(fused), bool(perturb), dt_gamma
+        self._bufs = None
+        self._mark = None
         dev = next(model.parameters()).device
         C = model.channel_dim
         self.rays_o = torch.zeros(self.n_rays, 3, device=dev)
@@ -83,13 +88,131 @@ class TrainStep:
 
     def _body(self):
         m = self.model
+        if self.fused and m.training and m.mean_count > 0 and m.bg_radius <= 0 and hasattr(m, "fdesc"):
+            return self._body_fused()
         for p in self.params:
             p.grad.zero_()
         out = m.render(self.rays_o[None], self.rays_d[None], bg_color=self.bg_color, max_steps=self.max_steps,
-                       T_thresh=self.T_thresh)
+                       T_thresh=self.T_thresh, perturb=self.perturb, dt_gamma=self.dt_gamma)
         loss = (out['image'].view(-1, m.channel_dim) - self.target).abs().mean()  # utils/loss_utils.py:9-10 l1_loss
         (loss * self.loss_scale).backward()
         self.loss.copy_(loss.detach())
+
+    def _fused_buffers(self, M):
+        """Every array of the fused step, allocated once per (M): a captured graph replays on fixed addresses."""
+        if self._bufs is not None and self._bufs["M"] == M:
+            return self._bufs
+        m, N, C = self.model, self.n_rays, self.model.channel_dim
+        dev = self.rays_o.device
+        lib = _lib.load()
+        prec = _precision_code(m.precision)
+        f32 = dict(dtype=torch.float32, device=dev)
+        e = lambda *shape: torch.empty(*shape, **f32)
+        b = dict(M=M, nears=e(N), fars=e(N), noises=torch.zeros(N, **f32), rays=torch.empty(N, 3, dtype=torch.int32, device=dev),
+                 n_samples=torch.empty(1, dtype=torch.int32, device=dev), xyzs=e(M, 3), dirs=e(M, 3), deltas=e(M, 2),
+                 sigmas=e(M), rgbs=e(M, C), ws=e(N), depth=e(N), image=e(N, C), g_img=e(N, C), g_ws=e(N), g_sig=e(M),
+                 g_rgb=e(M, C), pred=e(N, C), depth_norm=e(N))
+        b["march_ws_bytes"] = lib.snerf_march_rays_train_workspace_bytes(N)
+        b["march_ws"] = torch.empty(b["march_ws_bytes"], dtype=torch.uint8, device=dev)
+        b["field_ws_bytes"] = max(lib.snerf_field_workspace_bytes(m.fdesc, M, prec, 0),
+                                  lib.snerf_field_workspace_bytes(m.fdesc, M, prec, 1))
+        b["field_ws"] = torch.empty(max(b["field_ws_bytes"], 256), dtype=torch.uint8, device=dev)
+        b["saved_bytes"] = lib.snerf_field_saved_bytes(m.fdesc, M, prec)
+        b["saved"] = torch.empty(b["saved_bytes"], dtype=torch.uint8, device=dev) if b["saved_bytes"] else None
+        bg = self.bg_color
+        b["bg"] = bg.to(**f32).contiguous().view(-1) if torch.is_tensor(bg) else None
+        b["bg_scalar"] = 1.0 if bg is None else (0.0 if torch.is_tensor(bg) else float(bg))
+        self._bufs = b
+        return b
+
+    def _body_fused(self):
+        """The same step as a straight sequence of C-ABI calls: no autograd graph, no torch glue kernels.
+        near/far -> march (count, scan, write) -> field forward -> composite forward -> L1 loss + its gradient
+        (one launch: background blend, depth normalisation, loss, d loss/d image, d loss/d weights_sum) ->
+        composite backward -> field backward (accumulates straight into the parameters' .grad).
+        Call pattern of train.py:61-70 / nerf/renderer.py:75-114."""
+        m, N, C = self.model, self.n_rays, self.model.channel_dim
+        lib = _lib.load()
+        P, S, chk = _lib.ptr, _lib.stream(), _lib.check
+        prec = _precision_code(m.precision)
+        M = _pad_up(int(m.mean_count), 128)
+        b = self._fused_buffers(M)
+        sp, cp = m.sigma_net.params, m.color_net.params
+        nm = m.sigma_net.n_mlp
+        mark = self._mark or (lambda name: None)
+        mark("start")
+        for p in self.params:
+            p.grad.zero_()
+        counter = m.step_counter[m.local_step % 16]
+        counter.zero_()
+        m.local_step += 1
+        if self.perturb:
+            b["noises"].uniform_()
+        mark("zero_grads")
+        chk(lib.snerf_near_far_from_aabb(P(self.rays_o), P(self.rays_d), P(m.aabb_train), N, float(m.min_near),
+                                         P(b["nears"]), P(b["fars"]), S), "near_far_from_aabb")
+        mark("near_far")
+        geom = (float(m.bound), float(self.dt_gamma), int(self.max_steps), N, int(m.cascade), int(m.grid_size))
+        chk(lib.snerf_march_rays_train_count(P(self.rays_o), P(self.rays_d), P(m.density_bitfield), *geom, P(b["nears"]),
+                                             P(b["fars"]), P(counter), P(b["noises"]), P(b["march_ws"]),
+                                             b["march_ws_bytes"], S), "march count")
+        chk(lib.snerf_march_rays_train_write(P(self.rays_o), P(self.rays_d), P(m.density_bitfield), *geom, M,
+                                             P(b["nears"]), P(b["fars"]), P(b["xyzs"]), P(b["dirs"]), P(b["deltas"]),
+                                             P(b["rays"]), P(b["noises"]), 1, P(b["n_samples"]), P(b["march_ws"]),
+                                             b["march_ws_bytes"], S), "march write")
+        mark("march")
+        spd = sp.detach()
+        chk(lib.snerf_field_forward(m.fdesc, P(b["xyzs"]), P(b["dirs"]), M, P(spd[nm:]), P(spd[:nm]), P(cp.detach()), prec,
+                                    P(b["sigmas"]), P(b["rgbs"]), P(b["saved"]), b["saved_bytes"], P(b["field_ws"]),
+                                    b["field_ws_bytes"], S), "field forward")
+        if m.density_scale != 1:
+            b["sigmas"].mul_(m.density_scale)
+        mark("field_fwd")
+        chk(lib.snerf_composite_rays_train_forward(P(b["sigmas"]), P(b["rgbs"]), P(b["deltas"]), P(b["rays"]), M, N,
+                                                   float(self.T_thresh), C, P(b["ws"]), P(b["depth"]), P(b["image"]), S),
+            "composite forward")
+        mark("composite_fwd")
+        chk(lib.snerf_l1_loss_backward(P(b["image"]), P(b["ws"]), P(self.target), P(b["bg"]), b["bg_scalar"], N, C,
+                                       float(self.loss_scale) / (N * C), P(self.loss), P(b["g_img"]), P(b["g_ws"]),
+                                       P(b["pred"]), P(b["depth"]), P(b["nears"]), P(b["fars"]), P(b["depth_norm"]), S),
+            "l1 loss")
+        mark("loss")
+        chk(lib.snerf_composite_rays_train_backward_ex(P(b["g_ws"]), P(b["g_img"]), P(b["sigmas"]), P(b["rgbs"]),
+                                                       P(b["deltas"]), P(b["rays"]), P(b["ws"]), P(b["image"]), M, N,
+                                                       float(self.T_thresh), C, P(b["g_sig"]), P(b["g_rgb"]),
+                                                       P(b["n_samples"]), S), "composite backward")
+        if m.density_scale != 1:
+            b["g_sig"].mul_(m.density_scale)
+        mark("composite_bwd")
+        chk(lib.snerf_field_backward(m.fdesc, P(b["xyzs"]), P(b["dirs"]), M, P(spd[nm:]), P(spd[:nm]), P(cp.detach()),
+                                     P(b["g_sig"]), P(b["g_rgb"]), prec, P(sp.grad[nm:]), P(sp.grad[:nm]), P(cp.grad),
+                                     P(b["saved"]), b["saved_bytes"], P(b["field_ws"]), b["field_ws_bytes"], S),
+            "field backward")
+        mark("field_bwd")
+        self.outputs = {"image": b["pred"], "depth": b["depth_norm"], "weights_sum": b["ws"]}
+
+    def profile_stages(self, iters=10):
+        """Device time of each stage of the fused step (CUDA events on the launch stream, eager launches): returns
+        ({stage: ms}, n_samples, M)."""
+        acc = {}
+        for it in range(iters + 2):
+            evs = []
+
+            def mark(name):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                evs.append((name, e))
+            self._mark = mark
+            try:
+                self._body_fused()
+            finally:
+                self._mark = None
+            torch.cuda.synchronize()
+            if it >= 2:
+                for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
+                    acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1) / iters
+        n_samples = int(self._bufs["n_samples"].item())
+        return acc, n_samples, self._bufs["M"]
 
     def warmup(self, rays_o, rays_d, target, iters=3):
         """Reference-style first steps on the synchronising path, then ``mean_count`` from the measured sample

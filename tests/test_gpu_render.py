@@ -182,3 +182,39 @@ def test_cuda_graph_train_step_matches_eager(built_lib, cuda):
     assert rel_err(res[True][1].cpu().numpy(), res[False][1].cpu().numpy()) <= 1e-4
     h = [torch.from_numpy(a).pin_memory() for a in (ro, rd, tgt)]
     assert abs(ts.step_from_host(*h) - res[True][0]) <= 1e-6
+
+
+@pytest.mark.parametrize("precision,C,bg", [("fp32", 3, 1), ("bf16", 3, 1), ("fp32", 4, "tensor")])
+def test_fused_train_step_matches_autograd_step(precision, C, bg, built_lib, cuda):
+    """TrainStep's fused body (a straight sequence of C-ABI calls with the L1 loss kernel) against the same step through
+    NeRFNetwork.render + torch autograd: same loss, same gradients, same render outputs."""
+    from stable_nerf_b200 import NeRFNetwork, synthetic as syn
+    from stable_nerf_b200.trainer import TrainStep
+    ro, rd = syn.train_batch(640, 100, 100, 138.0, n_views=2, seed=9)
+    tgt = np.random.default_rng(1).random((640, C), dtype=np.float32)
+    grid = syn.occupancy_grid(lego_like=True)
+    res = {}
+    for fused in (False, True):
+        model = NeRFNetwork(channel_dim=C, precision=precision, density_scale=1 if C == 3 else 2).to(cuda)
+        with torch.no_grad():
+            model.sigma_net.params[model.sigma_net.n_mlp:] *= 1e4
+        model.density_bitfield.copy_(torch.from_numpy(syn.pack_bitfield(grid)))
+        model.train()
+        bg_color = torch.tensor([0.2, 0.4, 0.6, 1.0], device=cuda) if bg == "tensor" else bg
+        ts = TrainStep(model, 640, max_steps=128, use_graph=False, fused=fused, bg_color=bg_color, loss_scale=0.5)
+        t = [torch.from_numpy(a).to(cuda) for a in (ro, rd, tgt)]
+        ts.warmup(*t)
+        loss = ts.step(*t)
+        torch.cuda.synchronize()
+        assert (getattr(ts, "outputs", None) is not None) == fused
+        res[fused] = (float(loss), model.sigma_net.params.grad.cpu().numpy().copy(),
+                      model.color_net.params.grad.cpu().numpy().copy())
+        if fused:
+            model.eval_outputs = None
+            out = {k: v.clone() for k, v in ts.outputs.items()}
+            ref = model.render(t[0][None], t[1][None], bg_color=bg_color, max_steps=128)
+            assert rel_err(out["image"].cpu().numpy(), ref["image"].view(-1, C).detach().cpu().numpy()) <= 1e-5
+            assert rel_err(out["depth"].cpu().numpy(), ref["depth"].view(-1).detach().cpu().numpy()) <= 1e-5
+    tol = 1e-4 if precision == "fp32" else 2e-3  # bf16: atomics order feeds bf16 roundings downstream
+    assert abs(res[True][0] - res[False][0]) <= 1e-6 * abs(res[False][0])
+    assert rel_err(res[True][1], res[False][1]) <= tol and rel_err(res[True][2], res[False][2]) <= tol
