@@ -141,10 +141,10 @@ __device__ __forceinline__ float norm01(float v, float bound) { return __fdiv_rn
 
 // The 32-column input operand of sample m is 4 groups of 8 columns.  NET 0: group g = hash-grid levels 4g..4g+3;
 // NET 1: groups 0,1 = SH-4 of the direction, groups 2,3 = the 15 geometry features + a zero pad.
-// Writes groups [G0, G0+NG) of row `row` into chunk 0 of tile a0 (zeros for rows past M).
+// fetch_input produces groups [G0, G0+NG) of sample m in registers (zeros for rows past M); store_input writes them
+// into row `row` of chunk 0 of tile a0.  Split so that the global loads can be issued long before the tile needs them.
 template <int NET, int G0, int NG, bool kFromSaved>
-__device__ __forceinline__ void load_input(const TcParams& p, uint32_t m, uint32_t row, uint8_t* a0) {
-  uint4 out[NG];
+__device__ __forceinline__ void fetch_input(const TcParams& p, uint32_t m, uint4 (&out)[NG]) {
 #pragma unroll
   for (int g = 0; g < NG; g++) out[g] = make_uint4(0u, 0u, 0u, 0u);
   if (m < p.M) {
@@ -182,10 +182,19 @@ __device__ __forceinline__ void load_input(const TcParams& p, uint32_t m, uint32
       }
     }
   }
+}
+template <int G0, int NG>
+__device__ __forceinline__ void store_input(const uint4 (&out)[NG], uint32_t row, uint8_t* a0) {
   uint8_t* rp = a0 + row_off(row);
   const uint32_t r7 = row & 7u;
 #pragma unroll
   for (int g = 0; g < NG; g++) *reinterpret_cast<uint4*>(rp + (((uint32_t)(G0 + g) ^ r7) << 4)) = out[g];
+}
+template <int NET, int G0, int NG, bool kFromSaved>
+__device__ __forceinline__ void load_input(const TcParams& p, uint32_t m, uint32_t row, uint8_t* a0) {
+  uint4 out[NG];
+  fetch_input<NET, G0, NG, kFromSaved>(p, m, out);
+  store_input<G0, NG>(out, row, a0);
 }
 
 // D[128 x N] (+)= A[128 x 16*KSTEPS] . W[N x 16*KSTEPS]^T : K-major A tile (rows = samples) x K-major weight image
@@ -564,19 +573,43 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
 #pragma unroll
     for (int k = 0; k < 16; k++) acc_last[k] = 0.f;
 
+    // this thread's half of the input row of tile t, in registers (fetched one tile ahead of its use)
+    uint4 in_regs[2];
+    auto fetch_tile_input = [&](uint32_t t) {
+      const uint32_t mm = t * kTile + row;
+      if (NET == 0 && p.enc) {
+        if (hc == 0) fetch_input<NET, 0, 2, true>(p, mm, in_regs);
+        else fetch_input<NET, 2, 2, true>(p, mm, in_regs);
+      } else {
+        if (hc == 0) fetch_input<NET, 0, 2, false>(p, mm, in_regs);
+        else fetch_input<NET, 2, 2, false>(p, mm, in_regs);
+      }
+    };
+    if (blockIdx.x < n_tiles) fetch_tile_input(blockIdx.x);
+
     for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, iter++) {
       const uint32_t m = t * kTile + row;
       mark(0);
       // ---------------- forward recompute
-      if (NET == 0 && p.enc) {
-        if (hc == 0) load_input<NET, 0, 2, true>(p, m, row, a0);
-        else load_input<NET, 2, 2, true>(p, m, row, a0);
-      } else {
-        if (hc == 0) load_input<NET, 0, 2, false>(p, m, row, a0);
-        else load_input<NET, 2, 2, false>(p, m, row, a0);
-      }
+      if (hc == 0) store_input<0, 2>(in_regs, row, a0);
+      else store_input<2, 2>(in_regs, row, a0);
       hand_over();
       mark(1);
+      // the upstream gradients of this tile's rows: issued now, consumed after the forward recompute
+      float up[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) up[k] = 0.f;
+      if (hc == 0 && m < p.M) {
+        if (NET == 0) {
+          up[0] = __ldg(p.grad_sigmas + m);
+          const float4* gg = reinterpret_cast<const float4*>(p.g_geo + (size_t)m * 16);
+          const float4 x0 = __ldg(gg), x1 = __ldg(gg + 1), x2 = __ldg(gg + 2), x3 = __ldg(gg + 3);
+          up[1] = x0.x; up[2] = x0.y; up[3] = x0.z; up[4] = x0.w; up[5] = x1.x; up[6] = x1.y; up[7] = x1.z; up[8] = x1.w;
+          up[9] = x2.x; up[10] = x2.y; up[11] = x2.z; up[12] = x2.w; up[13] = x3.x; up[14] = x3.y; up[15] = x3.z;
+        } else {
+          for (uint32_t c = 0; c < p.C; c++) up[c] = __ldg(p.grad_rgbs + (size_t)m * p.C + c);
+        }
+      }
       for (int i = 0; i < L; i++) {
         wait_mma();
         mark(2);
@@ -596,16 +629,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
           for (int k = 0; k < 16; k++) go[k] = 0.f;
           if (m < p.M) {
             if (NET == 0) {
-              go[0] = v[0] > 0.f ? __ldg(p.grad_sigmas + m) : 0.f;
-              const float4* gg = reinterpret_cast<const float4*>(p.g_geo + (size_t)m * 16);
-              const float4 x0 = __ldg(gg), x1 = __ldg(gg + 1), x2 = __ldg(gg + 2), x3 = __ldg(gg + 3);
-              const float gv[16] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z, x3.w};
+              go[0] = v[0] > 0.f ? up[0] : 0.f;
 #pragma unroll
-              for (int k = 0; k < 15; k++) go[1 + k] = gv[k];
+              for (int k = 1; k < 16; k++) go[k] = up[k];
             } else {
-              for (uint32_t c = 0; c < p.C; c++) {
+#pragma unroll
+              for (int c = 0; c < SNERF_MAX_CHANNELS; c++) {
                 const float y = 1.0f / (1.0f + __expf(-v[c]));
-                go[c] = __ldg(p.grad_rgbs + (size_t)m * p.C + c) * y * (1.0f - y);
+                go[c] = (uint32_t)c < p.C ? up[c] * y * (1.0f - y) : 0.f;
               }
             }
           }
@@ -647,6 +678,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
       }
 
       // ---------------- first matrix W_0 [128 x 32]
+      if (t + gridDim.x < n_tiles) fetch_tile_input(t + gridDim.x);  // lands while the last two phases run
       wait_mma();  // wgrad
       mark(12);
       if (hc == 0) {
