@@ -12,6 +12,8 @@
 // (sample, level) result is a float2; results are staged in an XOR-swizzled shared tile and written back as one
 // contiguous 16 KiB block.  The backward kernel mirrors this: coalesced read of the gradient tile, 8 float2
 // reductions (red.global.add.v2.f32) per (sample, level).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "encode.cuh"
 
@@ -23,7 +25,9 @@ constexpr int kEncThreads = 256;
 // swizzled position of the float2 slot (sample s, level l) inside a [kEncTile][16] float2 tile
 __device__ __forceinline__ int tile_slot(int s, int l) { return s * 16 + (l ^ (s & 15)); }
 
-template <bool kNormalize>
+// kBf16Out: the features are rounded to bf16 (RNE) and stored as [M, 2L] bf16 -- the operand format of the tensor-core
+// sigma net (field_tc.cu), which then reads its input tile instead of gathering it.
+template <bool kNormalize, bool kBf16Out>
 __global__ void __launch_bounds__(kEncThreads) k_hashgrid_fwd(snerf_grid_desc g, const float* __restrict__ x,
                                                               float bound, const float2* __restrict__ table,
                                                               uint32_t M, float* __restrict__ enc) {
@@ -57,6 +61,14 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_fwd(snerf_grid_desc g,
     tile[tile_slot(s, l)] = acc;
   }
   __syncthreads();
+  if (kBf16Out) {
+    __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(enc) + (size_t)m0 * L;
+    for (uint32_t i = threadIdx.x; i < ns * L; i += kEncThreads) {
+      const float2 v = tile[tile_slot(i / L, i % L)];
+      out[i] = __floats2bfloat162_rn(v.x, v.y);
+    }
+    return;
+  }
   float2* out = reinterpret_cast<float2*>(enc) + (size_t)m0 * L;
   if (L == 16) {
     for (uint32_t i = threadIdx.x; i < ns * 16; i += kEncThreads) out[i] = tile[tile_slot(i >> 4, i & 15)];
@@ -173,9 +185,16 @@ int launch_hashgrid_fwd(const snerf_grid_desc* g, const float* x, bool normalize
                         uint32_t M, float* enc, cudaStream_t s) {
   const uint32_t blocks = div_up(M, kEncTile);
   if (normalize)
-    k_hashgrid_fwd<true><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, reinterpret_cast<const float2*>(table), M, enc);
+    k_hashgrid_fwd<true, false><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, reinterpret_cast<const float2*>(table), M, enc);
   else
-    k_hashgrid_fwd<false><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, reinterpret_cast<const float2*>(table), M, enc);
+    k_hashgrid_fwd<false, false><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, reinterpret_cast<const float2*>(table), M, enc);
+  return finish_launch();
+}
+// world-space x -> bf16 features [M, 2L] (the tensor-core path's input operand)
+int launch_hashgrid_fwd_bf16(const snerf_grid_desc* g, const float* x, float bound, const float* table, uint32_t M,
+                             void* enc_bf16, cudaStream_t s) {
+  k_hashgrid_fwd<true, true><<<div_up(M, kEncTile), kEncThreads, 0, s>>>(*g, x, bound, reinterpret_cast<const float2*>(table),
+                                                                         M, reinterpret_cast<float*>(enc_bf16));
   return finish_launch();
 }
 int launch_hashgrid_bwd(const snerf_grid_desc* g, const float* x, bool normalize, float bound, const float* grad_enc,

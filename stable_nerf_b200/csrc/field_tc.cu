@@ -97,7 +97,8 @@ struct TcParams {
   float* rgbs;
   float* geo_f32;        // optional [M,15] fp32 (density())
   __nv_bfloat16* geo;    // [M,16] bf16: (geo0..geo14, sigma_raw) written by the sigma net, read by the colour net
-  __nv_bfloat16* enc;    // [M,32] bf16 hash-grid features: written by the sigma forward, read by its backward
+  __nv_bfloat16* enc;    // [M,32] bf16 hash-grid features (k_hashgrid_fwd): input of the sigma net, forward and backward
+  int enc_ready;         // forward: enc already holds the features (otherwise the kernel gathers them itself)
   // backward
   const float* grad_sigmas;
   const float* grad_rgbs;
@@ -287,7 +288,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_field_fwd(const TcParams p) 
 
   for (uint32_t t = blockIdx.x + gridDim.x * wg; t < n_tiles; t += gridDim.x * kFwdGroups) {
     const uint32_t m = t * kTile + row;
-    load_input<NET, 0, 4, false>(p, m, row, act);
+    if (NET == 0 && p.enc_ready) load_input<NET, 0, 4, true>(p, m, row, act);
+    else load_input<NET, 0, 4, false>(p, m, row, act);
     worker_sync();
     for (int i = 0; i <= L; i++) {
       if ((warp & 3u) == 0) {  // the worker's first warp issues (converged warp, elected lane, uniform operands)
@@ -868,7 +870,11 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
   fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
   p.sigmas = sigmas;
   p.geo = sigma_only ? nullptr : w.geo;
-  p.enc = saved ? w.enc : nullptr;  // only worth writing when a backward will read it
+  // the gather runs as its own full-occupancy kernel (latency-bound inside the persistent MLP kernel); its bf16
+  // output is both the sigma net's input tile and, when a hand-off buffer is given, what the backward re-reads
+  if (int e = launch_hashgrid_fwd_bf16(&f->grid, xyzs, f->bound, table, M, w.enc, s)) return e;
+  p.enc = w.enc;
+  p.enc_ready = 1;
   p.geo_f32 = geo_feat;
   if (int e = set_smem(k_field_fwd<0>, fwd_smem(ps))) return e;
   k_field_fwd<0><<<grid_for(M), kFwdThreads, fwd_smem(ps), s>>>(p);
@@ -910,7 +916,9 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
     fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
     p.sigmas = w.g_geo;  // scratch: any M floats, overwritten by step 2
     p.geo = w.geo;
+    if (int e = launch_hashgrid_fwd_bf16(&f->grid, xyzs, f->bound, table, M, w.enc, s)) return e;
     p.enc = w.enc;
+    p.enc_ready = 1;
     if (int e = set_smem(k_field_fwd<0>, fwd_smem(ps))) return e;
     k_field_fwd<0><<<grid_for(M), kFwdThreads, fwd_smem(ps), s>>>(p);
     launches++;
