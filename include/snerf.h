@@ -250,6 +250,9 @@ int snerf_field_backward(const snerf_field_desc* f, const float* xyzs, const flo
 int snerf_tc_selftest(const float* A, const float* B, float* D, uint32_t N, uint32_t K, int a_mn, int b_mn,
                       snerf_stream_t stream);
 
+/* Measurement aid: levels with resolution <= res merge equal cells inside a warp before the scatter-add (default 300). */
+void snerf_debug_set_dedupe_max_res(uint32_t res);
+
 /* Timing probe of the tcgen05 building blocks (one CTA, clock64): out = 32 int64 on the device.  Not on the hot path. */
 int snerf_tc_probe(long long* out, int variant, snerf_stream_t stream);
 

@@ -39,3 +39,13 @@ for name, pts in (("coherent", (xyzs + 1) * 0.5), ("random", torch.rand(M, 3, de
     t_f = timeit(lambda: chk(lib.snerf_hashgrid_forward(g, P(pts), P(table), M, P(enc), S()), "hf"))
     t_b = timeit(lambda: chk(lib.snerf_hashgrid_backward(g, P(pts), P(genc), M, P(gtab), S()), "hb"))
     print(f"{name}: hashgrid fwd {t_f:.1f} us ({t_f*1e3/M:.3f} ns/sample), bwd {t_b:.1f} us")
+
+pts = ((xyzs + 1) * 0.5).contiguous()
+gtab = torch.zeros_like(table)
+# all levels active: sweep of the merging threshold
+genc = torch.randn(M, 32, device=dev)
+for dd in (0, 64, 128, 300, 600, 0x80000000, 0x80000000 + 64, 0x80000000 + 128, 0x80000000 + 300, 0x80000000 + 600):
+    lib.snerf_debug_set_dedupe_max_res(dd)
+    t = timeit(lambda: chk(lib.snerf_hashgrid_backward(g, P(pts), P(genc), M, P(gtab), S()), "hb"), n=10)
+    print(f"all levels, dedupe_max_res {dd & 0x7fffffff} pairing {not (dd >> 31)}: {t:.1f} us")
+lib.snerf_debug_set_dedupe_max_res(300)

@@ -81,14 +81,14 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_fwd(snerf_grid_desc g,
 // cycle (REDG, measured), so the kernel is organised to issue fewer lanes, not fewer bytes:
 //   * a warp works on 32 consecutive samples of one level; consecutive samples of a ray fall into the same cell at the
 //     coarse levels, so runs of lanes with equal (index0, index1) are summed with a segmented warp scan first and only
-//     the last lane of a run issues the reduction (levels with resolution <= kDedupeMaxRes);
+//     the last lane of a run issues the reduction (levels with resolution <= dedupe_max_res);
 //   * the two corners that differ in x are adjacent entries whenever index0 is even (always for a hashed level with
 //     even x: x ^ h and (x+1) ^ h differ in bit 0 only): one 16-byte red.global.add.v4.f32 instead of two v2's;
 //   * samples whose gradient is exactly zero (padding, terminated rays) issue nothing.
-constexpr uint32_t kDedupeMaxRes = 600;
+static uint32_t g_dedupe_max_res = 300;  // tunable through snerf_debug_set_dedupe_max_res (measurement aid)
 
-__device__ __forceinline__ void red_pair(float2* __restrict__ grad_table, uint32_t i0, uint32_t i1, float4 v) {
-  if (i1 == i0 + 1u && (i0 & 1u) == 0u) {
+__device__ __forceinline__ void red_pair(float2* __restrict__ grad_table, uint32_t i0, uint32_t i1, float4 v, bool pairing) {
+  if (pairing && i1 == i0 + 1u && (i0 & 1u) == 0u) {
     atomicAdd(reinterpret_cast<float4*>(grad_table + i0), v);
   } else {
     atomicAdd(grad_table + i0, make_float2(v.x, v.y));
@@ -99,7 +99,8 @@ __device__ __forceinline__ void red_pair(float2* __restrict__ grad_table, uint32
 template <bool kNormalize>
 __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g, const float* __restrict__ x,
                                                               float bound, const float* __restrict__ grad_enc,
-                                                              uint32_t M, float2* __restrict__ grad_table) {
+                                                              uint32_t M, float2* __restrict__ grad_table,
+                                                              uint32_t dedupe_max_res) {
   __shared__ float xs[kEncTile * 3];
   __shared__ float2 tile[kEncTile * 16];
   const uint32_t m0 = blockIdx.x * kEncTile;
@@ -124,7 +125,8 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g,
     const LevelInfo li = level_info(g, l);
     const uint32_t sc = s < ns ? s : 0u;
     const Cell c = grid_cell(xs[sc * 3], xs[sc * 3 + 1], xs[sc * 3 + 2], li.scale);
-    const bool dedupe = li.res <= kDedupeMaxRes;
+    const bool pairing = !(dedupe_max_res >> 31);
+    const bool dedupe = li.res <= (dedupe_max_res & 0x7fffffffu);
 #pragma unroll
     for (uint32_t kp = 0; kp < 4; kp++) {  // corner pair (x, x+1) at (y + kp&1, z + kp>>1)
       const uint32_t cy = c.c[1] + (kp & 1u), cz = c.c[2] + (kp >> 1);
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g,
       const float w0 = corner_weight(c, kp * 2u), w1 = corner_weight(c, kp * 2u + 1u);
       float4 v = make_float4(w0 * gv.x, w0 * gv.y, w1 * gv.x, w1 * gv.y);
       if (!dedupe) {
-        if (active) red_pair(grad_table, i0, i1, v);
+        if (active) red_pair(grad_table, i0, i1, v, pairing);
         continue;
       }
       if (!active) { i0 = 0xffffffffu - (uint32_t)lane; i1 = i0; }  // a run of its own, value zero
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g,
       }
       const bool next_head = __shfl_down_sync(kFull, (int)head, 1) != 0;
       const bool tail = lane == 31 || next_head;
-      if (tail && active) red_pair(grad_table, i0, i1, v);
+      if (tail && active) red_pair(grad_table, i0, i1, v, pairing);
     }
   }
 }
@@ -201,9 +203,11 @@ int launch_hashgrid_bwd(const snerf_grid_desc* g, const float* x, bool normalize
                         uint32_t M, float* grad_table, cudaStream_t s) {
   const uint32_t blocks = div_up(M, kEncTile);
   if (normalize)
-    k_hashgrid_bwd<true><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, grad_enc, M, reinterpret_cast<float2*>(grad_table));
+    k_hashgrid_bwd<true><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, grad_enc, M, reinterpret_cast<float2*>(grad_table),
+                                                         g_dedupe_max_res);
   else
-    k_hashgrid_bwd<false><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, grad_enc, M, reinterpret_cast<float2*>(grad_table));
+    k_hashgrid_bwd<false><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, grad_enc, M, reinterpret_cast<float2*>(grad_table),
+                                                          g_dedupe_max_res);
   return finish_launch();
 }
 
@@ -212,6 +216,8 @@ int launch_hashgrid_bwd(const snerf_grid_desc* g, const float* x, bool normalize
 using namespace snerf;
 
 extern "C" {
+
+void snerf_debug_set_dedupe_max_res(uint32_t res) { g_dedupe_max_res = res; }
 
 int snerf_hashgrid_forward(const snerf_grid_desc* g, const float* x01, const float* table, uint32_t M, float* enc,
                            snerf_stream_t stream) {
