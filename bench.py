@@ -212,6 +212,42 @@ def stage_times(model, ts, iters=10):
     return acc, n_samples, M
 
 
+def render_bench(model, dev, world, rank, frames, barrier, max_over_ranks):
+    """cfg3: full-frame 800x800 inference render (march_rays / field / composite_rays / compact_rays loop,
+    nerf/renderer.py:117-167), pixel rows sharded over the ranks.  Returns the `render` object of the JSON line."""
+    import torch
+    from stable_nerf_b200 import synthetic as syn
+    from stable_nerf_b200.trainer import shard_range
+    ro, rd = syn.full_frame()
+    lo, hi = shard_range(ro.shape[0], rank, world)
+    ro, rd = torch.from_numpy(ro[lo:hi]).to(dev)[None], torch.from_numpy(rd[lo:hi]).to(dev)[None]
+    was_training = model.training
+    model.eval()
+    with torch.no_grad():
+        model.render(ro, rd, bg_color=1, max_steps=MAX_STEPS)  # warm-up frame (sizes the workspaces)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rows = samples = iters = 0
+        for _ in range(frames):
+            out = model.render(ro, rd, bg_color=1, max_steps=MAX_STEPS)
+            st = model.last_render_stats
+            rows, samples, iters = rows + st["rows"], samples + st["samples"], iters + st["iterations"]
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    tot = torch.tensor([rows, samples], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tot)
+    model.train(was_training)
+    return {"workload": "cfg3: 800x800 full-frame inference render, eval loop with on-device compaction, T_thresh 1e-4, "
+                        f"max_steps {MAX_STEPS}, pixel rows sharded over {world} GPU(s)",
+            "samples_per_s": float(tot[1]) / (ms * 1e-3), "rows_per_s_incl_padding": float(tot[0]) / (ms * 1e-3),
+            "ms_per_frame": ms / frames, "frames": frames, "rays": 640000, "loop_iterations_per_frame": iters / frames,
+            "samples_per_frame": float(tot[1]) / frames, "unit": "samples/s"}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -300,6 +336,8 @@ def run_gpu_arm(args):
         "clocks": clocks.summary(),
     }
 
+    if not args.no_render:
+        out["render"] = render_bench(model, dev, world, rank, 3, barrier, max_over_ranks)
     if rank == 0 and not args.no_stages:
         pk = peaks()
         local_step = model.local_step
@@ -316,20 +354,40 @@ def run_gpu_arm(args):
             "field_fwd": ("tensor", 188416.0 * M),
             "field_bwd": ("tensor", 565248.0 * M),  # recompute + dgrad + wgrad
         }
-        dom = max((k for k in st if k in alg), key=st.get)
-        bound, work = alg[dom]
-        t = st[dom] * 1e-3
+        # per-kernel device times of the field calls (one kernel per launch through the library's stage mask)
+        kt = ts.profile_field_kernels() if ts.fused else {}
+        out["field_kernels_us"] = {k: round(v, 2) for k, v in kt.items()}
+        kalg = {  # algorithmic work per launch: flops (tensor) or bytes (hbm/L2), SURVEY section 8d per-sample figures x M
+            "hashgrid_gather": ("hbm", (12 + 1024 + 64) * M),      # xyz + 128 fp32x2 gathers (L2-resident table) + bf16 out
+            "sigma_net_fwd": ("tensor", 2.0 * 38912 * M),
+            "color_net_fwd": ("tensor", 2.0 * 55296 * M),
+            "color_net_bwd": ("tensor", 6.0 * 55296 * M),           # recompute + dgrad + wgrad
+            "sigma_net_bwd": ("tensor", 6.0 * 38912 * M),
+            "hashgrid_scatter": ("hbm", (12 + 128 + 1024) * M),    # xyz + d enc + 128 fp32x2 reductions (L2-resident)
+        }
+        ncu_traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "ncu_kernel_traffic.json")
+        if os.path.exists(tpath):
+            ncu_traffic = json.load(open(tpath))
+        cands = {k: (v * 1e-3, kalg[k]) for k, v in kt.items() if k in kalg}
+        for k in ("near_far", "march", "composite_fwd", "composite_bwd"):
+            if k in st:
+                cands[k] = (st[k], alg[k])
+        dom = max(cands, key=lambda k: cands[k][0])
+        t_ms, (bound, work) = cands[dom]
+        t = t_ms * 1e-3
         if bound == "hbm":
             ach, peak, unit = work / t / 1e9, pk["hbm"], "GB/s"
         else:
             ach, peak, unit = work / t / 1e12, pk["tf_sust"], "TFLOP/s"
         out["roofline"] = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                           "traffic": None, "peak_source": pk["src"]}
+                           "traffic": ncu_traffic.get(dom), "peak_source": pk["src"], "launch_us": t_ms * 1e3}
         out["stage_rooflines"] = {}
-        for k, (b, w) in alg.items():
-            if k in st and st[k] > 0:
-                a = w / (st[k] * 1e-3) / (1e9 if b == "hbm" else 1e12)
-                out["stage_rooflines"][k] = {"bound": b, "achieved": round(a, 2), "frac": round(a / (pk["hbm"] if b == "hbm" else pk["tf_sust"]), 4)}
+        for k, (tm, (b_, w)) in cands.items():
+            if tm > 0:
+                a_ = w / (tm * 1e-3) / (1e9 if b_ == "hbm" else 1e12)
+                out["stage_rooflines"][k] = {"bound": b_, "achieved": round(a_, 2), "unit": "GB/s" if b_ == "hbm" else "TFLOP/s",
+                                             "frac": round(a_ / (pk["hbm"] if b_ == "hbm" else pk["tf_sust"]), 4)}
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline()
     if rank == 0:
@@ -348,6 +406,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-render", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -250,6 +250,11 @@ int snerf_field_backward(const snerf_field_desc* f, const float* xyzs, const flo
 int snerf_tc_selftest(const float* A, const float* B, float* D, uint32_t N, uint32_t K, int a_mn, int b_mn,
                       snerf_stream_t stream);
 
+/* Measurement aid: which kernels of the bf16 field calls are launched (bench.py times them one by one).  Forward:
+ * 1 weight packing, 2 hash-grid gather, 4 sigma net, 8 colour net; backward: 16 weight packing, 32 colour net,
+ * 64 sigma net, 128 table scatter-add.  Default 0xffffffff (all); results are only meaningful with all bits set. */
+void snerf_debug_set_field_stage_mask(uint32_t mask);
+
 /* Measurement aid: levels with resolution <= res merge equal cells inside a warp before the scatter-add (default 300). */
 void snerf_debug_set_dedupe_max_res(uint32_t res);
 

@@ -103,7 +103,9 @@ struct TcParams {
   const float* grad_sigmas;
   const float* grad_rgbs;
   float* g_geo;          // [M,16] fp32: d loss / d geo (cols 0..14) written by the colour bwd, read by the sigma bwd
-  float* grad_w;         // fp32 gradient of this net's flat matrices (accumulated)
+  float* grad_w;         // fp32 gradient of this net's flat matrices (accumulated by k_reduce_partials)
+  float* dw_part;        // [gridDim.x][n_params] per-CTA partial weight gradients (plain stores, no atomics)
+  uint32_t n_params;     // parameters of this net
   float* d_enc;          // [M,32] fp32: d loss / d encoding, written by the sigma bwd, scattered by k_hashgrid_bwd
   long long* dbg;        // optional phase-timing buffer (snerf_debug_phase_buffer): clock64 marks of CTA 0, 2nd tile
 };
@@ -718,27 +720,28 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
     }
     if (p.dbg && tid == 0 && blockIdx.x == 0) p.dbg[0] = n_marks;
 
-    // ---------------- flush the weight gradients of this CTA
+    // ---------------- hand this CTA's weight gradients to k_reduce_partials (plain coalesced stores: 148 CTAs adding
+    // into the same 200 KB with atomics serialise at the L2 and cost as much as several tiles)
     if (iter > 0) {
       tc_fence_after();
+      float* part = p.dw_part + (size_t)blockIdx.x * p.n_params;
       if (hc == 0) {
-        float* g0 = p.grad_w + p.net.src_off[0] + (size_t)row * 32;
+        float4* g0 = reinterpret_cast<float4*>(part + p.net.src_off[0] + (size_t)row * 32);
 #pragma unroll
-        for (int k = 0; k < 32; k += 4)
-          atomicAdd(reinterpret_cast<float4*>(g0 + k), make_float4(acc_first[k], acc_first[k + 1], acc_first[k + 2], acc_first[k + 3]));
-        float* gl = p.grad_w + p.net.src_off[L];
+        for (int k = 0; k < 8; k++) g0[k] = make_float4(acc_first[4 * k], acc_first[4 * k + 1], acc_first[4 * k + 2], acc_first[4 * k + 3]);
+        float* gl = part + p.net.src_off[L];
 #pragma unroll
-        for (int n = 0; n < 16; n++) atomicAdd(gl + (size_t)n * kTile + row, acc_last[n]);
+        for (int n = 0; n < 16; n++) gl[(size_t)n * kTile + row] = acc_last[n];
       }
       for (int i = 1; i < L; i++) {
-        float* gw = p.grad_w + p.net.src_off[i] + (size_t)row * kTile + hc * 64u;
+        float* gw = part + p.net.src_off[i] + (size_t)row * kTile + hc * 64u;
 #pragma unroll
         for (uint32_t cc = 0; cc < 2; cc++) {
           float v[32];
           tmem_ld32(tlane + 128u * (uint32_t)i + hc * 64u + cc * 32u, v);
 #pragma unroll
           for (int k = 0; k < 32; k += 4)
-            atomicAdd(reinterpret_cast<float4*>(gw + cc * 32u + k), make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]));
+            *reinterpret_cast<float4*>(gw + cc * 32u + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
         }
       }
     }
@@ -748,7 +751,24 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// grad_w[i] += sum over CTAs of part[c][i]: fixed summation order inside a group of CTAs, one atomic per group
+constexpr uint32_t kReduceGroups = 4;
+__global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ part, uint32_t n_ctas, uint32_t n_params,
+                                                         float* __restrict__ grad_w) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
+  if (i * 4u >= n_params) return;
+  const uint32_t per = div_up(n_ctas, kReduceGroups), c0 = blockIdx.y * per, c1 = min(n_ctas, c0 + per);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t c = c0; c < c1; c++) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)c * n_params) + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (c1 > c0) atomicAdd(reinterpret_cast<float4*>(grad_w) + i, acc);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
+
+constexpr uint32_t kMaxGrid = 160;  // persistent kernels launch at most one CTA per SM (148 on B200)
 
 struct TcWorkspace {
   uint8_t* wimg_sigma;
@@ -757,6 +777,7 @@ struct TcWorkspace {
   __nv_bfloat16* enc;
   float* g_geo;
   float* d_enc;
+  float* dw_part;  // per-CTA partial weight gradients of one net at a time (max of the two nets)
 };
 
 // forward -> backward hand-off buffer: [geo: M x 16 bf16][pad to 1 KiB][enc: M x 32 bf16]
@@ -781,6 +802,7 @@ static size_t carve_tc(const snerf_field_desc* f, uint32_t M, int backward, char
   o.enc = (__nv_bfloat16*)(hand ? hand + saved_geo_bytes(M) : nullptr);
   o.g_geo = backward ? (float*)take((size_t)(M ? M : 1) * 16 * sizeof(float)) : nullptr;
   o.d_enc = backward ? (float*)take((size_t)(M ? M : 1) * 32 * sizeof(float)) : nullptr;
+  o.dw_part = backward ? (float*)take((size_t)kMaxGrid * std::max(sigma_shape(f).n_params, color_shape(f).n_params) * sizeof(float)) : nullptr;
   return off;
 }
 
@@ -788,6 +810,10 @@ size_t field_tc_workspace_bytes(const snerf_field_desc* f, uint32_t M, int backw
   return carve_tc(f, M, backward, nullptr, nullptr);
 }
 
+static uint32_t g_stage_mask = 0xffffffffu;  // measurement aid: which kernels of a field call are launched
+void field_tc_set_stage_mask(uint32_t mask) { g_stage_mask = mask; }
+enum : uint32_t { kStFwdPack = 1, kStFwdEncode = 2, kStFwdSigma = 4, kStFwdColor = 8, kStBwdPack = 16, kStBwdColor = 32,
+                  kStBwdSigma = 64, kStBwdScatter = 128 };
 static long long* g_phase_dbg = nullptr;
 static int g_phase_net = 0;
 void field_tc_set_phase_buffer(void* p, int net) { g_phase_dbg = (long long*)p; g_phase_net = net; }
@@ -824,7 +850,7 @@ static void fill_common(TcParams& p, const snerf_field_desc* f, const PackedNet&
   p.dbg = nullptr;
 }
 
-static uint32_t grid_for(uint32_t M) { return min(div_up(M, kTile), (uint32_t)sm_count()); }
+static uint32_t grid_for(uint32_t M) { return min(div_up(M, kTile), min((uint32_t)sm_count(), kMaxGrid)); }
 static size_t fwd_smem(const PackedNet& n) { return n.total_bytes + (size_t)kFwdGroups * kActBytes + 1024; }
 // ring depth of the backward's weight stream: whatever the 227 KiB of shared memory leave after the activations
 static uint32_t bwd_slots(const PackedNet& n) {
@@ -848,6 +874,7 @@ static int launch_bwd(const TcParams& p, const PackedNet& n, uint32_t M, cudaStr
   } else {
     return SNERF_E_UNSUPPORTED;  // the activations of a tile leave no room for the weight ring
   }
+  k_reduce_partials<<<dim3(div_up(p.n_params / 4, 256), kReduceGroups), 256, 0, s>>>(p.dw_part, grid_for(M), p.n_params, p.grad_w);
   return SNERF_OK;
 }
 
@@ -864,28 +891,40 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
     w.enc = (__nv_bfloat16*)((char*)saved + saved_geo_bytes(M));
   }
   const PackedNet ps = make_packed(sigma_shape(f)), pc = make_packed(color_shape(f));
-  k_pack_weights<<<div_up(ps.total_bytes / 16, 256), 256, 0, s>>>(w_sigma, ps, w.wimg_sigma);
-  if (!sigma_only) k_pack_weights<<<div_up(pc.total_bytes / 16, 256), 256, 0, s>>>(w_color, pc, w.wimg_color);
+  const uint32_t st = g_stage_mask;
+  unsigned launches = 0;
+  if (st & kStFwdPack) {
+    k_pack_weights<<<div_up(ps.total_bytes / 16, 256), 256, 0, s>>>(w_sigma, ps, w.wimg_sigma);
+    launches++;
+    if (!sigma_only) {
+      k_pack_weights<<<div_up(pc.total_bytes / 16, 256), 256, 0, s>>>(w_color, pc, w.wimg_color);
+      launches++;
+    }
+  }
   TcParams p;
   fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
   p.sigmas = sigmas;
   p.geo = sigma_only ? nullptr : w.geo;
   // the gather runs as its own full-occupancy kernel (latency-bound inside the persistent MLP kernel); its bf16
   // output is both the sigma net's input tile and, when a hand-off buffer is given, what the backward re-reads
-  if (int e = launch_hashgrid_fwd_bf16(&f->grid, xyzs, f->bound, table, M, w.enc, s)) return e;
+  if (st & kStFwdEncode) {
+    if (int e = launch_hashgrid_fwd_bf16(&f->grid, xyzs, f->bound, table, M, w.enc, s)) return e;
+  }
   p.enc = w.enc;
   p.enc_ready = 1;
   p.geo_f32 = geo_feat;
-  if (int e = set_smem(k_field_fwd<0>, fwd_smem(ps))) return e;
-  k_field_fwd<0><<<grid_for(M), kFwdThreads, fwd_smem(ps), s>>>(p);
-  unsigned launches = 2;
-  if (!sigma_only) {
+  if (st & kStFwdSigma) {
+    if (int e = set_smem(k_field_fwd<0>, fwd_smem(ps))) return e;
+    k_field_fwd<0><<<grid_for(M), kFwdThreads, fwd_smem(ps), s>>>(p);
+    launches++;
+  }
+  if (!sigma_only && (st & kStFwdColor)) {
     fill_common(p, f, pc, M, xyzs, dirs, table, w.wimg_color);
     p.geo = w.geo;
     p.rgbs = rgbs;
     if (int e = set_smem(k_field_fwd<1>, fwd_smem(pc))) return e;
     k_field_fwd<1><<<grid_for(M), kFwdThreads, fwd_smem(pc), s>>>(p);
-    launches += 2;
+    launches++;
   }
   return finish_launch(launches);
 }
@@ -903,12 +942,16 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   carve_tc(f, M, 1, (char*)ws, &w);
   const NetShape ss = sigma_shape(f), sc = color_shape(f);
   const PackedNet ps = make_packed(ss), pc = make_packed(sc);
-  k_pack_weights<<<div_up(ps.total_bytes / 16, 256), 256, 0, s>>>(w_sigma, ps, w.wimg_sigma);
-  k_pack_weights<<<div_up(pc.total_bytes / 16, 256), 256, 0, s>>>(w_color, pc, w.wimg_color);
+  const uint32_t st = g_stage_mask;
+  unsigned launches = 0;
+  if (st & kStBwdPack) {
+    k_pack_weights<<<div_up(ps.total_bytes / 16, 256), 256, 0, s>>>(w_sigma, ps, w.wimg_sigma);
+    k_pack_weights<<<div_up(pc.total_bytes / 16, 256), 256, 0, s>>>(w_color, pc, w.wimg_color);
+    launches += 2;
+  }
   // 1. the geometry features the colour net consumes and the encoded inputs of the sigma net: handed over by the
   //    forward, or regenerated by running the sigma net's forward again
   TcParams p;
-  unsigned launches = 4;
   if (saved) {
     w.geo = (__nv_bfloat16*)const_cast<void*>(saved);
     w.enc = (__nv_bfloat16*)((char*)const_cast<void*>(saved) + saved_geo_bytes(M));
@@ -929,19 +972,31 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   p.grad_rgbs = grad_rgbs;
   p.g_geo = w.g_geo;
   p.grad_w = grad_w_color;
+  p.dw_part = w.dw_part;
+  p.n_params = sc.n_params;
   p.dbg = g_phase_net == 1 ? g_phase_dbg : nullptr;
-  if (int e = launch_bwd<1>(p, pc, M, s)) return e;
+  if (st & kStBwdColor) {
+    if (int e = launch_bwd<1>(p, pc, M, s)) return e;
+    launches += 2;
+  }
   // 3. sigma net: recompute from the saved encoding + dgrad + wgrad + table scatter-add
   fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
   p.enc = w.enc;
   p.grad_sigmas = grad_sigmas;
   p.g_geo = w.g_geo;
   p.grad_w = grad_w_sigma;
+  p.dw_part = w.dw_part;
+  p.n_params = ss.n_params;
   p.d_enc = w.d_enc;
   p.dbg = g_phase_net == 0 ? g_phase_dbg : nullptr;
-  if (int e = launch_bwd<0>(p, ps, M, s)) return e;
+  if (st & kStBwdSigma) {
+    if (int e = launch_bwd<0>(p, ps, M, s)) return e;
+    launches += 2;
+  }
   // 4. table scatter-add of d loss / d encoding (its own kernel: full occupancy, warp-level merging of equal cells)
-  if (int e = launch_hashgrid_bwd(&f->grid, xyzs, true, f->bound, w.d_enc, M, grad_table, s)) return e;
+  if (st & kStBwdScatter) {
+    if (int e = launch_hashgrid_bwd(&f->grid, xyzs, true, f->bound, w.d_enc, M, grad_table, s)) return e;
+  }
   return finish_launch(launches);
 }
 

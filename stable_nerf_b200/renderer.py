@@ -111,13 +111,19 @@ class NeRFRenderer(nn.Module):
             count = torch.empty(1, dtype=torch.int32, device=device)
             rays_t = nears.clone()
             n_alive, step = N, 0
+            stats = {"iterations": 0, "rows": 0, "samples": 0}  # network-evaluated rows incl. / excl. alignment padding
+            self.last_render_stats = stats
             while step < max_steps and n_alive > 0:
                 n_step = max(min(N // n_alive, 8), 1)
                 xyzs, dirs, deltas = raymarching.march_rays(
                     n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound, self.density_bitfield, self.cascade,
                     self.grid_size, nears, fars, 128, perturb if step == 0 else False, dt_gamma, max_steps)
+                stats["iterations"] += 1
+                stats["rows"] += xyzs.shape[0]
+                stats["samples"] += n_alive * n_step
                 sigmas, rgbs = self(xyzs, dirs)
-                sigmas = self.density_scale * sigmas
+                if self.density_scale != 1:
+                    sigmas = self.density_scale * sigmas
                 raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth,
                                            image, T_thresh, self.channel_dim)
                 spare, count = raymarching.compact_rays(rays_alive, n_alive, out=spare, count=count)

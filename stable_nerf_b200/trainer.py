@@ -214,6 +214,49 @@ class TrainStep:
         n_samples = int(self._bufs["n_samples"].item())
         return acc, n_samples, self._bufs["M"]
 
+    def profile_field_kernels(self, iters=10):
+        """Device time (us) of each kernel of the bf16 field calls on the last step's samples, one kernel per launch
+        through the library's stage mask (CUDA events on the launch stream).  Leaves the gradients meaningless."""
+        m, b = self.model, self._bufs
+        lib = _lib.load()
+        P, S, chk = _lib.ptr, _lib.stream(), _lib.check
+        prec = _precision_code(m.precision)
+        if prec != _lib.PRECISION_BF16 or b is None:
+            return {}
+        M, nm = b["M"], m.sigma_net.n_mlp
+        sp, cp = m.sigma_net.params, m.color_net.params
+        spd = sp.detach()
+
+        def fwd():
+            chk(lib.snerf_field_forward(m.fdesc, P(b["xyzs"]), P(b["dirs"]), M, P(spd[nm:]), P(spd[:nm]), P(cp.detach()),
+                                        prec, P(b["sigmas"]), P(b["rgbs"]), P(b["saved"]), b["saved_bytes"],
+                                        P(b["field_ws"]), b["field_ws_bytes"], S), "field forward")
+
+        def bwd():
+            chk(lib.snerf_field_backward(m.fdesc, P(b["xyzs"]), P(b["dirs"]), M, P(spd[nm:]), P(spd[:nm]), P(cp.detach()),
+                                         P(b["g_sig"]), P(b["g_rgb"]), prec, P(sp.grad[nm:]), P(sp.grad[:nm]), P(cp.grad),
+                                         P(b["saved"]), b["saved_bytes"], P(b["field_ws"]), b["field_ws_bytes"], S),
+                "field backward")
+        stages = [("pack_weights_fwd", 1, fwd), ("hashgrid_gather", 2, fwd), ("sigma_net_fwd", 4, fwd),
+                  ("color_net_fwd", 8, fwd), ("pack_weights_bwd", 16, bwd), ("color_net_bwd", 32, bwd),
+                  ("sigma_net_bwd", 64, bwd), ("hashgrid_scatter", 128, bwd)]
+        out = {}
+        try:
+            for name, mask, fn in stages:
+                lib.snerf_debug_set_field_stage_mask(mask)
+                for _ in range(2):
+                    fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                out[name] = e0.elapsed_time(e1) / iters * 1e3
+        finally:
+            lib.snerf_debug_set_field_stage_mask(0xffffffff)
+        return out
+
     def warmup(self, rays_o, rays_d, target, iters=3):
         """Reference-style first steps on the synchronising path, then ``mean_count`` from the measured sample
         counts (nerf/renderer.py:321-325) so that later steps never read the device."""
