@@ -75,8 +75,12 @@ int snerf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t*
  * Training march + compositing  (reference: raymarching.h:13-15)
  * ---------------------------------------------------------------------------------------------- */
 
-/* bytes of scratch snerf_march_rays_train needs for N rays */
+/* bytes of scratch snerf_march_rays_train needs for N rays (minimum) */
 size_t snerf_march_rays_train_workspace_bytes(uint32_t N);
+/* Same plus N*max_steps floats: with a workspace of at least this size the counting pass keeps every sample's
+ * position along its ray and the write pass expands them (coalesced, no second march); with a smaller one the write
+ * pass marches again.  Results are identical.  Pass the SAME workspace_bytes to _count and _write. */
+size_t snerf_march_rays_train_workspace_bytes_ex(uint32_t N, uint32_t max_steps);
 
 /* raymarching.cu:312-491, raymarching.py:218.
  * Same inputs and outputs as the reference.  Differences: sample offsets come from a

@@ -55,6 +55,7 @@ SIGNATURES = {
     "snerf_morton3D_invert": (c_int, [_P, _U, _P, _S]),
     "snerf_packbits": (c_int, [_P, _U, _F, _P, _S]),
     "snerf_march_rays_train_workspace_bytes": (c_size_t, [_U]),
+    "snerf_march_rays_train_workspace_bytes_ex": (c_size_t, [_U, _U]),
     "snerf_march_rays_train_count": (c_int, [_P, _P, _P, _F, _F, _U, _U, _U, _U, _P, _P, _P, _P, _P, c_size_t, _S]),
     "snerf_march_rays_train_write": (c_int, [_P, _P, _P, _F, _F, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, c_int,
                                              _P, _P, c_size_t, _S]),

@@ -242,18 +242,29 @@ struct WarpMarch {
 // (in order); my_* describe this lane's element; my_last = last_t seen by this lane's sample.
 __device__ __forceinline__ bool march_round(const MarchParams& p, const Ray& r, const uint8_t* __restrict__ grid, float far,
                                             uint32_t budget, int lane, WarpMarch& st, uint32_t& emitted, float& x, float& y,
-                                            float& z, float& dt, float& my_next, float& my_last) {
-  // the chain: every lane steps through all 32 elements and keeps its own (t, t_next)
-  float t = st.t_base, my_t = 0.f;
+                                            float& z, float& dt, float& my_t, float& my_next, float& my_last) {
+  // the chain: lane j needs element j (t) and element j+1 (t_next) of the serially rounded sequence
+  float t = st.t_base;
+  my_t = 0.f;
   my_next = 0.f;
+  bool have = false;
   if (p.dt_gamma == 0.0f) {  // dt == dt_min: clamp(0, dt_min, dt_max)
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-      const float tn = fadd(t, p.dt_min);
-      if (j == lane) { my_t = t; my_next = tn; }
-      t = tn;
+    // Inside one binade every step adds the same exactly representable increment q = fl(t + dt) - t, so element j is
+    // t + j*q (exact).  Verified, not assumed: the values are the serial chain iff each lane's successor equals
+    // fl(own + dt); binade crossings and round-to-even ties fail the check and take the serial loop below.
+    const float q = fadd(fadd(t, p.dt_min), -t);
+    const float cand = ffma((float)lane, q, t);
+    const float cand_next = fadd(cand, p.dt_min);
+    const float succ = __shfl_down_sync(kFull, cand, 1);
+    const bool ok = lane == 31 || succ == cand_next;
+    if (__all_sync(kFull, ok)) {
+      my_t = cand;
+      my_next = cand_next;
+      t = __shfl_sync(kFull, cand_next, 31);
+      have = true;
     }
-  } else {
+  }
+  if (!have) {
 #pragma unroll 8
     for (int j = 0; j < 32; j++) {
       const float tn = fadd(t, clampf(fmul(t, p.dt_gamma), p.dt_min, p.dt_max));
@@ -309,7 +320,8 @@ __global__ void __launch_bounds__(kMarchThreads) k_march_train_count(MarchParams
                                                                      const float* __restrict__ nears,
                                                                      const float* __restrict__ fars,
                                                                      const float* __restrict__ noises,
-                                                                     uint32_t* __restrict__ counts) {
+                                                                     uint32_t* __restrict__ counts,
+                                                                     float* __restrict__ t_scratch) {
   const uint32_t n = blockIdx.x * kMarchRaysPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -322,8 +334,14 @@ __global__ void __launch_bounds__(kMarchThreads) k_march_train_count(MarchParams
   st.last_t = st.t_base;
   st.count = 0;
   uint32_t emitted;
-  float x, y, z, dt, my_next, my_last;
-  while (march_round(p, r, grid, far, p.max_steps, lane, st, emitted, x, y, z, dt, my_next, my_last)) {
+  float x, y, z, dt, my_t, my_next, my_last;
+  bool more = true;
+  while (more) {
+    const uint32_t before_count = st.count;
+    more = march_round(p, r, grid, far, p.max_steps, lane, st, emitted, x, y, z, dt, my_t, my_next, my_last);
+    // the sample positions along the ray (4 B/sample): with them the write pass is a plain expansion, no second march
+    if (t_scratch && ((emitted >> lane) & 1u))
+      t_scratch[(size_t)n * p.max_steps + before_count + (uint32_t)__popc(emitted & ((1u << lane) - 1u))] = my_t;
   }
   if (lane == 0) counts[n] = st.count;
 }
@@ -401,8 +419,8 @@ __global__ void __launch_bounds__(kMarchThreads) k_march_train_write(
   while (more) {
     const uint32_t before_count = st.count;
     uint32_t emitted;
-    float x, y, z, dt, my_next, my_last;
-    more = march_round(p, r, grid, far, num_steps, lane, st, emitted, x, y, z, dt, my_next, my_last);
+    float x, y, z, dt, my_t, my_next, my_last;
+    more = march_round(p, r, grid, far, num_steps, lane, st, emitted, x, y, z, dt, my_t, my_next, my_last);
     if ((emitted >> lane) & 1u) {
       const size_t row = (size_t)point_index + before_count + (uint32_t)__popc(emitted & ((1u << lane) - 1u));
       float* px = xyzs + row * 3;
@@ -411,6 +429,58 @@ __global__ void __launch_bounds__(kMarchThreads) k_march_train_write(
       pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
       reinterpret_cast<float2*>(deltas)[row] = make_float2(dt, fadd(my_next, -my_last));
     }
+  }
+}
+
+// Write pass when the count pass kept the sample positions (t_scratch): every sample is independent.
+//   x = clamp(o + t d), dt = clamp(t*dt_gamma), t_next = t + dt, delta = (dt, t_next - t_next of the previous sample
+//   (t0 for the first)) -- the same expressions, in the same rounding, as the marching loop (raymarching.cu:452-472).
+__global__ void __launch_bounds__(kMarchThreads) k_march_train_expand(
+    MarchParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d, uint32_t N, uint32_t M,
+    const float* __restrict__ nears, const float* __restrict__ noises, const uint32_t* __restrict__ counts,
+    const uint32_t* __restrict__ offsets, const float* __restrict__ t_scratch, float* __restrict__ xyzs,
+    float* __restrict__ dirs, float* __restrict__ deltas, int32_t* __restrict__ rays, int zero_unwritten,
+    int32_t* __restrict__ n_samples_out) {
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t total = offsets[N];
+  if (gtid == 0 && n_samples_out) *n_samples_out = (int32_t)total;
+  if (zero_unwritten)  // alignment padding: rows [total, M)
+    for (uint32_t i = total + gtid; i < M; i += gridDim.x * blockDim.x) zero_rows(xyzs, dirs, deltas, i);
+  const uint32_t n = blockIdx.x * kMarchRaysPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const uint32_t num_steps = counts[n], point_index = offsets[n];
+  if (lane == 0) {
+    rays[n * 3] = (int32_t)n;
+    rays[n * 3 + 1] = (int32_t)point_index;
+    rays[n * 3 + 2] = (int32_t)num_steps;
+  }
+  if (num_steps == 0) return;
+  if (point_index + num_steps > M) {  // raymarching.cu:417: overflowing rays are dropped
+    if (zero_unwritten)
+      for (uint32_t i = point_index + lane; i < M && i < point_index + num_steps; i += 32) zero_rows(xyzs, dirs, deltas, i);
+    return;
+  }
+  Ray r;
+  r.load(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+  const float t0 = ray_t0(p, __ldg(nears + n), __ldg(noises + n));
+  const float* ts = t_scratch + (size_t)n * p.max_steps;
+  for (uint32_t i = lane; i < num_steps; i += 32) {
+    const float t = ts[i];
+    const float dt = clampf(fmul(t, p.dt_gamma), p.dt_min, p.dt_max);
+    float last = t0;
+    if (i > 0) {
+      const float tp = ts[i - 1];
+      last = fadd(tp, clampf(fmul(tp, p.dt_gamma), p.dt_min, p.dt_max));
+    }
+    const size_t row = (size_t)point_index + i;
+    float* px = xyzs + row * 3;
+    float* pd = dirs + row * 3;
+    px[0] = clampf(ffma(t, r.dx, r.ox), -p.bound, p.bound);
+    px[1] = clampf(ffma(t, r.dy, r.oy), -p.bound, p.bound);
+    px[2] = clampf(ffma(t, r.dz, r.oz), -p.bound, p.bound);
+    pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+    reinterpret_cast<float2*>(deltas)[row] = make_float2(dt, fadd(fadd(t, dt), -last));
   }
 }
 
@@ -551,8 +621,17 @@ size_t snerf_march_rays_train_workspace_bytes(uint32_t N) {  // counts [N] | off
   return align_up(n * sizeof(uint32_t), 256) + align_up((n + 1) * sizeof(uint32_t), 256);
 }
 
+size_t snerf_march_rays_train_workspace_bytes_ex(uint32_t N, uint32_t max_steps) {  // ... | t_scratch [N*max_steps]
+  return snerf_march_rays_train_workspace_bytes(N) + align_up((size_t)(N ? N : 1) * max_steps * sizeof(float), 256);
+}
+
 static uint32_t* ws_offsets(void* workspace, uint32_t N) {
   return (uint32_t*)((char*)workspace + align_up((size_t)N * sizeof(uint32_t), 256));
+}
+// the sample-position scratch, or NULL when the caller's workspace has no room for it (the write pass then re-marches)
+static float* ws_t_scratch(void* workspace, size_t workspace_bytes, uint32_t N, uint32_t max_steps) {
+  if (workspace_bytes < snerf_march_rays_train_workspace_bytes_ex(N, max_steps)) return nullptr;
+  return (float*)((char*)workspace + snerf_march_rays_train_workspace_bytes(N));
 }
 
 int snerf_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
@@ -567,7 +646,8 @@ int snerf_march_rays_train_count(const float* rays_o, const float* rays_d, const
   uint32_t* counts = (uint32_t*)workspace;
   const uint32_t nblocks = div_up(N, kMarchRaysPerBlock);
   cudaStream_t s = (cudaStream_t)stream;
-  k_march_train_count<<<nblocks, kMarchThreads, 0, s>>>(p, rays_o, rays_d, grid, N, nears, fars, noises, counts);
+  k_march_train_count<<<nblocks, kMarchThreads, 0, s>>>(p, rays_o, rays_d, grid, N, nears, fars, noises, counts,
+                                                        ws_t_scratch(workspace, workspace_bytes, N, max_steps));
   k_march_train_scan<<<1, 1024, 0, s>>>(counts, N, ws_offsets(workspace, N), counter);
   return finish_launch(2);
 }
@@ -585,6 +665,12 @@ int snerf_march_rays_train_write(const float* rays_o, const float* rays_d, const
   MarchParams p;
   if (int e = make_march_params(&p, bound, dt_gamma, max_steps, C, H)) return e;
   const uint32_t nblocks = div_up(N, kMarchRaysPerBlock);
+  if (const float* ts = ws_t_scratch(workspace, workspace_bytes, N, max_steps)) {
+    k_march_train_expand<<<nblocks, kMarchThreads, 0, (cudaStream_t)stream>>>(
+        p, rays_o, rays_d, N, M, nears, noises, (const uint32_t*)workspace, ws_offsets(workspace, N), ts, xyzs, dirs, deltas,
+        rays, zero_unwritten, n_samples_out);
+    return finish_launch();
+  }
   k_march_train_write<<<nblocks, kMarchThreads, 0, (cudaStream_t)stream>>>(
       p, rays_o, rays_d, grid, N, M, nears, fars, noises, (const uint32_t*)workspace, ws_offsets(workspace, N), xyzs,
       dirs, deltas, rays, zero_unwritten, n_samples_out);

@@ -28,6 +28,13 @@ def _cuda_f32_rows(t, width):
     return t.to(torch.float32).contiguous().view(-1, width)
 
 
+def march_train_workspace_bytes(lib, N, max_steps, limit=1 << 30):
+    """Workspace of the training march: with room for N*max_steps sample positions (<= `limit` bytes) the write pass
+    expands them instead of marching a second time."""
+    big = lib.snerf_march_rays_train_workspace_bytes_ex(N, max_steps)
+    return big if big <= limit else lib.snerf_march_rays_train_workspace_bytes(N)
+
+
 def _pad_up(m, align):
     # raymarching.py:201-202: always adds, a full `align` when already aligned (SURVEY Q7)
     return m + (align - m % align) if align > 0 else m
@@ -147,7 +154,7 @@ class _march_rays_train(Function):
             torch.zeros(N, dtype=torch.float32, device=dev)
         rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
 
-        ws_bytes = lib.snerf_march_rays_train_workspace_bytes(N)
+        ws_bytes = march_train_workspace_bytes(lib, N, int(max_steps))
         ws = workspace.get("march_train", ws_bytes, dev)
         geom = (float(bound), float(dt_gamma), int(max_steps), N, int(C), int(H))
         check(lib.snerf_march_rays_train_count(ptr(rays_o), ptr(rays_d), ptr(density_bitfield), *geom, ptr(nears),

@@ -16,7 +16,7 @@ import torch.distributed as dist
 
 from . import _lib
 from .field import _precision_code
-from .raymarching import _pad_up
+from .raymarching import _pad_up, march_train_workspace_bytes
 
 
 def shard_range(n, rank, world):
@@ -112,7 +112,7 @@ class TrainStep:
                  n_samples=torch.empty(1, dtype=torch.int32, device=dev), xyzs=e(M, 3), dirs=e(M, 3), deltas=e(M, 2),
                  sigmas=e(M), rgbs=e(M, C), ws=e(N), depth=e(N), image=e(N, C), g_img=e(N, C), g_ws=e(N), g_sig=e(M),
                  g_rgb=e(M, C), pred=e(N, C), depth_norm=e(N))
-        b["march_ws_bytes"] = lib.snerf_march_rays_train_workspace_bytes(N)
+        b["march_ws_bytes"] = march_train_workspace_bytes(lib, N, self.max_steps)
         b["march_ws"] = torch.empty(b["march_ws_bytes"], dtype=torch.uint8, device=dev)
         b["field_ws_bytes"] = max(lib.snerf_field_workspace_bytes(m.fdesc, M, prec, 0),
                                   lib.snerf_field_workspace_bytes(m.fdesc, M, prec, 1))

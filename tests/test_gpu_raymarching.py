@@ -44,8 +44,10 @@ def run_train_march(sc, dev, inp):
     return o, d, nears, fars
 
 
-def cuda_march_with_noises(sc, dev, inp, nears, fars, M=None):
-    """call the C ABI directly so the seeded noises are used (the python op draws torch.rand when perturb=True)"""
+def cuda_march_with_noises(sc, dev, inp, nears, fars, M=None, keep_positions=True):
+    """call the C ABI directly so the seeded noises are used (the python op draws torch.rand when perturb=True).
+    keep_positions: workspace with room for the per-sample positions (the write pass expands them) or the minimal one
+    (the write pass marches again); both must give the same bits."""
     from stable_nerf_b200 import _lib
     from stable_nerf_b200._lib import check, ptr, stream
     lib = _lib.load()
@@ -53,7 +55,8 @@ def cuda_march_with_noises(sc, dev, inp, nears, fars, M=None):
     bf, noises = dev_t(inp["bitfield"], dev), dev_t(inp["noises"], dev)
     N = sc.n_rays
     counter = torch.zeros(2, dtype=torch.int32, device=dev)
-    nb = lib.snerf_march_rays_train_workspace_bytes(N)
+    nb = (lib.snerf_march_rays_train_workspace_bytes_ex(N, sc.max_steps) if keep_positions
+          else lib.snerf_march_rays_train_workspace_bytes(N))
     ws = torch.empty(nb, dtype=torch.uint8, device=dev)
     geom = (sc.bound, sc.dt_gamma, sc.max_steps, N, sc.cascades, sc.H)
     check(lib.snerf_march_rays_train_count(ptr(o), ptr(d), ptr(bf), *geom, ptr(nears), ptr(fars), ptr(counter),
@@ -84,6 +87,9 @@ def test_near_far_and_march_train_vs_oracle(sc, built_lib, cuda):
     assert_bits_equal(fars.cpu().numpy(), of, "fars")
 
     counter, xyzs, dirs, deltas, rays, total = cuda_march_with_noises(sc, cuda, inp, nears, fars)
+    again = cuda_march_with_noises(sc, cuda, inp, nears, fars, keep_positions=False)  # second-march write pass
+    for a, b, name in zip((counter, xyzs, dirs, deltas, rays), again, ("counter", "xyzs", "dirs", "deltas", "rays")):
+        assert_bits_equal(a, b, name + " (expand vs re-march write pass)")
     ox, od, odl, orays, ocounter = orc.march_rays_train(inp["rays_o"], inp["rays_d"], sc.bound, inp["bitfield"],
                                                         sc.cascades, sc.H, on, of, inp["noises"], sc.dt_gamma,
                                                         sc.max_steps)
