@@ -248,6 +248,50 @@ def render_bench(model, dev, world, rank, frames, barrier, max_over_ranks):
             "samples_per_frame": float(tot[1]) / frames, "unit": "samples/s"}
 
 
+def large_batch_profile(model, dev, pk, n_rays=1 << 18):
+    """cfg5's per-step ray count on ONE GPU (2^18 rays, ~22 M samples): at this size the byte-moving kernels are no
+    longer launch-bound, so their HBM fractions mean something.  Eager fused step, CUDA events per stage / kernel."""
+    import torch
+    from stable_nerf_b200.trainer import TrainStep
+    _, rays_o, rays_d, target = workload(n_rays, seed=7)
+    model.mean_count, model.local_step = 0, 0
+    ts = TrainStep(model, n_rays, max_steps=MAX_STEPS, use_graph=False)
+    d = [torch.from_numpy(a).to(dev) for a in (rays_o, rays_d, target)]
+    ts.warmup(*d, iters=1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        ts.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    st, ns, M = ts.profile_stages(iters=3)
+    kt = ts.profile_field_kernels(iters=3)
+    C = CHANNELS
+    work = {
+        "march": ("hbm", st.get("march", 0) * 1e3, 48.0 * n_rays + 32.0 * ns),
+        "composite_fwd": ("hbm", st.get("composite_fwd", 0) * 1e3, (12 + 4 * C) * ns + (20 + 4 * C) * n_rays),
+        "composite_bwd": ("hbm", st.get("composite_bwd", 0) * 1e3, (16 + 8 * C) * ns + (20 + 8 * C) * n_rays),
+        "hashgrid_gather": ("hbm", kt.get("hashgrid_gather", 0), (12 + 1024 + 64) * M),
+        "hashgrid_scatter": ("hbm", kt.get("hashgrid_scatter", 0), (12 + 128 + 1024) * M),
+        "sigma_net_fwd": ("tensor", kt.get("sigma_net_fwd", 0), 2.0 * 38912 * M),
+        "color_net_fwd": ("tensor", kt.get("color_net_fwd", 0), 2.0 * 55296 * M),
+        "color_net_bwd": ("tensor", kt.get("color_net_bwd", 0), 6.0 * 55296 * M),
+        "sigma_net_bwd": ("tensor", kt.get("sigma_net_bwd", 0), 6.0 * 38912 * M),
+    }
+    roof = {}
+    for k, (b, us, w) in work.items():
+        if us > 0:
+            a = w / (us * 1e-6) / (1e9 if b == "hbm" else 1e12)
+            roof[k] = {"bound": b, "us": round(us, 1), "achieved": round(a, 1), "unit": "GB/s" if b == "hbm" else "TFLOP/s",
+                       "frac": round(a / (pk["hbm"] if b == "hbm" else pk["tf_sust"]), 4)}
+    del ts
+    torch.cuda.empty_cache()
+    return {"workload": f"cfg5 per-step batch on one GPU: {n_rays} rays, {ns} samples, eager fused step (no graph)",
+            "rays": n_rays, "samples": ns, "ms_per_step": ms, "rays_per_s": n_rays / (ms * 1e-3),
+            "samples_per_s": ns / (ms * 1e-3), "stage_rooflines": roof}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -388,6 +432,8 @@ def run_gpu_arm(args):
                 a_ = w / (tm * 1e-3) / (1e9 if b_ == "hbm" else 1e12)
                 out["stage_rooflines"][k] = {"bound": b_, "achieved": round(a_, 2), "unit": "GB/s" if b_ == "hbm" else "TFLOP/s",
                                              "frac": round(a_ / (pk["hbm"] if b_ == "hbm" else pk["tf_sust"]), 4)}
+    if rank == 0 and world == 1 and not args.no_large and not args.no_stages and ts.fused:
+        out["large_batch"] = large_batch_profile(model, dev, peaks())
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline()
     if rank == 0:
@@ -407,6 +453,7 @@ def main():
     ap.add_argument("--no-stages", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--no-large", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
