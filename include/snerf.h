@@ -254,6 +254,10 @@ int snerf_field_backward(const snerf_field_desc* f, const float* xyzs, const flo
 int snerf_tc_selftest(const float* A, const float* B, float* D, uint32_t N, uint32_t K, int a_mn, int b_mn,
                       snerf_stream_t stream);
 
+/* The training march uses a warp per ray up to this many rays and a thread per ray above (default 49152): the two
+ * grains produce the same bits, the crossover is a measured throughput choice. */
+void snerf_debug_set_march_warp_max_rays(uint32_t n);
+
 /* Measurement aid: which kernels of the bf16 field calls are launched (bench.py times them one by one).  Forward:
  * 1 weight packing, 2 hash-grid gather, 4 sigma net, 8 colour net; backward: 16 weight packing, 32 colour net,
  * 64 sigma net, 128 table scatter-add.  Default 0xffffffff (all); results are only meaningful with all bits set. */

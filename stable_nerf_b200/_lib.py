@@ -83,6 +83,7 @@ SIGNATURES = {
     "snerf_field_backward": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_size_t,
                                      _P, c_size_t, _S]),
     "snerf_tc_selftest": (c_int, [_P, _P, _P, _U, _U, c_int, c_int, _S]),
+    "snerf_debug_set_march_warp_max_rays": (None, [_U]),
     "snerf_debug_set_field_stage_mask": (None, [_U]),
     "snerf_debug_set_dedupe_max_res": (None, [_U]),
     "snerf_tc_probe": (c_int, [_P, c_int, _S]),

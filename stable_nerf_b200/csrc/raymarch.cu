@@ -346,6 +346,88 @@ __global__ void __launch_bounds__(kMarchThreads) k_march_train_count(MarchParams
   if (lane == 0) counts[n] = st.count;
 }
 
+__device__ __forceinline__ void zero_rows(float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+                                          uint32_t i) {
+  xyzs[(size_t)i * 3] = 0.f; xyzs[(size_t)i * 3 + 1] = 0.f; xyzs[(size_t)i * 3 + 2] = 0.f;
+  dirs[(size_t)i * 3] = 0.f; dirs[(size_t)i * 3 + 1] = 0.f; dirs[(size_t)i * 3 + 2] = 0.f;
+  reinterpret_cast<float2*>(deltas)[i] = make_float2(0.f, 0.f);
+}
+
+// Thread per ray: the reference's serial loop as it stands.  One lane does ~20x fewer instructions per ray than a
+// cooperating warp (no chain elements are tested that the skip logic would jump over), so with enough rays to fill the
+// machine (N > g_march_warp_max_rays) this is the faster grain; below that it is latency-bound (1 warp per SM at 4096
+// rays) and the warp-per-ray kernels above win.  Same bits either way.
+constexpr int kMarchThreadBlock = 128;
+
+__global__ void __launch_bounds__(kMarchThreadBlock) k_march_train_count_thread(
+    MarchParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
+    uint32_t N, const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ noises,
+    uint32_t* __restrict__ counts, float* __restrict__ t_scratch) {
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  Ray r;
+  r.load(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+  const float far = fars[n];
+  float t = ray_t0(p, nears[n], noises[n]);
+  float x, y, z, dt;
+  uint32_t num_steps = 0;
+  float* ts = t_scratch ? t_scratch + (size_t)n * p.max_steps : nullptr;
+  while (t < far && num_steps < p.max_steps) {
+    const float t_here = t;
+    if (march_iter(p, r, grid, t, x, y, z, dt)) {
+      if (ts) ts[num_steps] = t_here;
+      num_steps++;
+      t = fadd(t, dt);
+    }
+  }
+  counts[n] = num_steps;
+}
+
+__global__ void __launch_bounds__(kMarchThreadBlock) k_march_train_write_thread(
+    MarchParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
+    uint32_t N, uint32_t M, const float* __restrict__ nears, const float* __restrict__ fars,
+    const float* __restrict__ noises, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+    float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas, int32_t* __restrict__ rays,
+    int zero_unwritten, int32_t* __restrict__ n_samples_out) {
+  const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t total = offsets[N];
+  if (n == 0 && n_samples_out) *n_samples_out = (int32_t)total;
+  if (zero_unwritten)  // alignment padding: rows [total, M)
+    for (uint32_t i = total + n; i < M; i += gridDim.x * blockDim.x) zero_rows(xyzs, dirs, deltas, i);
+  if (n >= N) return;
+  const uint32_t num_steps = counts[n], point_index = offsets[n];
+  rays[n * 3] = (int32_t)n;
+  rays[n * 3 + 1] = (int32_t)point_index;
+  rays[n * 3 + 2] = (int32_t)num_steps;
+  if (num_steps == 0) return;
+  if (point_index + num_steps > M) {  // raymarching.cu:417: overflowing rays are dropped
+    if (zero_unwritten)
+      for (uint32_t i = point_index; i < M && i < point_index + num_steps; i++) zero_rows(xyzs, dirs, deltas, i);
+    return;
+  }
+  Ray r;
+  r.load(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+  const float far = fars[n];
+  float t = ray_t0(p, nears[n], noises[n]);
+  float last_t = t;
+  float* px = xyzs + (size_t)point_index * 3;
+  float* pd = dirs + (size_t)point_index * 3;
+  float2* pl = reinterpret_cast<float2*>(deltas) + point_index;
+  uint32_t step = 0;
+  float x, y, z, dt;
+  while (t < far && step < num_steps) {
+    if (march_iter(p, r, grid, t, x, y, z, dt)) {
+      px[0] = x; px[1] = y; px[2] = z;
+      pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+      t = fadd(t, dt);
+      *pl = make_float2(dt, fadd(t, -last_t));
+      last_t = t;
+      px += 3; pd += 3; pl += 1;
+      step++;
+    }
+  }
+}
+
 // single block: offsets[n] = exclusive scan of counts (ray order), offsets[N] = total; counter[0] += total,
 // counter[1] += N (what the reference's atomics leave, raymarching.cu:406-407)
 __global__ void __launch_bounds__(1024) k_march_train_scan(const uint32_t* __restrict__ counts, uint32_t N,
@@ -374,12 +456,6 @@ __global__ void __launch_bounds__(1024) k_march_train_scan(const uint32_t* __res
   }
 }
 
-__device__ __forceinline__ void zero_rows(float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
-                                          uint32_t i) {
-  xyzs[(size_t)i * 3] = 0.f; xyzs[(size_t)i * 3 + 1] = 0.f; xyzs[(size_t)i * 3 + 2] = 0.f;
-  dirs[(size_t)i * 3] = 0.f; dirs[(size_t)i * 3 + 1] = 0.f; dirs[(size_t)i * 3 + 2] = 0.f;
-  reinterpret_cast<float2*>(deltas)[i] = make_float2(0.f, 0.f);
-}
 
 __global__ void __launch_bounds__(kMarchThreads) k_march_train_write(
     MarchParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
@@ -576,7 +652,11 @@ using namespace snerf;
 
 // ------------------------------------------------------------------------------------------------ C ABI
 
+static uint32_t g_march_warp_max_rays = 49152;  // above: thread per ray (enough rays to fill the machine)
+
 extern "C" {
+
+void snerf_debug_set_march_warp_max_rays(uint32_t n) { g_march_warp_max_rays = n; }
 
 int snerf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
                              float* nears, float* fars, snerf_stream_t stream) {
@@ -646,8 +726,12 @@ int snerf_march_rays_train_count(const float* rays_o, const float* rays_d, const
   uint32_t* counts = (uint32_t*)workspace;
   const uint32_t nblocks = div_up(N, kMarchRaysPerBlock);
   cudaStream_t s = (cudaStream_t)stream;
-  k_march_train_count<<<nblocks, kMarchThreads, 0, s>>>(p, rays_o, rays_d, grid, N, nears, fars, noises, counts,
-                                                        ws_t_scratch(workspace, workspace_bytes, N, max_steps));
+  float* ts = ws_t_scratch(workspace, workspace_bytes, N, max_steps);
+  if (N <= g_march_warp_max_rays)
+    k_march_train_count<<<nblocks, kMarchThreads, 0, s>>>(p, rays_o, rays_d, grid, N, nears, fars, noises, counts, ts);
+  else
+    k_march_train_count_thread<<<div_up(N, kMarchThreadBlock), kMarchThreadBlock, 0, s>>>(p, rays_o, rays_d, grid, N, nears,
+                                                                                        fars, noises, counts, ts);
   k_march_train_scan<<<1, 1024, 0, s>>>(counts, N, ws_offsets(workspace, N), counter);
   return finish_launch(2);
 }
@@ -671,9 +755,14 @@ int snerf_march_rays_train_write(const float* rays_o, const float* rays_d, const
         rays, zero_unwritten, n_samples_out);
     return finish_launch();
   }
-  k_march_train_write<<<nblocks, kMarchThreads, 0, (cudaStream_t)stream>>>(
-      p, rays_o, rays_d, grid, N, M, nears, fars, noises, (const uint32_t*)workspace, ws_offsets(workspace, N), xyzs,
-      dirs, deltas, rays, zero_unwritten, n_samples_out);
+  if (N <= g_march_warp_max_rays)
+    k_march_train_write<<<nblocks, kMarchThreads, 0, (cudaStream_t)stream>>>(
+        p, rays_o, rays_d, grid, N, M, nears, fars, noises, (const uint32_t*)workspace, ws_offsets(workspace, N), xyzs,
+        dirs, deltas, rays, zero_unwritten, n_samples_out);
+  else
+    k_march_train_write_thread<<<div_up(N, kMarchThreadBlock), kMarchThreadBlock, 0, (cudaStream_t)stream>>>(
+        p, rays_o, rays_d, grid, N, M, nears, fars, noises, (const uint32_t*)workspace, ws_offsets(workspace, N), xyzs,
+        dirs, deltas, rays, zero_unwritten, n_samples_out);
   return finish_launch();
 }
 

@@ -90,6 +90,14 @@ def test_near_far_and_march_train_vs_oracle(sc, built_lib, cuda):
     again = cuda_march_with_noises(sc, cuda, inp, nears, fars, keep_positions=False)  # second-march write pass
     for a, b, name in zip((counter, xyzs, dirs, deltas, rays), again, ("counter", "xyzs", "dirs", "deltas", "rays")):
         assert_bits_equal(a, b, name + " (expand vs re-march write pass)")
+    built_lib.snerf_debug_set_march_warp_max_rays(0)  # thread-per-ray grain (what large batches use)
+    try:
+        for keep in (True, False):
+            again = cuda_march_with_noises(sc, cuda, inp, nears, fars, keep_positions=keep)
+            for a, b, name in zip((counter, xyzs, dirs, deltas, rays), again, ("counter", "xyzs", "dirs", "deltas", "rays")):
+                assert_bits_equal(a, b, name + f" (thread-per-ray grain, keep_positions={keep})")
+    finally:
+        built_lib.snerf_debug_set_march_warp_max_rays(49152)
     ox, od, odl, orays, ocounter = orc.march_rays_train(inp["rays_o"], inp["rays_d"], sc.bound, inp["bitfield"],
                                                         sc.cascades, sc.H, on, of, inp["noises"], sc.dt_gamma,
                                                         sc.max_steps)
