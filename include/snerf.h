@@ -249,6 +249,23 @@ int snerf_field_backward(const snerf_field_desc* f, const float* xyzs, const flo
                          float* grad_w_sigma, float* grad_w_color, const void* saved, size_t saved_bytes,
                          void* workspace, size_t workspace_bytes, snerf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * The steps either side of the path in a training iteration
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Tail of get_rays (utils/graphics_utils.py:75-83): poses [B,4,4] row-major cam2world, pixel indices int64
+ * (row*W + col; [B,N] if inds_per_batch else [N] shared by all poses; NULL = 0..N-1) -> rays_o, rays_d [B,N,3].
+ * Pixel centres at +0.5 (:22-24), directions normalised before the rotation (:79-80). */
+int snerf_get_rays(const float* poses, float fx, float fy, float cx, float cy, uint32_t W, const int64_t* inds,
+                   uint32_t B, uint32_t N, int inds_per_batch, float* rays_o, float* rays_d, snerf_stream_t stream);
+
+/* One Adam (decoupled_weight_decay = 0, test_nerf.py:52) or AdamW (= 1, train.py:183) step of torch.optim semantics
+ * (no amsgrad) over a flat fp32 parameter tensor: n a multiple of 4, pointers 16-byte aligned; step counts from 1.
+ * zero_grad != 0 leaves grads zeroed (the next step's accumulate-into gradients need no memset). */
+int snerf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, uint32_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int decoupled_weight_decay, uint32_t step, int zero_grad,
+                    snerf_stream_t stream);
+
 /* Hardware self-test of the tcgen05 building blocks: D[128,N] = A[128,K] * B[N,K]^T (bf16 operands, fp32
  * accumulate) for one tile, with either operand staged K-major or MN-major (a_mn / b_mn).  Not on the hot path. */
 int snerf_tc_selftest(const float* A, const float* B, float* D, uint32_t N, uint32_t K, int a_mn, int b_mn,

@@ -252,3 +252,44 @@ def trunc_exp_backward(g, x):
     dx = np.empty_like(x)
     lib().orc_trunc_exp_backward(_p(g), _p(x), c_uint32(x.shape[0]), _p(dx))
     return dx
+
+
+# ---------------------------------------------------------------------------------------------- section 8f neighbours
+
+def get_rays(poses, intrinsics, W, inds=None, n=None):
+    """Ray generation, numpy restatement of the tail of utils/graphics_utils.py:6-88: pixel centres (:22-24),
+    pinhole directions (:75-78), normalisation (:79), rotation by the cam2world matrix (:80), origins (:82-83).
+    poses [B,4,4]; inds int [N] or [B,N] (row*W + col), or None for 0..n-1.  Returns rays_o, rays_d [B,N,3] fp32."""
+    poses = np.asarray(poses, np.float32)
+    B = poses.shape[0]
+    fx, fy, cx, cy = (np.float32(v) for v in intrinsics)
+    if inds is None:
+        inds = np.arange(n, dtype=np.int64)
+    inds = np.asarray(inds, np.int64)
+    if inds.ndim == 1:
+        inds = np.broadcast_to(inds, (B, inds.shape[0]))
+    i = (inds % W).astype(np.float32) + np.float32(0.5)
+    j = (inds // W).astype(np.float32) + np.float32(0.5)
+    xs, ys, zs = (i - cx) / fx, (j - cy) / fy, np.ones_like(i)
+    d = np.stack([xs, ys, zs], -1)
+    d = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    rays_d = np.einsum('bnc,bkc->bnk', d, poses[:, :3, :3]).astype(np.float32)
+    rays_o = np.broadcast_to(poses[:, None, :3, 3], rays_d.shape).astype(np.float32)
+    return rays_o, rays_d
+
+
+def adam_step(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False):
+    """One step of torch.optim.Adam (decoupled=False; test_nerf.py:52) / AdamW (True; train.py:183) as documented by
+    torch (no amsgrad): fp32 state, bias corrections as python doubles.  Returns new (p, m, v)."""
+    p, g, m, v = (np.asarray(a, np.float32).copy() for a in (p, g, m, v))
+    b1, b2 = betas
+    if decoupled:
+        p *= np.float32(1.0 - lr * weight_decay)
+    elif weight_decay != 0:
+        g = g + np.float32(weight_decay) * p
+    m = m + (g - m) * np.float32(1.0 - b1)
+    v = v * np.float32(b2) + np.float32(1.0 - b2) * g * g
+    bc1, bc2 = 1.0 - b1 ** step, 1.0 - b2 ** step
+    denom = np.sqrt(v) * np.float32(1.0 / np.sqrt(bc2)) + np.float32(eps)
+    p = p - np.float32(lr / bc1) * (m / denom)
+    return p.astype(np.float32), m.astype(np.float32), v.astype(np.float32)
