@@ -99,6 +99,8 @@ struct TcParams {
   __nv_bfloat16* geo;    // [M,16] bf16: (geo0..geo14, sigma_raw) written by the sigma net, read by the colour net
   __nv_bfloat16* enc;    // [M,32] bf16 hash-grid features (k_hashgrid_fwd): input of the sigma net, forward and backward
   int enc_ready;         // forward: enc already holds the features (otherwise the kernel gathers them itself)
+  float4* rgb_y;         // [M] colour net outputs after the sigmoid (padded to 4): written by the colour forward,
+                         // read by its backward instead of recomputing the output layer
   // backward
   const float* grad_sigmas;
   const float* grad_rgbs;
@@ -327,7 +329,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_field_fwd(const TcParams p) 
             if (p.geo_f32)
               for (int k = 0; k < 15; k++) p.geo_f32[(size_t)m * 15 + k] = v[1 + k];
           } else {
-            for (uint32_t c = 0; c < p.C; c++) p.rgbs[(size_t)m * p.C + c] = 1.0f / (1.0f + __expf(-v[c]));  // sigmoid, :59
+            float y[SNERF_MAX_CHANNELS];
+#pragma unroll
+            for (int c = 0; c < SNERF_MAX_CHANNELS; c++) y[c] = (uint32_t)c < p.C ? 1.0f / (1.0f + __expf(-v[c])) : 0.f;  // sigmoid, :59
+            for (uint32_t c = 0; c < p.C; c++) p.rgbs[(size_t)m * p.C + c] = y[c];
+            if (p.rgb_y) p.rgb_y[m] = make_float4(y[0], y[1], y[2], y[3]);
           }
         }
         // the next tile's worker_sync orders these TMEM reads before the MMA that overwrites the accumulator
@@ -468,18 +474,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
           __syncwarp();
         }
       }
-      meet();
+      // ---- last matrix W_L [16 x 128].  The output layer is not recomputed: the gradient of the raw output (S) was
+      // built at the start of the tile from the forward's saved outputs.
+      meet();  // a_L written
       const uint32_t s_aL = smem_u32(a_hid(L));
-      const uint32_t sw_last = next_slot();  // W_L stays in its slot until the last layer's dgrad has read it
-      if (elect_one()) {
-        constexpr uint32_t idesc = make_idesc(kTile, 16u, false, false);
-#pragma unroll
-        for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_kmajor(s_aL, kTile, s), desc_kmajor(sw_last, 16u, s), idesc, s > 0);
-        mma_commit(&mbar);
-      }
-      __syncwarp();
-      // ---- last matrix W_L [16 x 128]
-      meet();  // gradient of the raw output written to S
       if (elect_one()) {  // wgrad (transposed): D[k, n] = sum_j a_L[j,k] g_out[j,n]
         constexpr uint32_t idesc = make_idesc(kTile, 16u, true, true);
 #pragma unroll
@@ -488,12 +486,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
       }
       __syncwarp();
       meet();  // accumulator read
-      if (elect_one()) {  // dgrad: D[m, k] = sum_n g_out[m,n] W_L[n,k]   (B = the W_L image read MN-major, rows = n)
-        mma_ss(tmem, desc_kmajor(s_e, kTile, 0), desc_mnmajor(sw_last, 16u, 0), make_idesc(kTile, kTile, false, true), false);
-        mma_commit(slot_empty_bar(sw_last));
-        mma_commit(&mbar);
+      {
+        const uint32_t sw_last = next_slot();
+        if (elect_one()) {  // dgrad: D[m, k] = sum_n g_out[m,n] W_L[n,k]   (B = the W_L image read MN-major, rows = n)
+          mma_ss(tmem, desc_kmajor(s_e, kTile, 0), desc_mnmajor(sw_last, 16u, 0), make_idesc(kTile, kTile, false, true), false);
+          mma_commit(slot_empty_bar(sw_last));
+          mma_commit(&mbar);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       // ---- hidden matrices W_{L-1} .. W_1 [128 x 128]
       uint32_t sg = s_e, sgn = s_aL;
       for (int i = L - 1; i >= 1; i--) {
@@ -523,22 +524,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
         __syncwarp();
         const uint32_t tmp = sg; sg = sgn; sgn = tmp;
       }
-      // ---- first matrix W_0 [128 x 32]
+      // ---- first matrix W_0 [128 x 32]: wgrad into columns [0,32), dgrad into [32,64), one phase
       meet();
-      if (elect_one()) {  // wgrad: D[n, k] = sum_j g_1[j,n] a_0[j,k]
-        constexpr uint32_t idesc = make_idesc(kTile, 32u, true, true);
-#pragma unroll
-        for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_mnmajor(sg, kTile, s), desc_mnmajor(s_a0, kTile, s), idesc, s > 0);
-        mma_commit(&mbar);
-      }
-      __syncwarp();
-      meet();  // accumulator read
       {
         const uint32_t sw = next_slot();
-        if (elect_one()) {  // dgrad: D[m, k] = sum_n g_1[m,n] W_0[n,k],  k < 32
-          constexpr uint32_t idesc = make_idesc(kTile, 32u, false, true);
+        if (elect_one()) {
+          constexpr uint32_t id_w = make_idesc(kTile, 32u, true, true), id_d = make_idesc(kTile, 32u, false, true);
+          // wgrad: D[n, k] = sum_j g_1[j,n] a_0[j,k]
 #pragma unroll
-          for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_kmajor(sg, kTile, s), desc_mnmajor(sw, kTile, s), idesc, s > 0);
+          for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_mnmajor(sg, kTile, s), desc_mnmajor(s_a0, kTile, s), id_w, s > 0);
+          // dgrad: D[m, k] = sum_n g_1[m,n] W_0[n,k],  k < 32
+#pragma unroll
+          for (uint32_t s = 0; s < 8; s++) mma_ss(tmem + 32u, desc_kmajor(sg, kTile, s), desc_mnmajor(sw, kTile, s), id_d, s > 0);
           mma_commit(slot_empty_bar(sw));
           mma_commit(&mbar);
         }
@@ -577,9 +574,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
 #pragma unroll
     for (int k = 0; k < 16; k++) acc_last[k] = 0.f;
 
-    // this thread's half of the input row of tile t, in registers (fetched one tile ahead of its use)
+    // This thread's half of the input row of tile t and (hc == 0) what the row's gradient of the raw network output is
+    // made of, loaded into registers one tile ahead of their use; nothing here depends on a loaded value, so the loads
+    // stay in flight under the running phase and are first touched at the start of the next tile.
     uint4 in_regs[2];
-    auto fetch_tile_input = [&](uint32_t t) {
+    float4 ug[4];   // NET 0: d loss / d geo (colour backward);   NET 1: [0] = sigmoid outputs y
+    float us[4];    // NET 0: [0] = d loss / d sigma;   NET 1: d loss / d rgb
+    uint32_t sraw_bits = 0;  // NET 0: sigma_raw as stored by the forward (bf16 bits)
+    auto fetch_tile = [&](uint32_t t) {
       const uint32_t mm = t * kTile + row;
       if (NET == 0 && p.enc) {
         if (hc == 0) fetch_input<NET, 0, 2, true>(p, mm, in_regs);
@@ -588,32 +590,58 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
         if (hc == 0) fetch_input<NET, 0, 2, false>(p, mm, in_regs);
         else fetch_input<NET, 2, 2, false>(p, mm, in_regs);
       }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { ug[k] = make_float4(0.f, 0.f, 0.f, 0.f); us[k] = 0.f; }
+      if (hc == 0 && mm < p.M) {
+        if (NET == 0) {
+          us[0] = __ldg(p.grad_sigmas + mm);
+          sraw_bits = __ldg(reinterpret_cast<const unsigned short*>(p.geo) + (size_t)mm * 16 + 15);
+          const float4* gg = reinterpret_cast<const float4*>(p.g_geo + (size_t)mm * 16);
+#pragma unroll
+          for (int k = 0; k < 4; k++) ug[k] = __ldg(gg + k);
+        } else {
+          ug[0] = __ldg(p.rgb_y + mm);
+#pragma unroll
+          for (int c = 0; c < SNERF_MAX_CHANNELS; c++)
+            if ((uint32_t)c < p.C) us[c] = __ldg(p.grad_rgbs + (size_t)mm * p.C + c);
+        }
+      }
     };
-    if (blockIdx.x < n_tiles) fetch_tile_input(blockIdx.x);
+    // gradient of the raw output of this thread's row (16 columns, bf16) from the prefetched pieces
+    auto out_grad = [&](uint4 (&og)[2]) {
+      float go[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) go[k] = 0.f;
+      if (NET == 0) {  // d/d sigma_raw through the ReLU (nerf/network.py:46) + d/d geo from the colour net
+        go[0] = __uint_as_float(sraw_bits << 16) > 0.f ? us[0] : 0.f;
+        go[1] = ug[0].x; go[2] = ug[0].y; go[3] = ug[0].z; go[4] = ug[0].w; go[5] = ug[1].x; go[6] = ug[1].y;
+        go[7] = ug[1].z; go[8] = ug[1].w; go[9] = ug[2].x; go[10] = ug[2].y; go[11] = ug[2].z; go[12] = ug[2].w;
+        go[13] = ug[3].x; go[14] = ug[3].y; go[15] = ug[3].z;
+      } else {  // through the sigmoid (nerf/network.py:59): y (1 - y) from the forward's saved outputs
+        const float y[4] = {ug[0].x, ug[0].y, ug[0].z, ug[0].w};
+#pragma unroll
+        for (int c = 0; c < SNERF_MAX_CHANNELS; c++) go[c] = us[c] * y[c] * (1.0f - y[c]);
+      }
+      og[0] = make_uint4(pack_bf16(go[0], go[1]), pack_bf16(go[2], go[3]), pack_bf16(go[4], go[5]), pack_bf16(go[6], go[7]));
+      og[1] = make_uint4(pack_bf16(go[8], go[9]), pack_bf16(go[10], go[11]), pack_bf16(go[12], go[13]), pack_bf16(go[14], go[15]));
+    };
+    if (blockIdx.x < n_tiles) fetch_tile(blockIdx.x);
 
     for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, iter++) {
       const uint32_t m = t * kTile + row;
       mark(0);
-      // ---------------- forward recompute
-      if (hc == 0) store_input<0, 2>(in_regs, row, a0);
-      else store_input<2, 2>(in_regs, row, a0);
+      // ---------------- input tile + gradient of the raw output (S), then the forward recompute of a_1 .. a_L
+      if (hc == 0) {
+        uint4 og[2];
+        out_grad(og);
+        store_input<0, 2>(in_regs, row, a0);
+        st_group(sbuf, kTile, row, 0, 0, og[0]);
+        st_group(sbuf, kTile, row, 0, 1, og[1]);
+      } else {
+        store_input<2, 2>(in_regs, row, a0);
+      }
       hand_over();
       mark(1);
-      // the upstream gradients of this tile's rows: issued now, consumed after the forward recompute
-      float up[16];
-#pragma unroll
-      for (int k = 0; k < 16; k++) up[k] = 0.f;
-      if (hc == 0 && m < p.M) {
-        if (NET == 0) {
-          up[0] = __ldg(p.grad_sigmas + m);
-          const float4* gg = reinterpret_cast<const float4*>(p.g_geo + (size_t)m * 16);
-          const float4 x0 = __ldg(gg), x1 = __ldg(gg + 1), x2 = __ldg(gg + 2), x3 = __ldg(gg + 3);
-          up[1] = x0.x; up[2] = x0.y; up[3] = x0.z; up[4] = x0.w; up[5] = x1.x; up[6] = x1.y; up[7] = x1.z; up[8] = x1.w;
-          up[9] = x2.x; up[10] = x2.y; up[11] = x2.z; up[12] = x2.w; up[13] = x3.x; up[14] = x3.y; up[15] = x3.z;
-        } else {
-          for (uint32_t c = 0; c < p.C; c++) up[c] = __ldg(p.grad_rgbs + (size_t)m * p.C + c);
-        }
-      }
       for (int i = 0; i < L; i++) {
         wait_mma();
         mark(2);
@@ -622,36 +650,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
         hand_over();
         mark(4);
       }
-      wait_mma();
-      mark(5);
-      {  // gradient of the raw output (16 columns) -> S
-        uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0;
-        if (hc == 0) {
-          float v[16], go[16];
-          tmem_ld16(tlane, v);
-#pragma unroll
-          for (int k = 0; k < 16; k++) go[k] = 0.f;
-          if (m < p.M) {
-            if (NET == 0) {
-              go[0] = v[0] > 0.f ? up[0] : 0.f;
-#pragma unroll
-              for (int k = 1; k < 16; k++) go[k] = up[k];
-            } else {
-#pragma unroll
-              for (int c = 0; c < SNERF_MAX_CHANNELS; c++) {
-                const float y = 1.0f / (1.0f + __expf(-v[c]));
-                go[c] = (uint32_t)c < p.C ? up[c] * y * (1.0f - y) : 0.f;
-              }
-            }
-          }
-          g0 = make_uint4(pack_bf16(go[0], go[1]), pack_bf16(go[2], go[3]), pack_bf16(go[4], go[5]), pack_bf16(go[6], go[7]));
-          g1 = make_uint4(pack_bf16(go[8], go[9]), pack_bf16(go[10], go[11]), pack_bf16(go[12], go[13]), pack_bf16(go[14], go[15]));
-          st_group(sbuf, kTile, row, 0, 0, g0);
-          st_group(sbuf, kTile, row, 0, 1, g1);
-        }
-      }
-      hand_over();
-      mark(6);
 
       // ---------------- last matrix W_L [16 x 128]
       wait_mma();  // wgrad
@@ -681,9 +679,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
         uint8_t* tmp = gcur; gcur = gnext; gnext = tmp;
       }
 
-      // ---------------- first matrix W_0 [128 x 32]
-      if (t + gridDim.x < n_tiles) fetch_tile_input(t + gridDim.x);  // lands while the last two phases run
-      wait_mma();  // wgrad
+      // ---------------- first matrix W_0 [128 x 32]: wgrad in columns [0,32), input gradient in [32,64)
+      if (t + gridDim.x < n_tiles) fetch_tile(t + gridDim.x);  // lands while the last phase runs
+      wait_mma();
       mark(12);
       if (hc == 0) {
         float v[32];
@@ -691,12 +689,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
 #pragma unroll
         for (int k = 0; k < 32; k++) acc_first[k] += v[k];
       }
-      hand_over_tmem();
-      wait_mma();  // dgrad
-      mark(13);
       {
         float v[16];
-        tmem_ld16(tlane + hc * 16u, v);  // input-gradient columns 16hc .. 16hc+15 of row `row`
+        tmem_ld16(tlane + 32u + hc * 16u, v);  // input-gradient columns 16hc .. 16hc+15 of row `row`
         if (m < p.M) {
           if (NET == 1) {
             if (hc == 1) {  // columns 16..30 = d loss / d geo
@@ -775,14 +770,16 @@ struct TcWorkspace {
   uint8_t* wimg_color;
   __nv_bfloat16* geo;
   __nv_bfloat16* enc;
+  float4* rgb_y;
   float* g_geo;
   float* d_enc;
   float* dw_part;  // per-CTA partial weight gradients of one net at a time (max of the two nets)
 };
 
-// forward -> backward hand-off buffer: [geo: M x 16 bf16][pad to 1 KiB][enc: M x 32 bf16]
+// forward -> backward hand-off buffer: [geo: M x 16 bf16][enc: M x 32 bf16][y: M x 4 f32], each padded to 1 KiB
 static size_t saved_geo_bytes(uint32_t M) { return align_up((size_t)(M ? M : 1) * 16 * sizeof(__nv_bfloat16), 1024); }
-size_t field_tc_saved_bytes(uint32_t M) { return saved_geo_bytes(M) + (size_t)(M ? M : 1) * 32 * sizeof(__nv_bfloat16); }
+static size_t saved_enc_bytes(uint32_t M) { return align_up((size_t)(M ? M : 1) * 32 * sizeof(__nv_bfloat16), 1024); }
+size_t field_tc_saved_bytes(uint32_t M) { return saved_geo_bytes(M) + saved_enc_bytes(M) + (size_t)(M ? M : 1) * sizeof(float4); }
 
 static size_t carve_tc(const snerf_field_desc* f, uint32_t M, int backward, char* base, TcWorkspace* w) {
   const PackedNet ps = make_packed(sigma_shape(f)), pc = make_packed(color_shape(f));
@@ -800,6 +797,7 @@ static size_t carve_tc(const snerf_field_desc* f, uint32_t M, int backward, char
   char* hand = take(field_tc_saved_bytes(M));  // used when the caller passes no hand-off buffer
   o.geo = (__nv_bfloat16*)hand;
   o.enc = (__nv_bfloat16*)(hand ? hand + saved_geo_bytes(M) : nullptr);
+  o.rgb_y = (float4*)(hand ? hand + saved_geo_bytes(M) + saved_enc_bytes(M) : nullptr);
   o.g_geo = backward ? (float*)take((size_t)(M ? M : 1) * 16 * sizeof(float)) : nullptr;
   o.d_enc = backward ? (float*)take((size_t)(M ? M : 1) * 32 * sizeof(float)) : nullptr;
   o.dw_part = backward ? (float*)take((size_t)kMaxGrid * std::max(sigma_shape(f).n_params, color_shape(f).n_params) * sizeof(float)) : nullptr;
@@ -889,6 +887,7 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
   if (saved) {  // the geometry features and the encoded inputs go straight into the hand-off buffer
     w.geo = (__nv_bfloat16*)saved;
     w.enc = (__nv_bfloat16*)((char*)saved + saved_geo_bytes(M));
+    w.rgb_y = (float4*)((char*)saved + saved_geo_bytes(M) + saved_enc_bytes(M));
   }
   const PackedNet ps = make_packed(sigma_shape(f)), pc = make_packed(color_shape(f));
   const uint32_t st = g_stage_mask;
@@ -922,6 +921,7 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
     fill_common(p, f, pc, M, xyzs, dirs, table, w.wimg_color);
     p.geo = w.geo;
     p.rgbs = rgbs;
+    p.rgb_y = w.rgb_y;
     if (int e = set_smem(k_field_fwd<1>, fwd_smem(pc))) return e;
     k_field_fwd<1><<<grid_for(M), kFwdThreads, fwd_smem(pc), s>>>(p);
     launches++;
@@ -955,6 +955,7 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   if (saved) {
     w.geo = (__nv_bfloat16*)const_cast<void*>(saved);
     w.enc = (__nv_bfloat16*)((char*)const_cast<void*>(saved) + saved_geo_bytes(M));
+    w.rgb_y = (float4*)((char*)const_cast<void*>(saved) + saved_geo_bytes(M) + saved_enc_bytes(M));
   } else {
     fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
     p.sigmas = w.g_geo;  // scratch: any M floats, overwritten by step 2
@@ -964,11 +965,19 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
     p.enc_ready = 1;
     if (int e = set_smem(k_field_fwd<0>, fwd_smem(ps))) return e;
     k_field_fwd<0><<<grid_for(M), kFwdThreads, fwd_smem(ps), s>>>(p);
-    launches++;
+    // ... and the colour net's, for its post-sigmoid outputs (the rgb scratch is the not-yet-used d_enc buffer)
+    fill_common(p, f, pc, M, xyzs, dirs, table, w.wimg_color);
+    p.geo = w.geo;
+    p.rgbs = w.d_enc;
+    p.rgb_y = w.rgb_y;
+    if (int e = set_smem(k_field_fwd<1>, fwd_smem(pc))) return e;
+    k_field_fwd<1><<<grid_for(M), kFwdThreads, fwd_smem(pc), s>>>(p);
+    launches += 2;
   }
   // 2. colour net: recompute + dgrad + wgrad; writes d loss / d geo
   fill_common(p, f, pc, M, xyzs, dirs, table, w.wimg_color);
   p.geo = w.geo;
+  p.rgb_y = w.rgb_y;
   p.grad_rgbs = grad_rgbs;
   p.g_geo = w.g_geo;
   p.grad_w = grad_w_color;
@@ -982,6 +991,7 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   // 3. sigma net: recompute from the saved encoding + dgrad + wgrad + table scatter-add
   fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
   p.enc = w.enc;
+  p.geo = w.geo;
   p.grad_sigmas = grad_sigmas;
   p.g_geo = w.g_geo;
   p.grad_w = grad_w_sigma;
