@@ -21,7 +21,9 @@ def timed(name, fn):
     e0.record(); r = fn(); e1.record()
     acc.setdefault(name, []).append((e0, e1))
     return r
-with torch.no_grad():
+import itertools
+for MIN_STEP in (1, 2, 4):
+  with torch.no_grad():
     for rep in range(2):
         acc.clear()
         torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -31,7 +33,7 @@ with torch.no_grad():
         count = torch.empty(1, dtype=torch.int32, device=dev); rays_t = nears.clone()
         n_alive, step, iters, hist = N, 0, 0, []
         while step < max_steps and n_alive > 0:
-            n_step = max(min(N // n_alive, 8), 1)
+            n_step = max(min(N // n_alive, 8), MIN_STEP)
             xyzs, dirs, deltas = timed("march", lambda: rm.march_rays(n_alive, n_step, alive, rays_t, ro, rd, model.bound, model.density_bitfield, model.cascade, model.grid_size, nears, fars, 128, False, 0, max_steps))
             sig, rgb = timed("field", lambda: model(xyzs, dirs))
             timed("composite", lambda: rm.composite_rays(n_alive, n_step, alive, rays_t, sig, rgb, deltas, ws, depth, image, T_thresh, 3))
@@ -40,6 +42,6 @@ with torch.no_grad():
             hist.append((n_alive, n_step))
             n_alive = int(count.item()); step += n_step; iters += 1
         torch.cuda.synchronize(); wall = (time.perf_counter() - t0) * 1e3
-    tot = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in acc.items()}
-print("iterations", iters, "wall ms", round(wall, 2), "device ms by category", {k: round(v, 2) for k, v in tot.items()}, "sum", round(sum(tot.values()), 2))
-print("n_alive/n_step history (every 8th):", hist[::8])
+  tot = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in acc.items()}
+  print("min n_step", MIN_STEP, "iterations", iters, "wall ms", round(wall, 2), "device ms by category", {k: round(v, 2) for k, v in tot.items()}, "sum", round(sum(tot.values()), 2))
+  print("n_alive/n_step history (every 8th):", hist[::8])

@@ -218,3 +218,27 @@ def test_fused_train_step_matches_autograd_step(precision, C, bg, built_lib, cud
     tol = 1e-4 if precision == "fp32" else 2e-3  # bf16: atomics order feeds bf16 roundings downstream
     assert abs(res[True][0] - res[False][0]) <= 1e-6 * abs(res[False][0])
     assert rel_err(res[True][1], res[False][1]) <= tol and rel_err(res[True][2], res[False][2]) <= tol
+
+
+def test_inference_schedule_changes_the_image_by_rounding_only(built_lib, cuda):
+    """min_n_step only changes how many samples are marched per loop iteration (nerf/renderer.py:146 starts at 1).
+    weights_sum / depth / image are accumulated per ray in sample order either way; rays_t is re-accumulated from the
+    deltas between iterations (as in the reference), which moves positions by an ulp -> images agree to 1e-5."""
+    from stable_nerf_b200 import NeRFNetwork, synthetic as syn
+    model = NeRFNetwork(precision="fp32").to(cuda)
+    with torch.no_grad():
+        model.sigma_net.params[model.sigma_net.n_mlp:] *= 1e4
+    model.density_bitfield.copy_(torch.from_numpy(syn.pack_bitfield(syn.occupancy_grid(lego_like=True))))
+    model.eval()
+    assert model.min_n_step == 1  # the reference's schedule is the default
+    ro, rd = syn.train_batch(3000, 100, 100, 138.0, n_views=2, seed=11)
+    o, d = torch.from_numpy(ro).to(cuda)[None], torch.from_numpy(rd).to(cuda)[None]
+    outs = {}
+    with torch.no_grad():
+        for k in (1, 4, 8):
+            model.min_n_step = k
+            r = model.render(o, d, bg_color=1, max_steps=256)
+            outs[k] = (r["image"].cpu().numpy(), r["depth"].cpu().numpy(), model.last_render_stats["iterations"])
+    assert outs[4][2] < outs[1][2]
+    for k in (4, 8):
+        assert rel_err(outs[k][0], outs[1][0]) <= 1e-5 and rel_err(outs[k][1], outs[1][1]) <= 1e-5
