@@ -52,6 +52,53 @@ __device__ __forceinline__ float corner_weight(const Cell& c, uint32_t corner) {
   return fmul(fmul(wx, wy), wz);
 }
 
+// ---------------------------------------------------------------------------------------------- table scatter-add
+// One (sample, level) gradient per lane, 32 consecutive samples of ONE level per warp (warp-uniform control flow).
+// The SM retires about one reduction LANE per cycle and same-address reductions serialise at the L2, so the warp issues
+// fewer lanes: runs of lanes with equal (index0, index1) -- consecutive samples of a ray in the same cell -- are summed
+// with a segmented scan first and only the last lane of a run issues (`dedupe`); the two corners that differ in x are
+// adjacent entries whenever index0 is even: one 16-byte red.global.add.v4.f32 instead of two v2's (`pairing`).
+__device__ __forceinline__ void red_pair(float2* __restrict__ grad_table, uint32_t i0, uint32_t i1, float4 v, bool pairing) {
+  if (pairing && i1 == i0 + 1u && (i0 & 1u) == 0u) {
+    atomicAdd(reinterpret_cast<float4*>(grad_table + i0), v);
+  } else {
+    atomicAdd(grad_table + i0, make_float2(v.x, v.y));
+    atomicAdd(grad_table + i1, make_float2(v.z, v.w));
+  }
+}
+
+__device__ __forceinline__ void scatter_level(const LevelInfo& li, const Cell& c, float2 gv, bool active, bool dedupe,
+                                              bool pairing, int lane, float2* __restrict__ grad_table) {
+#pragma unroll
+  for (uint32_t kp = 0; kp < 4; kp++) {  // corner pair (x, x+1) at (y + kp&1, z + kp>>1)
+    const uint32_t cy = c.c[1] + (kp & 1u), cz = c.c[2] + (kp >> 1);
+    uint32_t i0 = grid_index(li, c.c[0], cy, cz), i1 = grid_index(li, c.c[0] + 1u, cy, cz);
+    const float w0 = corner_weight(c, kp * 2u), w1 = corner_weight(c, kp * 2u + 1u);
+    float4 v = make_float4(w0 * gv.x, w0 * gv.y, w1 * gv.x, w1 * gv.y);
+    if (!dedupe) {
+      if (active) red_pair(grad_table, i0, i1, v, pairing);
+      continue;
+    }
+    if (!active) { i0 = 0xffffffffu - (uint32_t)lane; i1 = i0; }  // a run of its own, value zero
+    const uint32_t p0 = __shfl_up_sync(kFull, i0, 1), p1 = __shfl_up_sync(kFull, i1, 1);
+    const bool head = lane == 0 || p0 != i0 || p1 != i1;
+    bool f = head;  // a run head lies inside the span summed so far
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float ux = __shfl_up_sync(kFull, v.x, d), uy = __shfl_up_sync(kFull, v.y, d);
+      const float uz = __shfl_up_sync(kFull, v.z, d), uw = __shfl_up_sync(kFull, v.w, d);
+      const bool uf = __shfl_up_sync(kFull, (int)f, d) != 0;
+      if (lane >= d && !f) { v.x += ux; v.y += uy; v.z += uz; v.w += uw; f = uf; }
+    }
+    const bool next_head = __shfl_down_sync(kFull, (int)head, 1) != 0;
+    const bool tail = lane == 31 || next_head;
+    if (tail && active) red_pair(grad_table, i0, i1, v, pairing);
+  }
+}
+
+// swizzled position of the float2 slot (sample s, level l) inside a [rows][16] float2 tile
+__device__ __forceinline__ int tile_slot(int s, int l) { return s * 16 + (l ^ (s & 15)); }
+
 // degree-4 real spherical harmonics of 2*d01-1 (SURVEY Appendix A constants)
 __device__ __forceinline__ void sh4_eval(float x01, float y01, float z01, float* o) {
   const float x = x01 * 2.0f - 1.0f, y = y01 * 2.0f - 1.0f, z = z01 * 2.0f - 1.0f;

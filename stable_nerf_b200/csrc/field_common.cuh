@@ -55,6 +55,7 @@ int launch_hashgrid_fwd(const snerf_grid_desc* g, const float* x, bool normalize
                         uint32_t M, float* enc, cudaStream_t s);
 int launch_hashgrid_fwd_bf16(const snerf_grid_desc* g, const float* x, float bound, const float* table, uint32_t M,
                              void* enc_bf16, cudaStream_t s);
+uint32_t hashgrid_dedupe_max_res();
 int launch_hashgrid_bwd(const snerf_grid_desc* g, const float* x, bool normalize, float bound, const float* grad_enc,
                         uint32_t M, float* grad_table, cudaStream_t s);
 

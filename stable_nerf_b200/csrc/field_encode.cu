@@ -22,8 +22,6 @@ namespace snerf {
 constexpr int kEncTile = 128;    // samples per CTA
 constexpr int kEncThreads = 256;
 
-// swizzled position of the float2 slot (sample s, level l) inside a [kEncTile][16] float2 tile
-__device__ __forceinline__ int tile_slot(int s, int l) { return s * 16 + (l ^ (s & 15)); }
 
 // kBf16Out: the features are rounded to bf16 (RNE) and stored as [M, 2L] bf16 -- the operand format of the tensor-core
 // sigma net (field_tc.cu), which then reads its input tile instead of gathering it.
@@ -87,15 +85,6 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_fwd(snerf_grid_desc g,
 //   * samples whose gradient is exactly zero (padding, terminated rays) issue nothing.
 static uint32_t g_dedupe_max_res = 300;  // tunable through snerf_debug_set_dedupe_max_res (measurement aid)
 
-__device__ __forceinline__ void red_pair(float2* __restrict__ grad_table, uint32_t i0, uint32_t i1, float4 v, bool pairing) {
-  if (pairing && i1 == i0 + 1u && (i0 & 1u) == 0u) {
-    atomicAdd(reinterpret_cast<float4*>(grad_table + i0), v);
-  } else {
-    atomicAdd(grad_table + i0, make_float2(v.x, v.y));
-    atomicAdd(grad_table + i1, make_float2(v.z, v.w));
-  }
-}
-
 template <bool kNormalize>
 __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g, const float* __restrict__ x,
                                                               float bound, const float* __restrict__ grad_enc,
@@ -125,33 +114,7 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g,
     const LevelInfo li = level_info(g, l);
     const uint32_t sc = s < ns ? s : 0u;
     const Cell c = grid_cell(xs[sc * 3], xs[sc * 3 + 1], xs[sc * 3 + 2], li.scale);
-    const bool pairing = !(dedupe_max_res >> 31);
-    const bool dedupe = li.res <= (dedupe_max_res & 0x7fffffffu);
-#pragma unroll
-    for (uint32_t kp = 0; kp < 4; kp++) {  // corner pair (x, x+1) at (y + kp&1, z + kp>>1)
-      const uint32_t cy = c.c[1] + (kp & 1u), cz = c.c[2] + (kp >> 1);
-      uint32_t i0 = grid_index(li, c.c[0], cy, cz), i1 = grid_index(li, c.c[0] + 1u, cy, cz);
-      const float w0 = corner_weight(c, kp * 2u), w1 = corner_weight(c, kp * 2u + 1u);
-      float4 v = make_float4(w0 * gv.x, w0 * gv.y, w1 * gv.x, w1 * gv.y);
-      if (!dedupe) {
-        if (active) red_pair(grad_table, i0, i1, v, pairing);
-        continue;
-      }
-      if (!active) { i0 = 0xffffffffu - (uint32_t)lane; i1 = i0; }  // a run of its own, value zero
-      const uint32_t p0 = __shfl_up_sync(kFull, i0, 1), p1 = __shfl_up_sync(kFull, i1, 1);
-      const bool head = lane == 0 || p0 != i0 || p1 != i1;
-      bool f = head;  // a run head lies inside the span summed so far
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const float ux = __shfl_up_sync(kFull, v.x, d), uy = __shfl_up_sync(kFull, v.y, d);
-        const float uz = __shfl_up_sync(kFull, v.z, d), uw = __shfl_up_sync(kFull, v.w, d);
-        const bool uf = __shfl_up_sync(kFull, (int)f, d) != 0;
-        if (lane >= d && !f) { v.x += ux; v.y += uy; v.z += uz; v.w += uw; f = uf; }
-      }
-      const bool next_head = __shfl_down_sync(kFull, (int)head, 1) != 0;
-      const bool tail = lane == 31 || next_head;
-      if (tail && active) red_pair(grad_table, i0, i1, v, pairing);
-    }
+    scatter_level(li, c, gv, active, li.res <= (dedupe_max_res & 0x7fffffffu), !(dedupe_max_res >> 31), lane, grad_table);
   }
 }
 
@@ -174,6 +137,8 @@ __global__ void __launch_bounds__(256) k_trunc_exp_bwd(const float* __restrict__
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dx[i] = g[i] * expf(fminf(fmaxf(x[i], -15.0f), 15.0f));
 }
+
+uint32_t hashgrid_dedupe_max_res() { return g_dedupe_max_res & 0x7fffffffu; }
 
 int check_grid_desc(const snerf_grid_desc* g) {
   if (!g) return SNERF_E_BADARG;

@@ -367,12 +367,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_field_fwd(const TcParams p) 
 //              W_0 | W_1 .. W_{L-1} (2 chunks each) | W_L | W_{L-1} .. W_1 | W_0.
 
 constexpr uint32_t kBwdComputeThreads = 256;
-constexpr uint32_t kBwdThreads = kBwdComputeThreads + 64;
 constexpr uint32_t kBwdSyncThreads = kBwdComputeThreads + 32;  // compute warps + issuer warp meet at barrier 1
+__host__ __device__ constexpr uint32_t bwd_threads(int) { return kBwdComputeThreads + 64u; }
+// sigma net: the first / last matrices' weight gradients accumulate in spare TMEM columns (the colour net's three hidden
+// accumulators leave none, it keeps them in registers)
+constexpr uint32_t kColFirst = 384, kColLast = 416;
 constexpr uint32_t kSlotBytes = 16384;
 
 template <int NET, uint32_t NS>
-__global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) {
+__global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int L = p.net.n_mats - 1;  // hidden activations a_1..a_L ; matrices W_0..W_L
@@ -401,7 +404,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   auto a_hid = [&](int i) { return ahid + (uint32_t)(i - 1) * kActBytes; };
-
   if (warp == kBwdComputeThreads / 32 + 1) {
     // ======================================================================================== weight producer
     if (lane == 0) {
@@ -478,15 +480,28 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
       // built at the start of the tile from the forward's saved outputs.
       meet();  // a_L written
       const uint32_t s_aL = smem_u32(a_hid(L));
-      if (elect_one()) {  // wgrad (transposed): D[k, n] = sum_j a_L[j,k] g_out[j,n]
-        constexpr uint32_t idesc = make_idesc(kTile, 16u, true, true);
+      if (NET == 0) {
+        // wgrad accumulates across tiles in its own TMEM columns, so the dgrad follows it without a round trip
+        const uint32_t sw_last = next_slot();
+        if (elect_one()) {
+          constexpr uint32_t idesc = make_idesc(kTile, 16u, true, true);
 #pragma unroll
-        for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_mnmajor(s_aL, kTile, s), desc_mnmajor(s_e, kTile, s), idesc, s > 0);
-        mma_commit(&mbar);
-      }
-      __syncwarp();
-      meet();  // accumulator read
-      {
+          for (uint32_t s = 0; s < 8; s++)
+            mma_ss(tmem + kColLast, desc_mnmajor(s_aL, kTile, s), desc_mnmajor(s_e, kTile, s), idesc, iter > 0 || s > 0);
+          mma_ss(tmem, desc_kmajor(s_e, kTile, 0), desc_mnmajor(sw_last, 16u, 0), make_idesc(kTile, kTile, false, true), false);
+          mma_commit(slot_empty_bar(sw_last));
+          mma_commit(&mbar);
+        }
+        __syncwarp();
+      } else {
+        if (elect_one()) {  // wgrad (transposed): D[k, n] = sum_j a_L[j,k] g_out[j,n]
+          constexpr uint32_t idesc = make_idesc(kTile, 16u, true, true);
+#pragma unroll
+          for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_mnmajor(s_aL, kTile, s), desc_mnmajor(s_e, kTile, s), idesc, s > 0);
+          mma_commit(&mbar);
+        }
+        __syncwarp();
+        meet();  // accumulator read
         const uint32_t sw_last = next_slot();
         if (elect_one()) {  // dgrad: D[m, k] = sum_n g_out[m,n] W_L[n,k]   (B = the W_L image read MN-major, rows = n)
           mma_ss(tmem, desc_kmajor(s_e, kTile, 0), desc_mnmajor(sw_last, 16u, 0), make_idesc(kTile, kTile, false, true), false);
@@ -532,7 +547,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
           constexpr uint32_t id_w = make_idesc(kTile, 32u, true, true), id_d = make_idesc(kTile, 32u, false, true);
           // wgrad: D[n, k] = sum_j g_1[j,n] a_0[j,k]
 #pragma unroll
-          for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_mnmajor(sg, kTile, s), desc_mnmajor(s_a0, kTile, s), id_w, s > 0);
+          for (uint32_t s = 0; s < 8; s++)
+            mma_ss(NET == 0 ? tmem + kColFirst : tmem, desc_mnmajor(sg, kTile, s), desc_mnmajor(s_a0, kTile, s), id_w,
+                   NET == 0 ? (iter > 0 || s > 0) : s > 0);
           // dgrad: D[m, k] = sum_n g_1[m,n] W_0[n,k],  k < 32
 #pragma unroll
           for (uint32_t s = 0; s < 8; s++) mma_ss(tmem + 32u, desc_kmajor(sg, kTile, s), desc_mnmajor(sw, kTile, s), id_d, s > 0);
@@ -567,12 +584,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
         p.dbg[1 + n_marks++] = (clock64() << 8) | (long long)id;
     };
 
-    float acc_first[32];  // dW_0[n = row][k < 32]     (warps with hc == 0)
-    float acc_last[16];   // dW_L[n < 16][k = row]
+    // colour net: dW_0[n = row][k < 32] (warps with hc == 0) and dW_L[n < 16][k = row] accumulate in registers
+    float acc_first[NET == 0 ? 1 : 32];
+    float acc_last[NET == 0 ? 1 : 16];
 #pragma unroll
-    for (int k = 0; k < 32; k++) acc_first[k] = 0.f;
+    for (int k = 0; k < (NET == 0 ? 1 : 32); k++) acc_first[k] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; k++) acc_last[k] = 0.f;
+    for (int k = 0; k < (NET == 0 ? 1 : 16); k++) acc_last[k] = 0.f;
 
     // This thread's half of the input row of tile t and (hc == 0) what the row's gradient of the raw network output is
     // made of, loaded into registers one tile ahead of their use; nothing here depends on a loaded value, so the loads
@@ -652,15 +670,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
       }
 
       // ---------------- last matrix W_L [16 x 128]
-      wait_mma();  // wgrad
-      mark(7);
-      if (hc == 0) {
-        float v[16];
-        tmem_ld16(tlane, v);
+      if (NET != 0) {
+        wait_mma();  // wgrad
+        mark(7);
+        if (hc == 0) {
+          float v[16];
+          tmem_ld16(tlane, v);
 #pragma unroll
-        for (int k = 0; k < 16; k++) acc_last[k] += v[k];
+          for (int k = 0; k < 16; k++) acc_last[k] += v[k];
+        }
+        hand_over_tmem();
       }
-      hand_over_tmem();
       wait_mma();  // dgrad
       mark(8);
       epi_chunk<true>(tlane + hc * 64u, ebuf, a_hid(L), row, hc);
@@ -683,7 +703,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
       if (t + gridDim.x < n_tiles) fetch_tile(t + gridDim.x);  // lands while the last phase runs
       wait_mma();
       mark(12);
-      if (hc == 0) {
+      if (NET != 0 && hc == 0) {
         float v[32];
         tmem_ld32(tlane, v);
 #pragma unroll
@@ -721,12 +741,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_bwd(const TcParams p) 
       tc_fence_after();
       float* part = p.dw_part + (size_t)blockIdx.x * p.n_params;
       if (hc == 0) {
+        float first[32], last[16];
+        if (NET == 0) {
+          tmem_ld32(tlane + kColFirst, first);
+          tmem_ld16(tlane + kColLast, last);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; k++) first[k] = acc_first[NET == 0 ? 0 : k];
+#pragma unroll
+          for (int k = 0; k < 16; k++) last[k] = acc_last[NET == 0 ? 0 : k];
+        }
         float4* g0 = reinterpret_cast<float4*>(part + p.net.src_off[0] + (size_t)row * 32);
 #pragma unroll
-        for (int k = 0; k < 8; k++) g0[k] = make_float4(acc_first[4 * k], acc_first[4 * k + 1], acc_first[4 * k + 2], acc_first[4 * k + 3]);
+        for (int k = 0; k < 8; k++) g0[k] = make_float4(first[4 * k], first[4 * k + 1], first[4 * k + 2], first[4 * k + 3]);
         float* gl = part + p.net.src_off[L];
 #pragma unroll
-        for (int n = 0; n < 16; n++) gl[(size_t)n * kTile + row] = acc_last[n];
+        for (int n = 0; n < 16; n++) gl[(size_t)n * kTile + row] = last[n];
       }
       for (int i = 1; i < L; i++) {
         float* gw = part + p.net.src_off[i] + (size_t)row * kTile + hc * 64u;
@@ -851,24 +881,35 @@ static void fill_common(TcParams& p, const snerf_field_desc* f, const PackedNet&
 static uint32_t grid_for(uint32_t M) { return min(div_up(M, kTile), min((uint32_t)sm_count(), kMaxGrid)); }
 static size_t fwd_smem(const PackedNet& n) { return n.total_bytes + (size_t)kFwdGroups * kActBytes + 1024; }
 // ring depth of the backward's weight stream: whatever the 227 KiB of shared memory leave after the activations
-static uint32_t bwd_slots(const PackedNet& n) {
-  const size_t fixed = kInBytes + (size_t)(n.n_mats - 1) * kActBytes + kActBytes + 1024 + 512 /* static */;
-  const size_t room = 227 * 1024 > fixed ? 227 * 1024 - fixed : 0;
-  return room / kSlotBytes >= 5 ? 5u : (room / kSlotBytes >= 3 ? 3u : 0u);
+static size_t bwd_fixed_smem(const PackedNet& n, int net) {  // activations + gradient tile (+ the sigma net's d-enc tile)
+  (void)net;
+  return kInBytes + (size_t)(n.n_mats - 1) * kActBytes + kActBytes;
 }
-static size_t bwd_smem(const PackedNet& n) {
-  return kInBytes + (size_t)(n.n_mats - 1) * kActBytes + kActBytes + (size_t)bwd_slots(n) * kSlotBytes + 1024;
+static uint32_t bwd_slots(const PackedNet& n, int net) {
+  const size_t fixed = bwd_fixed_smem(n, net) + 1024 + 512 /* static */;
+  const size_t room = 227 * 1024 > fixed ? 227 * 1024 - fixed : 0;
+  const size_t k = room / kSlotBytes;
+  return k >= 5 ? 5u : (k >= 4 ? 4u : (k >= 3 ? 3u : 0u));
+}
+static size_t bwd_smem(const PackedNet& n, int net) {
+  return bwd_fixed_smem(n, net) + (size_t)bwd_slots(n, net) * kSlotBytes + 1024;
 }
 
 template <int NET>
 static int launch_bwd(const TcParams& p, const PackedNet& n, uint32_t M, cudaStream_t s) {
-  const uint32_t slots = bwd_slots(n);
+  const uint32_t slots = bwd_slots(n, NET);
+  const size_t smem = bwd_smem(n, NET);
+  // sigma net: first/last-matrix weight gradients live in TMEM columns [384, 432) next to (n_mats - 2) hidden accumulators
+  if (NET == 0 && n.n_mats - 2 > 2) return SNERF_E_UNSUPPORTED;
   if (slots == 5) {
-    if (int e = set_smem(k_field_bwd<NET, 5>, bwd_smem(n))) return e;
-    k_field_bwd<NET, 5><<<grid_for(M), kBwdThreads, bwd_smem(n), s>>>(p);
+    if (int e = set_smem(k_field_bwd<NET, 5>, smem)) return e;
+    k_field_bwd<NET, 5><<<grid_for(M), bwd_threads(NET), smem, s>>>(p);
+  } else if (slots == 4) {
+    if (int e = set_smem(k_field_bwd<NET, 4>, smem)) return e;
+    k_field_bwd<NET, 4><<<grid_for(M), bwd_threads(NET), smem, s>>>(p);
   } else if (slots == 3) {
-    if (int e = set_smem(k_field_bwd<NET, 3>, bwd_smem(n))) return e;
-    k_field_bwd<NET, 3><<<grid_for(M), kBwdThreads, bwd_smem(n), s>>>(p);
+    if (int e = set_smem(k_field_bwd<NET, 3>, smem)) return e;
+    k_field_bwd<NET, 3><<<grid_for(M), bwd_threads(NET), smem, s>>>(p);
   } else {
     return SNERF_E_UNSUPPORTED;  // the activations of a tile leave no room for the weight ring
   }
@@ -1003,7 +1044,9 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
     if (int e = launch_bwd<0>(p, ps, M, s)) return e;
     launches += 2;
   }
-  // 4. table scatter-add of d loss / d encoding (its own kernel: full occupancy, warp-level merging of equal cells)
+  // 4. table scatter-add of d loss / d encoding: its own full-occupancy kernel.  Running it inside the sigma kernel
+  //    (dedicated warps, or in the compute warps' MMA waits) was measured and did not overlap: the reductions retire at
+  //    ~1 lane/clk/SM and hold up the epilogues' shared-memory traffic, so the two costs add up either way.
   if (st & kStBwdScatter) {
     if (int e = launch_hashgrid_bwd(&f->grid, xyzs, true, f->bound, w.d_enc, M, grad_table, s)) return e;
   }
