@@ -322,7 +322,9 @@ def run_gpu_arm(args):
     ts = TrainStep(model, RAYS_PER_GPU, max_steps=MAX_STEPS, use_graph=not args.no_graph, world_size=world,
                    loss_scale=1.0 / world)
     d_o, d_d, d_t = (torch.from_numpy(a).to(dev) for a in (rays_o, rays_d, target))
-    h_o, h_d, h_t = (torch.from_numpy(a).pin_memory() for a in (rays_o, rays_d, target))
+    h_o, h_d, h_t = ts.pinned_inputs()  # one pinned staging buffer: the step's inputs travel in a single H2D copy
+    for h, a in zip((h_o, h_d, h_t), (rays_o, rays_d, target)):
+        h.copy_(torch.from_numpy(a))
     ts.warmup(d_o, d_d, d_t)
 
     def barrier():

@@ -38,7 +38,7 @@ size_t snerf_field_workspace_bytes(const snerf_field_desc* f, uint32_t M, int pr
 
 size_t snerf_field_saved_bytes(const snerf_field_desc* f, uint32_t M, int precision) {
   if (check_field_desc(f) || precision != SNERF_PRECISION_BF16) return 0;
-  return field_tc_saved_bytes(M);
+  return field_tc_saved_bytes(f, M);
 }
 
 int snerf_field_forward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,

@@ -71,7 +71,7 @@ int field_fp32_backward(const snerf_field_desc* f, const float* xyzs, const floa
 
 // field_tc.cu (tcgen05 bf16 path)
 size_t field_tc_workspace_bytes(const snerf_field_desc* f, uint32_t M, int backward);
-size_t field_tc_saved_bytes(uint32_t M);
+size_t field_tc_saved_bytes(const snerf_field_desc* f, uint32_t M);
 void field_tc_set_phase_buffer(void* dev_buffer, int net);
 void field_tc_set_stage_mask(uint32_t mask);
 int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,

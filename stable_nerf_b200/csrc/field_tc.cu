@@ -806,15 +806,12 @@ struct TcWorkspace {
   float* dw_part;  // per-CTA partial weight gradients of one net at a time (max of the two nets)
 };
 
-// forward -> backward hand-off buffer: [geo: M x 16 bf16][enc: M x 32 bf16][y: M x 4 f32], each padded to 1 KiB
-static size_t saved_geo_bytes(uint32_t M) { return align_up((size_t)(M ? M : 1) * 16 * sizeof(__nv_bfloat16), 1024); }
-static size_t saved_enc_bytes(uint32_t M) { return align_up((size_t)(M ? M : 1) * 32 * sizeof(__nv_bfloat16), 1024); }
-size_t field_tc_saved_bytes(uint32_t M) { return saved_geo_bytes(M) + saved_enc_bytes(M) + (size_t)(M ? M : 1) * sizeof(float4); }
-
-static size_t carve_tc(const snerf_field_desc* f, uint32_t M, int backward, char* base, TcWorkspace* w) {
+// forward -> backward hand-off: [packed sigma weights][packed colour weights][geo: M x 16 bf16][enc: M x 32 bf16]
+// [y: M x 4 f32], each padded to 1 KiB.  The same layout sits inside the workspace for calls without a hand-off buffer.
+static size_t carve_handoff(const snerf_field_desc* f, uint32_t M, char* base, TcWorkspace* w) {
   const PackedNet ps = make_packed(sigma_shape(f)), pc = make_packed(color_shape(f));
-  // the caller's buffer only has to be 16-byte aligned: 1 KiB of slack is requested and the base rounded up here
-  size_t off = base ? (size_t)((1024u - ((uintptr_t)base & 1023u)) & 1023u) : 1024;
+  const size_t m = M ? M : 1;
+  size_t off = 0;
   auto take = [&](size_t bytes) {
     char* ptr = base ? base + off : nullptr;
     off += align_up(bytes, 1024);
@@ -824,10 +821,25 @@ static size_t carve_tc(const snerf_field_desc* f, uint32_t M, int backward, char
   TcWorkspace& o = w ? *w : tmp;
   o.wimg_sigma = (uint8_t*)take(ps.total_bytes);
   o.wimg_color = (uint8_t*)take(pc.total_bytes);
-  char* hand = take(field_tc_saved_bytes(M));  // used when the caller passes no hand-off buffer
-  o.geo = (__nv_bfloat16*)hand;
-  o.enc = (__nv_bfloat16*)(hand ? hand + saved_geo_bytes(M) : nullptr);
-  o.rgb_y = (float4*)(hand ? hand + saved_geo_bytes(M) + saved_enc_bytes(M) : nullptr);
+  o.geo = (__nv_bfloat16*)take(m * 16 * sizeof(__nv_bfloat16));
+  o.enc = (__nv_bfloat16*)take(m * 32 * sizeof(__nv_bfloat16));
+  o.rgb_y = (float4*)take(m * sizeof(float4));
+  return off;
+}
+size_t field_tc_saved_bytes(const snerf_field_desc* f, uint32_t M) { return carve_handoff(f, M, nullptr, nullptr); }
+
+static size_t carve_tc(const snerf_field_desc* f, uint32_t M, int backward, char* base, TcWorkspace* w) {
+  // the caller's buffer only has to be 16-byte aligned: 1 KiB of slack is requested and the base rounded up here
+  size_t off = base ? (size_t)((1024u - ((uintptr_t)base & 1023u)) & 1023u) : 1024;
+  auto take = [&](size_t bytes) {
+    char* ptr = base ? base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return ptr;
+  };
+  TcWorkspace tmp;
+  TcWorkspace& o = w ? *w : tmp;
+  char* hand = take(field_tc_saved_bytes(f, M));  // used when the caller passes no hand-off buffer
+  carve_handoff(f, M, hand, &o);
   o.g_geo = backward ? (float*)take((size_t)(M ? M : 1) * 16 * sizeof(float)) : nullptr;
   o.d_enc = backward ? (float*)take((size_t)(M ? M : 1) * 32 * sizeof(float)) : nullptr;
   o.dw_part = backward ? (float*)take((size_t)kMaxGrid * std::max(sigma_shape(f).n_params, color_shape(f).n_params) * sizeof(float)) : nullptr;
@@ -922,14 +934,10 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
                      bool sigma_only, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (ws_bytes < field_tc_workspace_bytes(f, M, 0)) return SNERF_E_WORKSPACE;
   if (((uintptr_t)ws & 15u) || ((uintptr_t)saved & 15u)) return SNERF_E_BADARG;
-  if (saved && saved_bytes < field_tc_saved_bytes(M)) return SNERF_E_WORKSPACE;
+  if (saved && saved_bytes < field_tc_saved_bytes(f, M)) return SNERF_E_WORKSPACE;
   TcWorkspace w;
   carve_tc(f, M, 0, (char*)ws, &w);
-  if (saved) {  // the geometry features and the encoded inputs go straight into the hand-off buffer
-    w.geo = (__nv_bfloat16*)saved;
-    w.enc = (__nv_bfloat16*)((char*)saved + saved_geo_bytes(M));
-    w.rgb_y = (float4*)((char*)saved + saved_geo_bytes(M) + saved_enc_bytes(M));
-  }
+  if (saved) carve_handoff(f, M, (char*)saved, &w);  // packed weights, geometry features, encoded inputs, colour outputs
   const PackedNet ps = make_packed(sigma_shape(f)), pc = make_packed(color_shape(f));
   const uint32_t st = g_stage_mask;
   unsigned launches = 0;
@@ -975,7 +983,7 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
                       float* grad_table, float* grad_w_sigma, float* grad_w_color, const void* saved, size_t saved_bytes,
                       void* ws, size_t ws_bytes, cudaStream_t s) {
   if (ws_bytes < field_tc_workspace_bytes(f, M, 1)) return SNERF_E_WORKSPACE;
-  if (saved && (saved_bytes < field_tc_saved_bytes(M) || ((uintptr_t)saved & 15u))) return SNERF_E_BADARG;
+  if (saved && (saved_bytes < field_tc_saved_bytes(f, M) || ((uintptr_t)saved & 15u))) return SNERF_E_BADARG;
   if (((uintptr_t)ws & 15u) || ((uintptr_t)grad_w_sigma & 15u) || ((uintptr_t)grad_w_color & 15u) ||
       ((uintptr_t)grad_table & 7u))
     return SNERF_E_BADARG;
@@ -985,7 +993,8 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   const PackedNet ps = make_packed(ss), pc = make_packed(sc);
   const uint32_t st = g_stage_mask;
   unsigned launches = 0;
-  if (st & kStBwdPack) {
+  if (saved) carve_handoff(f, M, (char*)const_cast<void*>(saved), &w);  // incl. the forward's packed weight images
+  if ((st & kStBwdPack) && !saved) {
     k_pack_weights<<<div_up(ps.total_bytes / 16, 256), 256, 0, s>>>(w_sigma, ps, w.wimg_sigma);
     k_pack_weights<<<div_up(pc.total_bytes / 16, 256), 256, 0, s>>>(w_color, pc, w.wimg_color);
     launches += 2;
@@ -993,11 +1002,7 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   // 1. the geometry features the colour net consumes and the encoded inputs of the sigma net: handed over by the
   //    forward, or regenerated by running the sigma net's forward again
   TcParams p;
-  if (saved) {
-    w.geo = (__nv_bfloat16*)const_cast<void*>(saved);
-    w.enc = (__nv_bfloat16*)((char*)const_cast<void*>(saved) + saved_geo_bytes(M));
-    w.rgb_y = (float4*)((char*)const_cast<void*>(saved) + saved_geo_bytes(M) + saved_enc_bytes(M));
-  } else {
+  if (!saved) {
     fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
     p.sigmas = w.g_geo;  // scratch: any M floats, overwritten by step 2
     p.geo = w.geo;

@@ -81,9 +81,13 @@ class TrainStep:
         self._opt_zeroes = bool(getattr(optimizer, "zero_grad_in_step", False))
         dev = next(model.parameters()).device
         C = model.channel_dim
-        self.rays_o = torch.zeros(self.n_rays, 3, device=dev)
-        self.rays_d = torch.zeros(self.n_rays, 3, device=dev)
-        self.target = torch.zeros(self.n_rays, C, device=dev)
+        # one allocation [rays_o | rays_d | target] (and a pinned host mirror of it): a step's inputs arrive in ONE H2D copy
+        n3 = self.n_rays * 3
+        self._inputs = torch.zeros(2 * n3 + self.n_rays * C, device=dev)
+        self.rays_o = self._inputs[:n3].view(self.n_rays, 3)
+        self.rays_d = self._inputs[n3:2 * n3].view(self.n_rays, 3)
+        self.target = self._inputs[2 * n3:].view(self.n_rays, C)
+        self._staging = None
         self.loss = torch.zeros((), device=dev)
         self.loss_host = torch.zeros((), pin_memory=True) if dev.type == "cuda" else torch.zeros(())
         self.use_graph = use_graph
@@ -328,9 +332,24 @@ class TrainStep:
             self.optimizer.step()
         return self.loss
 
+    def pinned_inputs(self):
+        """(rays_o, rays_d, target) views into ONE pinned host buffer laid out like the device inputs.  Filled by the
+        data loader and passed to ``step_from_host``, they travel in a single 36+4C B/ray copy instead of three."""
+        if self._staging is None:
+            self._staging = torch.zeros(self._inputs.numel(), pin_memory=self._inputs.is_cuda)
+        n3 = self.n_rays * 3
+        st = self._staging
+        return (st[:n3].view(self.n_rays, 3), st[n3:2 * n3].view(self.n_rays, 3), st[2 * n3:].view(self.n_rays, -1))
+
     def step_from_host(self, rays_o_pinned, rays_d_pinned, target_pinned):
         """End-to-end form: pinned host inputs -> device, one step, loss back to the host (synchronises)."""
-        self.step(rays_o_pinned, rays_d_pinned, target_pinned)
+        if self._staging is not None and rays_o_pinned.data_ptr() == self._staging.data_ptr() and \
+                rays_d_pinned.data_ptr() == self._staging.data_ptr() + 4 * self.n_rays * 3 and \
+                target_pinned.data_ptr() == self._staging.data_ptr() + 8 * self.n_rays * 3:
+            self._inputs.copy_(self._staging, non_blocking=True)
+            self.step()
+        else:
+            self.step(rays_o_pinned, rays_d_pinned, target_pinned)
         self.loss_host.copy_(self.loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(self.loss_host)

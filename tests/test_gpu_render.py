@@ -182,6 +182,10 @@ def test_cuda_graph_train_step_matches_eager(built_lib, cuda):
     assert rel_err(res[True][1].cpu().numpy(), res[False][1].cpu().numpy()) <= 1e-4
     h = [torch.from_numpy(a).pin_memory() for a in (ro, rd, tgt)]
     assert abs(ts.step_from_host(*h) - res[True][0]) <= 1e-6
+    hs = ts.pinned_inputs()  # single-copy staging path
+    for dst, src in zip(hs, (ro, rd, tgt)):
+        dst.copy_(torch.from_numpy(src))
+    assert abs(ts.step_from_host(*hs) - res[True][0]) <= 1e-6
 
 
 @pytest.mark.parametrize("precision,C,bg", [("fp32", 3, 1), ("bf16", 3, 1), ("fp32", 4, "tensor")])
