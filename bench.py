@@ -237,6 +237,22 @@ def render_bench(model, dev, world, rank, frames, barrier, max_over_ranks, min_n
         e1.record()
         barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
+    upd_ms = None
+    if min_n_step == 1:  # cfg3 "with density-grid update": one full sweep (2 097 152 density queries), nerf/renderer.py:236-327
+        state = (model.density_grid.clone(), model.density_bitfield.clone(), model.mean_density, model.iter_density,
+                 model.mean_count, model.local_step)
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        model.iter_density = 0
+        model.update_extra_state()
+        model.iter_density = 0
+        u0.record()
+        model.update_extra_state()
+        u1.record()
+        torch.cuda.synchronize()
+        upd_ms = u0.elapsed_time(u1)
+        model.density_grid.copy_(state[0])
+        model.density_bitfield.copy_(state[1])
+        model.mean_density, model.iter_density, model.mean_count, model.local_step = state[2:]
     tot = torch.tensor([rows, samples], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
@@ -249,7 +265,7 @@ def render_bench(model, dev, world, rank, frames, barrier, max_over_ranks, min_n
                            f"at least {min_n_step} samples per ray and iteration (images equal to 1e-6)"),
             "samples_per_s": float(tot[1]) / (ms * 1e-3), "rows_per_s_incl_padding": float(tot[0]) / (ms * 1e-3),
             "ms_per_frame": ms / frames, "frames": frames, "rays": 640000, "loop_iterations_per_frame": iters / frames,
-            "samples_per_frame": float(tot[1]) / frames, "unit": "samples/s"}
+            "samples_per_frame": float(tot[1]) / frames, "unit": "samples/s", "density_grid_update_ms": upd_ms}
 
 
 def large_batch_profile(model, dev, pk, n_rays=1 << 18):
