@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(256) k_packbits(const float* __restrict__ grid
 
 struct MarchParams {
   float bound, dt_gamma, dt_min, dt_max, rH, half_H, Hm1, Cm1;
+  float mip_bound0, mip_rbound0;  // cascade 0: min(1, bound) and its IEEE reciprocal (all there is when C == 1)
   uint32_t C, H, H3, max_steps;
 };
 
@@ -112,6 +113,9 @@ static int make_march_params(MarchParams* p, float bound, float dt_gamma, uint32
   p->bound = bound; p->dt_gamma = dt_gamma; p->dt_min = dt_min; p->dt_max = dt_max; p->rH = rH;
   p->half_H = 0.5f * (float)H; p->Hm1 = (float)(H - 1); p->Cm1 = (float)C - 1.0f;
   p->C = C; p->H = H; p->H3 = H * H * H; p->max_steps = max_steps;
+  volatile float mb0 = bound < 1.0f ? bound : 1.0f;
+  volatile float rmb0 = 1.0f / mb0;  // == __frcp_rn(mb0): IEEE division
+  p->mip_bound0 = mb0; p->mip_rbound0 = rmb0;
   return SNERF_OK;
 }
 
@@ -140,9 +144,13 @@ __device__ __forceinline__ bool march_iter(const MarchParams& p, const Ray& r, c
   z = clampf(ffma(t, r.dz, r.oz), -p.bound, p.bound);
   dt = clampf(fmul(t, p.dt_gamma), p.dt_min, p.dt_max);
   const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
-  const int level = max(level_from(mx, p.Cm1), level_from(fmul(fmul(dt, (float)p.H), 0.5f), p.Cm1));
-  const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), p.bound);
-  const float mip_rbound = __frcp_rn(mip_bound);
+  int level = 0;
+  float mip_bound = p.mip_bound0, mip_rbound = p.mip_rbound0;
+  if (p.C > 1) {  // (uniform) with a single cascade the level is 0 whatever the position
+    level = max(level_from(mx, p.Cm1), level_from(fmul(fmul(dt, (float)p.H), 0.5f), p.Cm1));
+    mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), p.bound);
+    mip_rbound = __frcp_rn(mip_bound);
+  }
   // 0.5*(x*rb+1)*H goes through double in the reference; for H a power of two the fp32 product is identical
   const int nx = (int)clampf(fmul(ffma(x, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);
   const int ny = (int)clampf(fmul(ffma(y, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);
@@ -212,9 +220,13 @@ __device__ __forceinline__ bool march_test(const MarchParams& p, const Ray& r, c
   z = clampf(ffma(t, r.dz, r.oz), -p.bound, p.bound);
   dt = clampf(fmul(t, p.dt_gamma), p.dt_min, p.dt_max);
   const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
-  const int level = max(level_from(mx, p.Cm1), level_from(fmul(fmul(dt, (float)p.H), 0.5f), p.Cm1));
-  const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), p.bound);
-  const float mip_rbound = __frcp_rn(mip_bound);
+  int level = 0;
+  float mip_bound = p.mip_bound0, mip_rbound = p.mip_rbound0;
+  if (p.C > 1) {  // (uniform) with a single cascade the level is 0 whatever the position
+    level = max(level_from(mx, p.Cm1), level_from(fmul(fmul(dt, (float)p.H), 0.5f), p.Cm1));
+    mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), p.bound);
+    mip_rbound = __frcp_rn(mip_bound);
+  }
   const int nx = (int)clampf(fmul(ffma(x, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);
   const int ny = (int)clampf(fmul(ffma(y, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);
   const int nz = (int)clampf(fmul(ffma(z, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);
