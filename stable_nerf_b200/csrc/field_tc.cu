@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_field_fwd(const TcParams p) 
 //              W_0 | W_1 .. W_{L-1} (2 chunks each) | W_L | W_{L-1} .. W_1 | W_0.
 
 constexpr uint32_t kBwdComputeThreads = 256;
-constexpr uint32_t kBwdSyncThreads = kBwdComputeThreads + 32;  // compute warps + issuer warp meet at barrier 1
+constexpr uint32_t kBwdSyncThreads = kBwdComputeThreads / 2 + 32;  // one group of compute warps + the issuer warp
 __host__ __device__ constexpr uint32_t bwd_threads(int) { return kBwdComputeThreads + 64u; }
 // sigma net: the first / last matrices' weight gradients accumulate in spare TMEM columns (the colour net's three hidden
 // accumulators leave none, it keeps them in registers)
@@ -384,14 +384,15 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
   uint8_t* ebuf = ahid + (uint32_t)L * kActBytes;
   uint8_t* sbuf = ebuf;                           // [128 x 64] tile, 16 columns used: gradient of the net's raw output
   uint8_t* ring = ebuf + kActBytes;
-  __shared__ uint64_t mbar, full[NS], empty[NS];
+  __shared__ uint64_t mbarh[2], full[NS], empty[NS];
   __shared__ uint32_t tmem_base_s;
   const uint32_t tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31u, q = warp & 3u, hc = (warp >> 2) & 1u;
   const uint32_t row = q * 32u + lane;
   const uint32_t n_tiles = div_up(p.M, kTile);
 
   if (tid == 0) {
-    mbar_init(&mbar, 1);
+    mbar_init(&mbarh[0], 1);
+    mbar_init(&mbarh[1], 1);
     for (uint32_t i = 0; i < NS; i++) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -430,6 +431,13 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
     }
   } else if (warp == kBwdComputeThreads / 32) {
     // ======================================================================================== MMA issuer
+    // The eight compute warps are two groups (hc = 0 / 1: accumulator columns and operand-tile chunk 64hc .. 64hc+63).
+    // Each group hands over on its own named barrier (R0 / R1: "my chunk is written, my accumulator half is read") and
+    // waits on its own mbarrier (D0 / D1: "your accumulator half is ready").  In the hidden layers the MMAs of a layer
+    // are split so that half 0's epilogue runs under half 1's MMAs and the next layer starts on chunk 0 while chunk 1
+    // is still in its epilogue:
+    //   forward  : R0 -> [h0, K 0-3]   R1 -> [h0, K 4-7] => D0   [h1, K 0-7] => D1
+    //   backward : R0 -> [dgrad h0, K 0-3]   R1 -> [dgrad h0, K 4-7] => D0   [dgrad h1] => D1   [wgrad]
     uint32_t slot = 0, par = 0;
     auto next_slot = [&]() -> uint32_t {  // wait for the next chunk of the static fill order; returns its address
       mbar_wait(&full[slot], par);
@@ -439,15 +447,16 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
       return addr;
     };
     auto slot_empty_bar = [&](uint32_t addr) { return &empty[(addr - smem_u32(ring)) / kSlotBytes]; };
-    auto meet = [&]() {  // the compute warps have written the operands / read the accumulator
-      bar_sync(1u, kBwdSyncThreads);
+    auto meet = [&](uint32_t group) {  // group's warps have written their operand chunk / read their accumulator half
+      bar_sync(1u + group, kBwdSyncThreads);
       tc_fence_after();
     };
     const uint32_t s_a0 = smem_u32(a0), s_e = smem_u32(ebuf);
     uint32_t iter = 0;
     for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, iter++) {
-      // ---- forward recompute
-      meet();
+      // ---- forward recompute, first matrix (K = 32)
+      meet(0);
+      meet(1);
       {
         const uint32_t sw = next_slot();
         if (elect_one()) {
@@ -455,30 +464,44 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
 #pragma unroll
           for (uint32_t s = 0; s < 2; s++) mma_ss(tmem, desc_kmajor(s_a0, kTile, s), desc_kmajor(sw, kTile, s), idesc, s > 0);
           mma_commit(slot_empty_bar(sw));
-          mma_commit(&mbar);
+          mma_commit(&mbarh[0]);
+          mma_commit(&mbarh[1]);
         }
         __syncwarp();
       }
+      // ---- forward recompute, hidden matrices
       for (int i = 1; i < L; i++) {
-        meet();
         const uint32_t sa = smem_u32(a_hid(i));
-        constexpr uint32_t idesc = make_idesc(kTile, kTile, false, false);
+        constexpr uint32_t idesc = make_idesc(kTile, 64u, false, false);
+        meet(0);  // chunk 0 of a_i written, accumulator columns [0,64) read
+        const uint32_t sw0 = next_slot();  // image chunk 0 = K-steps 0-3, rows = the 128 outputs
+        if (elect_one()) {
 #pragma unroll
-        for (uint32_t c = 0; c < 2; c++) {  // K-steps 0-3 read chunk 0 (first slot), 4-7 chunk 1 (second slot)
-          const uint32_t sw = next_slot();
-          if (elect_one()) {
-#pragma unroll
-            for (uint32_t s = 0; s < 4; s++)
-              mma_ss(tmem, desc_kmajor(sa, kTile, c * 4u + s), desc_kmajor(sw, kTile, s), idesc, (c | s) > 0);
-            mma_commit(slot_empty_bar(sw));
-            if (c == 1) mma_commit(&mbar);
-          }
-          __syncwarp();
+          for (uint32_t s = 0; s < 4; s++) mma_ss(tmem, desc_kmajor(sa, kTile, s), desc_kmajor(sw0, kTile, s), idesc, s > 0);
         }
+        __syncwarp();
+        meet(1);  // chunk 1 written, columns [64,128) read
+        const uint32_t sw1 = next_slot();
+        if (elect_one()) {
+#pragma unroll
+          for (uint32_t s = 0; s < 4; s++) mma_ss(tmem, desc_kmajor(sa, kTile, 4u + s), desc_kmajor(sw1, kTile, s), idesc, true);
+          mma_commit(&mbarh[0]);
+#pragma unroll
+          for (uint32_t s = 0; s < 4; s++)  // outputs 64-127 = image rows 64-127 (8 atoms of 1 KiB further)
+            mma_ss(tmem + 64u, desc_kmajor(sa, kTile, s), desc_kmajor(sw0 + 8192u, kTile, s), idesc, s > 0);
+#pragma unroll
+          for (uint32_t s = 0; s < 4; s++)
+            mma_ss(tmem + 64u, desc_kmajor(sa, kTile, 4u + s), desc_kmajor(sw1 + 8192u, kTile, s), idesc, true);
+          mma_commit(slot_empty_bar(sw0));
+          mma_commit(slot_empty_bar(sw1));
+          mma_commit(&mbarh[1]);
+        }
+        __syncwarp();
       }
       // ---- last matrix W_L [16 x 128].  The output layer is not recomputed: the gradient of the raw output (S) was
       // built at the start of the tile from the forward's saved outputs.
-      meet();  // a_L written
+      meet(0);
+      meet(1);  // a_L written
       const uint32_t s_aL = smem_u32(a_hid(L));
       if (NET == 0) {
         // wgrad accumulates across tiles in its own TMEM columns, so the dgrad follows it without a round trip
@@ -490,47 +513,54 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
             mma_ss(tmem + kColLast, desc_mnmajor(s_aL, kTile, s), desc_mnmajor(s_e, kTile, s), idesc, iter > 0 || s > 0);
           mma_ss(tmem, desc_kmajor(s_e, kTile, 0), desc_mnmajor(sw_last, 16u, 0), make_idesc(kTile, kTile, false, true), false);
           mma_commit(slot_empty_bar(sw_last));
-          mma_commit(&mbar);
+          mma_commit(&mbarh[0]);
+          mma_commit(&mbarh[1]);
         }
         __syncwarp();
       } else {
-        if (elect_one()) {  // wgrad (transposed): D[k, n] = sum_j a_L[j,k] g_out[j,n]
+        if (elect_one()) {  // wgrad (transposed): D[k, n] = sum_j a_L[j,k] g_out[j,n]; read by group 0 only
           constexpr uint32_t idesc = make_idesc(kTile, 16u, true, true);
 #pragma unroll
           for (uint32_t s = 0; s < 8; s++) mma_ss(tmem, desc_mnmajor(s_aL, kTile, s), desc_mnmajor(s_e, kTile, s), idesc, s > 0);
-          mma_commit(&mbar);
+          mma_commit(&mbarh[0]);
         }
         __syncwarp();
-        meet();  // accumulator read
+        meet(0);  // accumulator read
         const uint32_t sw_last = next_slot();
         if (elect_one()) {  // dgrad: D[m, k] = sum_n g_out[m,n] W_L[n,k]   (B = the W_L image read MN-major, rows = n)
           mma_ss(tmem, desc_kmajor(s_e, kTile, 0), desc_mnmajor(sw_last, 16u, 0), make_idesc(kTile, kTile, false, true), false);
           mma_commit(slot_empty_bar(sw_last));
-          mma_commit(&mbar);
+          mma_commit(&mbarh[0]);
+          mma_commit(&mbarh[1]);
         }
         __syncwarp();
       }
       // ---- hidden matrices W_{L-1} .. W_1 [128 x 128]
       uint32_t sg = s_e, sgn = s_aL;
       for (int i = L - 1; i >= 1; i--) {
-        meet();  // gradient tile written
         const uint32_t sa = smem_u32(a_hid(i));
         constexpr uint32_t id_d = make_idesc(kTile, 64u, false, true), id_w = make_idesc(kTile, kTile, true, true);
-        // dgrad: D[m,k] = sum_n g[m,n] W_i[n,k]; chunk c of the image holds columns k in [64c, 64c+64)
-#pragma unroll
-        for (uint32_t c = 0; c < 2; c++) {
-          const uint32_t sw = next_slot();
-          if (elect_one()) {
-#pragma unroll
-            for (uint32_t s = 0; s < 8; s++)
-              mma_ss(tmem + c * 64u, desc_kmajor(sg, kTile, s), desc_mnmajor(sw, kTile, s), id_d, s > 0);
-            mma_commit(slot_empty_bar(sw));
-            if (c == 1) mma_commit(&mbar);
-          }
-          __syncwarp();
-        }
+        // dgrad: D[m,k] = sum_n g[m,n] W_i[n,k]; image chunk c holds the columns k in [64c, 64c+64) = half c;
+        // K-steps 0-3 / 4-7 read chunk 0 / 1 of the gradient tile
+        meet(0);  // gradient chunk 0 written, accumulator columns [0,64) read
+        const uint32_t sw0 = next_slot();
         if (elect_one()) {
-          // wgrad: dW_i[n,k] += sum_j g[j,n] a_i[j,k]   (accumulates across tiles in TMEM; runs under the epilogue)
+#pragma unroll
+          for (uint32_t s = 0; s < 4; s++) mma_ss(tmem, desc_kmajor(sg, kTile, s), desc_mnmajor(sw0, kTile, s), id_d, s > 0);
+        }
+        __syncwarp();
+        meet(1);  // gradient chunk 1 written, columns [64,128) read
+        const uint32_t sw1 = next_slot();
+        if (elect_one()) {
+#pragma unroll
+          for (uint32_t s = 4; s < 8; s++) mma_ss(tmem, desc_kmajor(sg, kTile, s), desc_mnmajor(sw0, kTile, s), id_d, true);
+          mma_commit(slot_empty_bar(sw0));
+          mma_commit(&mbarh[0]);
+#pragma unroll
+          for (uint32_t s = 0; s < 8; s++) mma_ss(tmem + 64u, desc_kmajor(sg, kTile, s), desc_mnmajor(sw1, kTile, s), id_d, s > 0);
+          mma_commit(slot_empty_bar(sw1));
+          mma_commit(&mbarh[1]);
+          // wgrad: dW_i[n,k] += sum_j g[j,n] a_i[j,k]   (accumulates across tiles in TMEM; runs under the epilogues)
           const uint32_t dw = tmem + 128u * (uint32_t)i;
 #pragma unroll
           for (uint32_t s = 0; s < 8; s++)
@@ -540,7 +570,8 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
         const uint32_t tmp = sg; sg = sgn; sgn = tmp;
       }
       // ---- first matrix W_0 [128 x 32]: wgrad into columns [0,32), dgrad into [32,64), one phase
-      meet();
+      meet(0);
+      meet(1);
       {
         const uint32_t sw = next_slot();
         if (elect_one()) {
@@ -554,7 +585,8 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
 #pragma unroll
           for (uint32_t s = 0; s < 8; s++) mma_ss(tmem + 32u, desc_kmajor(sg, kTile, s), desc_mnmajor(sw, kTile, s), id_d, s > 0);
           mma_commit(slot_empty_bar(sw));
-          mma_commit(&mbar);
+          mma_commit(&mbarh[0]);
+          mma_commit(&mbarh[1]);
         }
         __syncwarp();
       }
@@ -563,17 +595,17 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
     // ======================================================================================== compute warps
     const uint32_t tlane = tmem + ((q * 32u) << 16);
     uint32_t mph = 0;
-    auto hand_over = [&]() {  // generic-proxy writes of the compute warps -> visible to the tensor pipe; issuer may go
+    auto hand_over = [&]() {  // this group's generic-proxy writes -> visible to the tensor pipe; the issuer may go on
       tc_fence_before();
       fence_proxy_async();
-      bar_sync(1u, kBwdSyncThreads);
+      bar_sync(1u + hc, kBwdSyncThreads);
     };
-    auto hand_over_tmem = [&]() {  // accumulator has been read; issuer may overwrite it
+    auto hand_over_tmem = [&]() {  // this group's accumulator half has been read; the issuer may overwrite it
       tc_fence_before();
-      bar_sync(1u, kBwdSyncThreads);
+      bar_sync(1u + hc, kBwdSyncThreads);
     };
-    auto wait_mma = [&]() {
-      mbar_wait(&mbar, mph);
+    auto wait_mma = [&]() {  // this group's accumulator half is ready
+      mbar_wait(&mbarh[hc], mph);
       mph ^= 1u;
       tc_fence_after();
     };
@@ -670,15 +702,13 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
       }
 
       // ---------------- last matrix W_L [16 x 128]
-      if (NET != 0) {
+      if (NET != 0 && hc == 0) {  // (group 1 has no part in this phase)
         wait_mma();  // wgrad
         mark(7);
-        if (hc == 0) {
-          float v[16];
-          tmem_ld16(tlane, v);
+        float v[16];
+        tmem_ld16(tlane, v);
 #pragma unroll
-          for (int k = 0; k < 16; k++) acc_last[k] += v[k];
-        }
+        for (int k = 0; k < 16; k++) acc_last[k] += v[k];
         hand_over_tmem();
       }
       wait_mma();  // dgrad
