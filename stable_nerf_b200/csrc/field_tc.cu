@@ -290,14 +290,55 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_field_fwd(const TcParams p) 
     bar_sync(1u + wg, 128u);
   };
 
-  for (uint32_t t = blockIdx.x + gridDim.x * wg; t < n_tiles; t += gridDim.x * kFwdGroups) {
+  // The row's input, loaded one tile ahead (raw: nothing below depends on a loaded value until the next tile starts,
+  // so the loads stay in flight under the running tile).  NET 0 with precomputed features: the 32 bf16 columns;
+  // NET 1: the direction (SH-4 is evaluated when the tile starts) and the 15 geometry features.
+  const bool prefetch = NET == 1 || p.enc_ready;
+  uint4 pre[4];
+  float pd[3];
+  auto fetch_raw = [&](uint32_t t) {
+    const uint32_t mm = t * kTile + row;
+#pragma unroll
+    for (int g = 0; g < 4; g++) pre[g] = make_uint4(0u, 0u, 0u, 0u);
+    pd[0] = pd[1] = pd[2] = 0.f;
+    if (mm < p.M) {
+      if (NET == 0) {
+        const uint4* ep = reinterpret_cast<const uint4*>(p.enc + (size_t)mm * 32);
+#pragma unroll
+        for (int g = 0; g < 4; g++) pre[g] = __ldg(ep + g);
+      } else {
+        const uint4* gp = reinterpret_cast<const uint4*>(p.geo + (size_t)mm * 16);
+        pre[2] = __ldg(gp);
+        pre[3] = __ldg(gp + 1);
+#pragma unroll
+        for (int k = 0; k < 3; k++) pd[k] = __ldg(p.dirs + (size_t)mm * 3 + k);
+      }
+    }
+  };
+  const uint32_t t_first = blockIdx.x + gridDim.x * wg, t_step = gridDim.x * kFwdGroups;
+  if (prefetch && t_first < n_tiles) fetch_raw(t_first);
+
+  for (uint32_t t = t_first; t < n_tiles; t += t_step) {
     const uint32_t m = t * kTile + row;
-    if (NET == 0 && p.enc_ready) load_input<NET, 0, 4, true>(p, m, row, act);
-    else load_input<NET, 0, 4, false>(p, m, row, act);
+    if (prefetch) {
+      if (NET == 1) {
+        if (m < p.M) {
+          float o[16];
+          sh4_eval(fmul(fadd(pd[0], 1.0f), 0.5f), fmul(fadd(pd[1], 1.0f), 0.5f), fmul(fadd(pd[2], 1.0f), 0.5f), o);
+          pre[0] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+          pre[1] = make_uint4(pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]), pack_bf16(o[12], o[13]), pack_bf16(o[14], o[15]));
+          pre[3].w &= 0x0000ffffu;  // column 31 is the zero pad (the slot holds sigma_raw in the geo buffer)
+        }
+      }
+      store_input<0, 4>(pre, row, act);
+    } else {
+      load_input<NET, 0, 4, false>(p, m, row, act);
+    }
     worker_sync();
+    if (prefetch && t + t_step < n_tiles) fetch_raw(t + t_step);
     for (int i = 0; i <= L; i++) {
       if ((warp & 3u) == 0) {  // the worker's first warp issues (converged warp, elected lane, uniform operands)
-        if (t == blockIdx.x + gridDim.x * wg) mbar_wait(&wbar, 0);  // weights resident (first tile of the worker)
+        if (t == t_first) mbar_wait(&wbar, 0);  // weights resident (first tile of the worker)
         tc_fence_after();
         const uint8_t* w = wsm + p.net.img_off[i];
         if (elect_one()) {
