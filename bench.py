@@ -423,7 +423,7 @@ def run_gpu_arm(args):
     if not args.no_render:
         out["render"] = render_bench(model, dev, world, rank, 3, barrier, max_over_ranks)
         out["render_min_n_step_4"] = render_bench(model, dev, world, rank, 3, barrier, max_over_ranks, min_n_step=4)
-    if rank == 0 and not args.no_stages:
+    if rank == 0 and world == 1 and not args.no_stages:
         pk = peaks()
         local_step = model.local_step
         st, ns, M = ts.profile_stages() if ts.fused else stage_times(model, ts)

@@ -84,6 +84,9 @@ SIGNATURES = {
                                      _P, c_size_t, _S]),
     "snerf_get_rays": (c_int, [_P, _F, _F, _F, _F, _U, _P, _U, _U, c_int, _P, _P, _S]),
     "snerf_adam_step": (c_int, [_P, _P, _P, _P, _U, _F, _F, _F, _F, _F, c_int, _U, c_int, _S]),
+    "snerf_field_backward_ex": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_size_t,
+                                        _P, c_size_t, _P, _S]),
+    "snerf_hashgrid_backward_levels": (c_int, [POINTER(GridDesc), _P, _F, _P, _U, _P, _U, _U, _S]),
     "snerf_tc_selftest": (c_int, [_P, _P, _P, _U, _U, c_int, c_int, _S]),
     "snerf_debug_set_march_warp_max_rays": (None, [_U]),
     "snerf_debug_set_field_stage_mask": (None, [_U]),

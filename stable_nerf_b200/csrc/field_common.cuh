@@ -57,7 +57,8 @@ int launch_hashgrid_fwd_bf16(const snerf_grid_desc* g, const float* x, float bou
                              void* enc_bf16, cudaStream_t s);
 uint32_t hashgrid_dedupe_max_res();
 int launch_hashgrid_bwd(const snerf_grid_desc* g, const float* x, bool normalize, float bound, const float* grad_enc,
-                        uint32_t M, float* grad_table, cudaStream_t s);
+                        uint32_t M, float* grad_table, cudaStream_t s, uint32_t level_begin = 0,
+                        uint32_t level_end = SNERF_MAX_LEVELS);
 
 // field_fp32.cu
 size_t field_fp32_workspace_bytes(const snerf_field_desc* f, uint32_t M, int backward);
@@ -80,6 +81,6 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
 int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                       const float* w_sigma, const float* w_color, const float* grad_sigmas, const float* grad_rgbs,
                       float* grad_table, float* grad_w_sigma, float* grad_w_color, const void* saved, size_t saved_bytes,
-                      void* ws, size_t ws_bytes, cudaStream_t s);
+                      void* ws, size_t ws_bytes, cudaStream_t s, float* d_enc_out = nullptr);
 
 }  // namespace snerf

@@ -89,7 +89,8 @@ template <bool kNormalize>
 __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g, const float* __restrict__ x,
                                                               float bound, const float* __restrict__ grad_enc,
                                                               uint32_t M, float2* __restrict__ grad_table,
-                                                              uint32_t dedupe_max_res) {
+                                                              uint32_t dedupe_max_res, uint32_t level_begin,
+                                                              uint32_t level_end) {
   __shared__ float xs[kEncTile * 3];
   __shared__ float2 tile[kEncTile * 16];
   const uint32_t m0 = blockIdx.x * kEncTile;
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g,
   for (uint32_t i = threadIdx.x; i < ns * L; i += kEncThreads) tile[tile_slot(i / L, i % L)] = __ldg(gin + i);
   __syncthreads();
   // kEncTile is a multiple of 32: a warp's 32 items share the level, so everything below is warp-uniform control flow
-  for (uint32_t item = threadIdx.x; item < kEncTile * L; item += kEncThreads) {
+  for (uint32_t item = level_begin * kEncTile + threadIdx.x; item < kEncTile * level_end; item += kEncThreads) {
     const uint32_t s = item % kEncTile, l = item / kEncTile;
     float2 gv = make_float2(0.f, 0.f);
     if (s < ns) gv = tile[tile_slot(s, l)];
@@ -165,14 +166,16 @@ int launch_hashgrid_fwd_bf16(const snerf_grid_desc* g, const float* x, float bou
   return finish_launch();
 }
 int launch_hashgrid_bwd(const snerf_grid_desc* g, const float* x, bool normalize, float bound, const float* grad_enc,
-                        uint32_t M, float* grad_table, cudaStream_t s) {
+                        uint32_t M, float* grad_table, cudaStream_t s, uint32_t level_begin, uint32_t level_end) {
   const uint32_t blocks = div_up(M, kEncTile);
+  level_end = min(level_end, g->n_levels);
+  if (level_begin >= level_end) return SNERF_OK;
   if (normalize)
     k_hashgrid_bwd<true><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, grad_enc, M, reinterpret_cast<float2*>(grad_table),
-                                                         g_dedupe_max_res);
+                                                         g_dedupe_max_res, level_begin, level_end);
   else
     k_hashgrid_bwd<false><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, grad_enc, M, reinterpret_cast<float2*>(grad_table),
-                                                          g_dedupe_max_res);
+                                                          g_dedupe_max_res, level_begin, level_end);
   return finish_launch();
 }
 
@@ -197,7 +200,16 @@ int snerf_hashgrid_backward(const snerf_grid_desc* g, const float* x01, const fl
   if (int e = check_grid_desc(g)) return e;
   if (M == 0) return SNERF_OK;
   if (!x01 || !grad_enc || !grad_table) return SNERF_E_BADARG;
-  return launch_hashgrid_bwd(g, x01, false, 1.0f, grad_enc, M, grad_table, (cudaStream_t)stream);
+  return launch_hashgrid_bwd(g, x01, false, 1.0f, grad_enc, M, grad_table, (cudaStream_t)stream, 0, SNERF_MAX_LEVELS);
+}
+
+int snerf_hashgrid_backward_levels(const snerf_grid_desc* g, const float* xyzs, float bound, const float* grad_enc,
+                                   uint32_t M, float* grad_table, uint32_t level_begin, uint32_t level_end,
+                                   snerf_stream_t stream) {
+  if (int e = check_grid_desc(g)) return e;
+  if (M == 0) return SNERF_OK;
+  if (!xyzs || !grad_enc || !grad_table || !(bound > 0.f)) return SNERF_E_BADARG;
+  return launch_hashgrid_bwd(g, xyzs, true, bound, grad_enc, M, grad_table, (cudaStream_t)stream, level_begin, level_end);
 }
 
 int snerf_sh4_forward(const float* d01, uint32_t M, float* sh, snerf_stream_t stream) {

@@ -1052,8 +1052,9 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
 int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                       const float* w_sigma, const float* w_color, const float* grad_sigmas, const float* grad_rgbs,
                       float* grad_table, float* grad_w_sigma, float* grad_w_color, const void* saved, size_t saved_bytes,
-                      void* ws, size_t ws_bytes, cudaStream_t s) {
+                      void* ws, size_t ws_bytes, cudaStream_t s, float* d_enc_out) {
   if (ws_bytes < field_tc_workspace_bytes(f, M, 1)) return SNERF_E_WORKSPACE;
+  if ((uintptr_t)d_enc_out & 15u) return SNERF_E_BADARG;
   if (saved && (saved_bytes < field_tc_saved_bytes(f, M) || ((uintptr_t)saved & 15u))) return SNERF_E_BADARG;
   if (((uintptr_t)ws & 15u) || ((uintptr_t)grad_w_sigma & 15u) || ((uintptr_t)grad_w_color & 15u) ||
       ((uintptr_t)grad_table & 7u))
@@ -1114,7 +1115,7 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   p.grad_w = grad_w_sigma;
   p.dw_part = w.dw_part;
   p.n_params = ss.n_params;
-  p.d_enc = w.d_enc;
+  p.d_enc = d_enc_out ? d_enc_out : w.d_enc;  // caller-owned: it scatters the levels itself (snerf_hashgrid_backward_levels)
   p.dbg = g_phase_net == 0 ? g_phase_dbg : nullptr;
   if (st & kStBwdSigma) {
     if (int e = launch_bwd<0>(p, ps, M, s)) return e;
@@ -1123,7 +1124,7 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   // 4. table scatter-add of d loss / d encoding: its own full-occupancy kernel.  Running it inside the sigma kernel
   //    (dedicated warps, or in the compute warps' MMA waits) was measured and did not overlap: the reductions retire at
   //    ~1 lane/clk/SM and hold up the epilogues' shared-memory traffic, so the two costs add up either way.
-  if (st & kStBwdScatter) {
+  if ((st & kStBwdScatter) && !d_enc_out) {
     if (int e = launch_hashgrid_bwd(&f->grid, xyzs, true, f->bound, w.d_enc, M, grad_table, s)) return e;
   }
   return finish_launch(launches);

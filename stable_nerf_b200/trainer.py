@@ -68,7 +68,8 @@ class TrainStep:
     """
 
     def __init__(self, model, n_rays, max_steps=1024, bg_color=1, T_thresh=1e-4, use_graph=True, world_size=1,
-                 loss_scale=1.0, fused=True, perturb=False, dt_gamma=0, optimizer=None):
+                 loss_scale=1.0, fused=True, perturb=False, dt_gamma=0, optimizer=None, overlap_allreduce=True,
+                 scatter_groups=4):
         self.model, self.n_rays, self.max_steps = model, int(n_rays), int(max_steps)
         self.bg_color, self.T_thresh, self.world_size = bg_color, T_thresh, world_size
         self.loss_scale = loss_scale
@@ -79,6 +80,10 @@ class TrainStep:
         # one that zeroes the gradients inside its step spares the step's own 49 MB memset
         self.optimizer = optimizer
         self._opt_zeroes = bool(getattr(optimizer, "zero_grad_in_step", False))
+        # several ranks: the table scatter-add runs per group of levels OUTSIDE the graph, and each group's slice of the
+        # gradient starts its all-reduce while the next group is still being scattered (trainer._scatter_and_reduce)
+        self.overlap_allreduce = bool(overlap_allreduce) and world_size > 1
+        self.scatter_groups = int(scatter_groups)
         dev = next(model.parameters()).device
         C = model.channel_dim
         # one allocation [rays_o | rays_d | target] (and a pinned host mirror of it): a step's inputs arrive in ONE H2D copy
@@ -131,6 +136,8 @@ class TrainStep:
         b["field_ws"] = torch.empty(max(b["field_ws_bytes"], 256), dtype=torch.uint8, device=dev)
         b["saved_bytes"] = lib.snerf_field_saved_bytes(m.fdesc, M, prec)
         b["saved"] = torch.empty(b["saved_bytes"], dtype=torch.uint8, device=dev) if b["saved_bytes"] else None
+        if self.overlap_allreduce and prec == _lib.PRECISION_BF16:
+            b["d_enc"] = e(M, m.fdesc.grid.n_levels * m.fdesc.grid.n_features)
         bg = self.bg_color
         b["bg"] = bg.to(**f32).contiguous().view(-1) if torch.is_tensor(bg) else None
         b["bg_scalar"] = 1.0 if bg is None else (0.0 if torch.is_tensor(bg) else float(bg))
@@ -197,10 +204,10 @@ class TrainStep:
         if m.density_scale != 1:
             b["g_sig"].mul_(m.density_scale)
         mark("composite_bwd")
-        chk(lib.snerf_field_backward(m.fdesc, P(b["xyzs"]), P(b["dirs"]), M, P(spd[nm:]), P(spd[:nm]), P(cp.detach()),
-                                     P(b["g_sig"]), P(b["g_rgb"]), prec, P(sp.grad[nm:]), P(sp.grad[:nm]), P(cp.grad),
-                                     P(b["saved"]), b["saved_bytes"], P(b["field_ws"]), b["field_ws_bytes"], S),
-            "field backward")
+        chk(lib.snerf_field_backward_ex(m.fdesc, P(b["xyzs"]), P(b["dirs"]), M, P(spd[nm:]), P(spd[:nm]), P(cp.detach()),
+                                        P(b["g_sig"]), P(b["g_rgb"]), prec, P(sp.grad[nm:]), P(sp.grad[:nm]), P(cp.grad),
+                                        P(b["saved"]), b["saved_bytes"], P(b["field_ws"]), b["field_ws_bytes"],
+                                        P(b.get("d_enc")), S), "field backward")
         mark("field_bwd")
         self.outputs = {"image": b["pred"], "depth": b["depth_norm"], "weights_sum": b["ws"]}
 
@@ -326,11 +333,37 @@ class TrainStep:
             self.graph.replay()
         else:
             self._body()
-        if self.world_size > 1 and not (self.graph is not None and getattr(self, "allreduce_in_graph", False)):
-            allreduce_gradients(self.params, self.world_size)
+        if self.world_size > 1:
+            if self._bufs is not None and self._bufs.get("d_enc") is not None:
+                self._scatter_and_reduce()
+            else:
+                allreduce_gradients(self.params, self.world_size)
         if self.optimizer is not None:
             self.optimizer.step()
         return self.loss
+
+    def _scatter_and_reduce(self):
+        """Table scatter-add in groups of levels, each group's (contiguous) slice of the gradient all-reduced while the
+        next group is scattered; the MLP gradients (complete when the graph ends) go first.  dist.all_reduce(async_op)
+        runs on NCCL's own stream after everything queued so far on the current stream, i.e. after its group's launch."""
+        m, b = self.model, self._bufs
+        lib = _lib.load()
+        P, S, chk = _lib.ptr, _lib.stream(), _lib.check
+        g = m.fdesc.grid
+        nm, F = m.sigma_net.n_mlp, g.n_features
+        grad = m.sigma_net.params.grad
+        handles = [dist.all_reduce(m.color_net.params.grad, async_op=True), dist.all_reduce(grad[:nm], async_op=True)]
+        L = g.n_levels
+        per = max(1, -(-L // max(1, self.scatter_groups)))
+        for lb in range(0, L, per):
+            le = min(L, lb + per)
+            chk(lib.snerf_hashgrid_backward_levels(g, P(b["xyzs"]), float(m.bound), P(b["d_enc"]), b["M"], P(grad[nm:]),
+                                                   lb, le, S), "scatter levels")
+            lo = nm + g.offset[lb] * F
+            hi = nm + (g.offset[le] * F if le < L else g.n_entries * F)
+            handles.append(dist.all_reduce(grad[lo:hi], async_op=True))
+        for h in handles:
+            h.wait()
 
     def pinned_inputs(self):
         """(rays_o, rays_d, target) views into ONE pinned host buffer laid out like the device inputs.  Filled by the

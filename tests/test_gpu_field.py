@@ -211,3 +211,39 @@ def test_network_module_autograd(setup, built_lib, cuda):
     names = [n for n, _ in model.named_parameters()]
     assert names == ["sigma_net.params", "encoder_dir.params", "color_net.params"]
     assert len(model.get_params(1e-3)) == 3
+
+
+def test_backward_ex_with_level_grouped_scatter(setup, built_lib, cuda):
+    """snerf_field_backward_ex (d_enc handed to the caller) + snerf_hashgrid_backward_levels in groups == the plain
+    backward: what the ray-sharded train step uses to overlap the table's all-reduce with its scatter-add."""
+    from stable_nerf_b200._lib import check, ptr, stream
+    lib = built_lib
+    C, M = 3, 3000
+    f, of, ws, table, wc = setup[C]
+    x, dirs = sample_points(M, seed=99)
+    rng = np.random.default_rng(5)
+    g_sig = rng.standard_normal(M).astype(np.float32)
+    g_rgb = rng.standard_normal((M, C)).astype(np.float32)
+    _, _, (gt, gws, gwc) = run_cuda_field(f, x, dirs, ws, table, wc, 1, g_sig, g_rgb, cuda, use_saved=True)
+    t = {k: dev_t(v, cuda) for k, v in dict(x=x, d=dirs, ws=ws, tab=table, wc=wc, gs=g_sig, gr=g_rgb).items()}
+    sig = torch.empty(M, device=cuda)
+    rgb = torch.empty(M, C, device=cuda)
+    nb = max(lib.snerf_field_workspace_bytes(f, M, 1, 0), lib.snerf_field_workspace_bytes(f, M, 1, 1))
+    wsb = torch.empty(nb, dtype=torch.uint8, device=cuda)
+    ns = lib.snerf_field_saved_bytes(f, M, 1)
+    saved = torch.empty(ns, dtype=torch.uint8, device=cuda)
+    check(lib.snerf_field_forward(f, ptr(t["x"]), ptr(t["d"]), M, ptr(t["tab"]), ptr(t["ws"]), ptr(t["wc"]), 1, ptr(sig),
+                                  ptr(rgb), ptr(saved), ns, ptr(wsb), nb, stream()), "fwd")
+    gt2, gws2, gwc2 = torch.zeros_like(t["tab"]), torch.zeros_like(t["ws"]), torch.zeros_like(t["wc"])
+    d_enc = torch.empty(M, 32, device=cuda)
+    check(lib.snerf_field_backward_ex(f, ptr(t["x"]), ptr(t["d"]), M, ptr(t["tab"]), ptr(t["ws"]), ptr(t["wc"]), ptr(t["gs"]),
+                                      ptr(t["gr"]), 1, ptr(gt2), ptr(gws2), ptr(gwc2), ptr(saved), ns, ptr(wsb), nb,
+                                      ptr(d_enc), stream()), "bwd ex")
+    torch.cuda.synchronize()
+    assert float(gt2.abs().max()) == 0.0  # the table is the caller's job now
+    for lb, le in ((0, 5), (5, 6), (6, 16)):
+        check(lib.snerf_hashgrid_backward_levels(f.grid, ptr(t["x"]), f.bound, ptr(d_enc), M, ptr(gt2), lb, le, stream()),
+              "levels")
+    torch.cuda.synchronize()
+    assert rel_err(gt2.cpu().numpy(), gt) <= 1e-5 and rel_err(gws2.cpu().numpy(), gws) <= 1e-5
+    assert rel_err(gwc2.cpu().numpy(), gwc) <= 1e-5
