@@ -219,8 +219,9 @@ def render_bench(model, dev, world, rank, frames, barrier, max_over_ranks, min_n
     from stable_nerf_b200 import synthetic as syn
     from stable_nerf_b200.trainer import shard_range
     ro, rd = syn.full_frame()
-    lo, hi = shard_range(ro.shape[0], rank, world)
-    ro, rd = torch.from_numpy(ro[lo:hi]).to(dev)[None], torch.from_numpy(rd[lo:hi]).to(dev)[None]
+    # pixels interleaved over the ranks (rank r renders pixels r, r+W, ...): every shard is a uniform subsample of the
+    # image, so the ranks carry equal work (contiguous row blocks leave the object to the middle ranks)
+    ro, rd = (torch.from_numpy(np.ascontiguousarray(a[rank::world])).to(dev)[None] for a in (ro, rd))
     was_training = model.training
     model.eval()
     model.min_n_step = min_n_step
@@ -260,7 +261,7 @@ def render_bench(model, dev, world, rank, frames, barrier, max_over_ranks, min_n
     model.train(was_training)
     model.min_n_step = 1
     return {"workload": "cfg3: 800x800 full-frame inference render, eval loop with on-device compaction, T_thresh 1e-4, "
-                        f"max_steps {MAX_STEPS}, pixel rows sharded over {world} GPU(s), "
+                        f"max_steps {MAX_STEPS}, pixels interleaved over {world} GPU(s), "
                         + ("the reference's loop schedule (n_step from 1)" if min_n_step == 1 else
                            f"at least {min_n_step} samples per ray and iteration (images equal to 1e-6)"),
             "samples_per_s": float(tot[1]) / (ms * 1e-3), "rows_per_s_incl_padding": float(tot[0]) / (ms * 1e-3),
