@@ -239,6 +239,34 @@ __device__ __forceinline__ void epi_chunk(uint32_t taddr, uint8_t* dst, const ui
   }
 }
 
+// The ReLU mask of one 64-column chunk of one row (0xffff per bf16 half where the stored post-ReLU activation is > 0),
+// fetched BEFORE the wait for the dgrad accumulator: the activations are already in shared memory, so the 8 LDS.128 and
+// the 32 HSET2 run under the MMAs instead of after them.
+__device__ __forceinline__ void mask_prefetch(const uint8_t* mask_src, uint32_t row, uint32_t chunk, uint32_t (&mk)[32]) {
+  const uint32_t base = chunk * kTile * 128u + row_off(row), r7 = row & 7u;
+#pragma unroll
+  for (uint32_t j = 0; j < 8; j++) {
+    const uint4 q = *reinterpret_cast<const uint4*>(mask_src + base + ((j ^ r7) << 4));
+    mk[4 * j] = bf16x2_gt0(q.x); mk[4 * j + 1] = bf16x2_gt0(q.y); mk[4 * j + 2] = bf16x2_gt0(q.z); mk[4 * j + 3] = bf16x2_gt0(q.w);
+  }
+}
+// dgrad epilogue with a prefetched mask: D fp32 (TMEM) -> bf16 & mask -> dst
+__device__ __forceinline__ void epi_chunk_masked(uint32_t taddr, uint8_t* dst, const uint32_t (&mk)[32], uint32_t row,
+                                                 uint32_t chunk) {
+  uint32_t v[64];
+  tmem_ld64(taddr, v);
+  const uint32_t base = chunk * kTile * 128u + row_off(row), r7 = row & 7u;
+#pragma unroll
+  for (uint32_t j = 0; j < 8; j++) {
+    uint4 o;
+    o.x = pack_bf16(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])) & mk[4 * j];
+    o.y = pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])) & mk[4 * j + 1];
+    o.z = pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])) & mk[4 * j + 2];
+    o.w = pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])) & mk[4 * j + 3];
+    *reinterpret_cast<uint4*>(dst + base + ((j ^ r7) << 4)) = o;
+  }
+}
+
 __device__ __forceinline__ void sync_generic_to_async() {
   tc_fence_before();
   fence_proxy_async();
@@ -752,9 +780,11 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
         for (int k = 0; k < 16; k++) acc_last[k] += v[k];
         hand_over_tmem();
       }
+      uint32_t mk[32];
+      mask_prefetch(a_hid(L), row, hc, mk);
       wait_mma();  // dgrad
       mark(8);
-      epi_chunk<true>(tlane + hc * 64u, ebuf, a_hid(L), row, hc);
+      epi_chunk_masked(tlane + hc * 64u, ebuf, mk, row, hc);
       hand_over();
       mark(9);
 
@@ -762,9 +792,10 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
       uint8_t* gcur = ebuf;
       uint8_t* gnext = a_hid(L);
       for (int i = L - 1; i >= 1; i--) {
+        mask_prefetch(a_hid(i), row, hc, mk);
         wait_mma();  // dgrad (the wgrad runs under the epilogue)
         mark(10);
-        epi_chunk<true>(tlane + hc * 64u, gnext, a_hid(i), row, hc);
+        epi_chunk_masked(tlane + hc * 64u, gnext, mk, row, hc);
         hand_over();
         mark(11);
         uint8_t* tmp = gcur; gcur = gnext; gnext = tmp;
