@@ -879,7 +879,7 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
 }
 
 // grad_w[i] += sum over CTAs of part[c][i]: fixed summation order inside a group of CTAs, one atomic per group
-constexpr uint32_t kReduceGroups = 4;
+constexpr uint32_t kReduceGroups = 16;
 __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ part, uint32_t n_ctas, uint32_t n_params,
                                                          float* __restrict__ grad_w) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
