@@ -228,8 +228,10 @@ size_t snerf_field_saved_bytes(const snerf_field_desc* f, uint32_t M, int precis
 
 /* nerf/network.py:39-61 (NeRFNetwork.forward): xyzs [M,3] in [-bound,bound], dirs [M,3] unit ->
  * sigmas [M] (after ReLU), rgbs [M,channel_dim] (after sigmoid).
- * saved (may be NULL): snerf_field_saved_bytes() bytes that the forward fills for the backward of the SAME inputs
- * (the sigma net's geometry features, 32 B/sample); with it the backward does not re-run the sigma net first. */
+ * saved (may be NULL, 16-byte aligned): snerf_field_saved_bytes() bytes that the forward fills for the backward of the
+ * SAME samples and parameters: the packed bf16 weight images, the sigma net's geometry features + raw density, the
+ * hash-grid features and the colour outputs (112 B/sample + 200 KiB).  With it the backward packs nothing, gathers
+ * nothing and does not recompute the output layers; without it the backward regenerates all of that first. */
 int snerf_field_forward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M,
                         const float* table, const float* w_sigma, const float* w_color, int precision,
                         float* sigmas, float* rgbs, void* saved, size_t saved_bytes, void* workspace,
@@ -240,9 +242,10 @@ int snerf_field_density(const snerf_field_desc* f, const float* xyzs, uint32_t M
                         const float* w_sigma, int precision, float* sigmas, float* geo_feat, void* workspace,
                         size_t workspace_bytes, snerf_stream_t stream);
 
-/* Backward of snerf_field_forward.  Recomputes the forward activations from (xyzs, dirs) tile by tile, so
- * nothing but the inputs has to be kept between forward and backward.  grad_table / grad_w_* are
- * ACCUMULATED into (caller zeroes them when a new step starts). */
+/* Backward of snerf_field_forward.  The hidden activations are recomputed tile by tile on chip (saving them would
+ * cost 1.8 KB/sample of HBM traffic each way), so only the inputs and the optional hand-off buffer are kept between
+ * forward and backward.  grad_table / grad_w_* are ACCUMULATED into (caller zeroes them when a new step starts).
+ * bf16 path: n_hidden_sigma <= 3 (the sigma net's small weight gradients live in spare TMEM columns). */
 int snerf_field_backward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M,
                          const float* table, const float* w_sigma, const float* w_color,
                          const float* grad_sigmas, const float* grad_rgbs, int precision, float* grad_table,
