@@ -293,3 +293,21 @@ def adam_step(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0
     denom = np.sqrt(v) * np.float32(1.0 / np.sqrt(bc2)) + np.float32(eps)
     p = p - np.float32(lr / bc1) * (m / denom)
     return p.astype(np.float32), m.astype(np.float32), v.astype(np.float32)
+
+
+def l1_loss_backward(image, weights_sum, target, bg, grad_scale, depth=None, nears=None, fars=None):
+    """Numpy restatement of the step right after compositing in training: the background blend and depth normalisation
+    of nerf/renderer.py:111-112, utils/loss_utils.py:9-10 (mean absolute error) and the gradients torch autograd sends
+    back into composite_rays_train (train.py:61-70).  bg: scalar or [C].  Returns loss, grad_image [N,C],
+    grad_weights_sum [N], pred [N,C], depth_norm [N] or None."""
+    image, ws, target = (np.asarray(a, np.float32) for a in (image, weights_sum, target))
+    bg = np.broadcast_to(np.asarray(bg, np.float32), (image.shape[1],))
+    pred = image + (np.float32(1) - ws)[:, None] * bg[None, :]
+    d = pred - target
+    loss = float(np.abs(d.astype(np.float64)).mean())
+    g_img = (np.sign(d) * np.float32(grad_scale)).astype(np.float32)
+    g_ws = -(g_img * bg[None, :]).sum(-1).astype(np.float32)
+    dn = None
+    if depth is not None:
+        dn = (np.maximum(np.asarray(depth, np.float32) - nears, 0) / (fars - nears)).astype(np.float32)
+    return loss, g_img, g_ws, pred.astype(np.float32), dn

@@ -221,20 +221,20 @@ __global__ void __launch_bounds__(1024) k_l1_loss_backward(const float* __restri
   for (int k = 0; k < C; k++) bg[k] = bg_color ? __ldg(bg_color + k) : bg_scalar;
   float acc = 0.f;
   for (uint32_t n = threadIdx.x; n < N; n += blockDim.x) {
-    const float om = 1.0f - __ldg(weights_sum + n);
+    const float om = fadd(1.0f, -__ldg(weights_sum + n));  // separately rounded, like the torch ops of the reference
     float img[C], tgt[C], g[C], gws = 0.f;
     load_rgb<C>(image, n, img);
     load_rgb<C>(target, n, tgt);
 #pragma unroll
-    for (int k = 0; k < C; k++) img[k] += om * bg[k];  // nerf/renderer.py:111
+    for (int k = 0; k < C; k++) img[k] = fadd(img[k], fmul(om, bg[k]));  // nerf/renderer.py:111
     if (pred_image) store_rgb<C>(pred_image, n, img);
     if (depth_norm) {  // nerf/renderer.py:112
       const float nr = __ldg(nears + n);
-      depth_norm[n] = fmaxf(__ldg(depth + n) - nr, 0.f) / (__ldg(fars + n) - nr);
+      depth_norm[n] = __fdiv_rn(fmaxf(fadd(__ldg(depth + n), -nr), 0.f), fadd(__ldg(fars + n), -nr));
     }
 #pragma unroll
     for (int k = 0; k < C; k++) {
-      const float d = img[k] - tgt[k];
+      const float d = fadd(img[k], -tgt[k]);
       acc += fabsf(d);
       g[k] = d > 0.f ? grad_scale : (d < 0.f ? -grad_scale : 0.f);
       gws -= g[k] * bg[k];

@@ -87,3 +87,37 @@ def test_fused_adam_vs_torch_and_golden(name, built_lib, cuda):
         assert float(a.grad.abs().max()) == 0.0
     assert rel(a.detach().cpu().numpy(), b.detach().cpu().numpy()) <= 2e-6
     assert ours.state_dict()["state"][0]["step"] == 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,bg", [(3, 1.0), (4, [0.2, 0.4, 0.6, 1.0]), (1, 0.0)])
+def test_l1_loss_backward_kernel_vs_oracle_and_autograd(C, bg, built_lib, cuda):
+    """snerf_l1_loss_backward against the numpy oracle and against torch autograd of
+    ((image + (1 - ws) * bg) - target).abs().mean() (nerf/renderer.py:111, utils/loss_utils.py:9-10)."""
+    from oracle import oracle as orc
+    from stable_nerf_b200._lib import check, ptr, stream
+    rng = np.random.default_rng(C)
+    N = 5000
+    image, ws = rng.random((N, C), dtype=np.float32), rng.random(N, dtype=np.float32)
+    target = rng.random((N, C), dtype=np.float32)
+    target[:7] = (image + (1 - ws)[:, None] * np.broadcast_to(np.float32(bg), (C,)))[:7]  # exact zeros: sign(0) = 0
+    depth, nears = rng.random(N, dtype=np.float32) * 3, np.full(N, 0.2, np.float32)
+    fars = nears + 1 + rng.random(N, dtype=np.float32)
+    scale = 0.5 / (N * C)
+    loss_o, gi_o, gw_o, pred_o, dn_o = orc.l1_loss_backward(image, ws, target, bg, scale, depth, nears, fars)
+    d = {k: torch.from_numpy(v).to(cuda) for k, v in dict(image=image, ws=ws, target=target, depth=depth, nears=nears, fars=fars).items()}
+    bg_t = torch.tensor(bg, dtype=torch.float32, device=cuda) if isinstance(bg, list) else None
+    loss = torch.zeros((), device=cuda)
+    gi, gw, pred, dn = torch.empty(N, C, device=cuda), torch.empty(N, device=cuda), torch.empty(N, C, device=cuda), torch.empty(N, device=cuda)
+    check(built_lib.snerf_l1_loss_backward(ptr(d["image"]), ptr(d["ws"]), ptr(d["target"]), ptr(bg_t),
+                                           0.0 if isinstance(bg, list) else float(bg), N, C, scale, ptr(loss), ptr(gi), ptr(gw),
+                                           ptr(pred), ptr(d["depth"]), ptr(d["nears"]), ptr(d["fars"]), ptr(dn), stream()), "l1")
+    torch.cuda.synchronize()
+    assert abs(float(loss) - loss_o) <= 1e-6 * loss_o
+    assert np.array_equal(gi.cpu().numpy(), gi_o) and rel(gw.cpu().numpy(), gw_o) <= 1e-6
+    assert rel(pred.cpu().numpy(), pred_o) <= 1e-6 and rel(dn.cpu().numpy(), dn_o) <= 1e-6
+    img_t, ws_t = d["image"].clone().requires_grad_(True), d["ws"].clone().requires_grad_(True)
+    bgv = bg_t if bg_t is not None else float(bg)
+    l = ((img_t + (1 - ws_t).unsqueeze(-1) * bgv) - d["target"]).abs().mean() * 0.5
+    l.backward()
+    assert rel(gi.cpu().numpy(), img_t.grad.cpu().numpy()) <= 1e-6 and rel(gw.cpu().numpy(), ws_t.grad.cpu().numpy()) <= 1e-5
