@@ -106,21 +106,46 @@ __global__ void __launch_bounds__(256) k_tc_probe(long long* __restrict__ out, i
     for (int rep = 0; rep < 4; rep++) {
       __syncthreads();
       t0 = clock64();
-      if (tid == 0) {
+      if (tc::warp_idx_uniform() == 0) {  // converged warp, elected lane, warp-uniform operands: no R2UR broadcast loops
         tc::tc_fence_after();
-        const uint32_t N = variant == 1 ? 64u : 128u;
+        const uint32_t N = (variant & 1) ? 64u : 128u;
         const uint32_t idesc = tc::make_idesc(128, N, false, false);
-        for (int s = 0; s < counts[e]; s++)
-          tc::mma_ss(tmem, tc::desc_kmajor(tc::smem_u32(sA), 128, s & 7), tc::desc_kmajor(tc::smem_u32(sB), 128, s & 7), idesc, s > 0);
-        tc::mma_commit(&bar);
-        t_issue = clock64();
+        const uint32_t sa = tc::smem_u32(sA), sb = tc::smem_u32(sB);
+        if (tc::elect_one()) {
+          if (variant < 2) {
+            for (int s0 = 0; s0 < counts[e]; s0 += 8) {
+#pragma unroll
+              for (int s = 0; s < 8; s++)
+                if (s0 + s < counts[e])
+                  tc::mma_ss(tmem, tc::desc_kmajor(sa, 128, s), tc::desc_kmajor(sb, 128, s), idesc, (s0 | s) > 0);
+            }
+          } else {  // A operand from TMEM (columns 128..): only B is read from shared memory
+            for (int s0 = 0; s0 < counts[e]; s0 += 8) {
+#pragma unroll
+              for (int s = 0; s < 8; s++)
+                if (s0 + s < counts[e]) {
+                  const uint64_t bd = tc::desc_kmajor(sb, 128, s);
+                  asm volatile(
+                      "{\n\t.reg .pred p;\n\t"
+                      "setp.ne.b32 p, %4, 0;\n\t"
+                      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem),
+                      "r"(tmem + 128u + (uint32_t)s * 8u), "l"(bd), "r"(idesc), "r"((uint32_t)((s0 | s) > 0))
+                      : "memory");
+                }
+            }
+          }
+          tc::mma_commit(&bar);
+          t_issue = clock64();
+        }
+        __syncwarp();
       }
       tc::mbar_wait(&bar, ph);
       ph ^= 1u;
       tc::tc_fence_after();
       t1 = clock64();
     }
-    if (tid == 0) { out[slot] = t_issue - t0; out[slot + 1] = t1 - t0; }
+    if (tid == 0) out[slot + 1] = t1 - t0;
+    if (t_issue != 0) out[slot] = t_issue - t0;
     if (tid == 255) out[slot + 2] = t1 - t0;
     slot += 3;
   }
