@@ -433,7 +433,7 @@ def run_gpu_arm(args):
         C = CHANNELS
         alg = {  # algorithmic bytes / flops per launch (SURVEY section 8d figures)
             "near_far": ("hbm", 32.0 * RAYS_PER_GPU),
-            "march": ("hbm", 48.0 * RAYS_PER_GPU + 32.0 * ns),
+            "march": ("hbm", (32.0 + 48.0) * RAYS_PER_GPU + 32.0 * ns),  # near/far folded into the count launch
             "composite_fwd": ("hbm", (12 + 4 * C) * ns + (20 + 4 * C) * RAYS_PER_GPU),
             "composite_bwd": ("hbm", (16 + 8 * C) * ns + (20 + 8 * C) * RAYS_PER_GPU),
             "loss+composite_bwd": ("hbm", (16 + 8 * C) * ns + (20 + 8 * C) * RAYS_PER_GPU),

@@ -106,6 +106,13 @@ int snerf_march_rays_train_count(const float* rays_o, const float* rays_d, const
                                  float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                                  const float* nears, const float* fars, int32_t* counter, const float* noises,
                                  void* workspace, size_t workspace_bytes, snerf_stream_t stream);
+/* _count with snerf_near_far_from_aabb folded in (one launch fewer per step): nears/fars are OUTPUTS here, the same
+ * bits the stand-alone function writes; pass them on to _write. */
+int snerf_march_rays_train_count_aabb(const float* rays_o, const float* rays_d, const uint8_t* grid, const float* aabb,
+                                      float min_near, float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                                      uint32_t C, uint32_t H, float* nears, float* fars, int32_t* counter,
+                                      const float* noises, void* workspace, size_t workspace_bytes,
+                                      snerf_stream_t stream);
 int snerf_march_rays_train_write(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
                                  float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                                  const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,

@@ -57,6 +57,8 @@ SIGNATURES = {
     "snerf_march_rays_train_workspace_bytes": (c_size_t, [_U]),
     "snerf_march_rays_train_workspace_bytes_ex": (c_size_t, [_U, _U]),
     "snerf_march_rays_train_count": (c_int, [_P, _P, _P, _F, _F, _U, _U, _U, _U, _P, _P, _P, _P, _P, c_size_t, _S]),
+    "snerf_march_rays_train_count_aabb": (c_int, [_P, _P, _P, _P, _F, _F, _F, _U, _U, _U, _U, _P, _P, _P, _P, _P, c_size_t,
+                                                  _S]),
     "snerf_march_rays_train_write": (c_int, [_P, _P, _P, _F, _F, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, c_int,
                                              _P, _P, c_size_t, _S]),
     "snerf_march_rays_ex": (c_int, [_U, _U, _P, _P, _P, _P, _F, _F, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _U, _S]),

@@ -113,8 +113,17 @@ __global__ void __launch_bounds__(kCompThreads) k_composite_train_bwd(
     const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image, const float* __restrict__ sigmas,
     const float* __restrict__ rgbs, const float* __restrict__ deltas, const int32_t* __restrict__ rays,
     const float* __restrict__ weights_sum, const float* __restrict__ image, uint32_t M, uint32_t N, float T_thresh,
-    float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+    float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, const int32_t* __restrict__ n_samples) {
   const int lane = threadIdx.x & 31;
+  if (n_samples) {  // rows [*n_samples, M): alignment padding that no ray owns
+    float z[C];
+#pragma unroll
+    for (int k = 0; k < C; k++) z[k] = 0.f;
+    for (uint32_t i = (uint32_t)max(0, *n_samples) + blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+      grad_sigmas[i] = 0.f;
+      store_rgb<C>(grad_rgbs, i, z);
+    }
+  }
   const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (n >= N) return;
   const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
@@ -346,7 +355,7 @@ int snerf_composite_rays_train_backward_ex(const float* grad_weights_sum, const 
     cudaError_t e = cudaMemsetAsync(grad_sigmas, 0, (size_t)M * sizeof(float), s);
     if (e == cudaSuccess) e = cudaMemsetAsync(grad_rgbs, 0, (size_t)M * channel_dim * sizeof(float), s);
     if (e != cudaSuccess) return (int)e;
-  } else {
+  } else if (N == 0) {
     SNERF_DISPATCH_C(channel_dim, (k_zero_tail<kC><<<8, 256, 0, s>>>(n_samples, M, grad_sigmas, grad_rgbs)));
     launches++;
   }
@@ -356,7 +365,7 @@ int snerf_composite_rays_train_backward_ex(const float* grad_weights_sum, const 
     const uint32_t blocks = div_up(N, kCompThreads / 32);
     SNERF_DISPATCH_C(channel_dim, (k_composite_train_bwd<kC><<<blocks, kCompThreads, 0, s>>>(
                                       grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N,
-                                      T_thresh, grad_sigmas, grad_rgbs)));
+                                      T_thresh, grad_sigmas, grad_rgbs, n_samples)));
     launches++;
   }
   return finish_launch(launches);

@@ -60,7 +60,12 @@ static PackedNet make_packed(const NetShape& s) {
 }
 
 // fp32 [out,in] row-major -> bf16 operand image (rows = out index, 128B-swizzled 64-column chunks)
-__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ w, PackedNet p, uint8_t* __restrict__ img) {
+// blockIdx.y selects the net (0: sigma, 1: colour): both images in one launch
+__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ w0, PackedNet p0, uint8_t* __restrict__ img0,
+                                                      const float* __restrict__ w1, PackedNet p1, uint8_t* __restrict__ img1) {
+  const float* __restrict__ w = blockIdx.y ? w1 : w0;
+  const PackedNet& p = blockIdx.y ? p1 : p0;
+  uint8_t* __restrict__ img = blockIdx.y ? img1 : img0;
   const uint32_t total_groups = p.total_bytes / 16u;
   for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < total_groups; gi += gridDim.x * blockDim.x) {
     const uint32_t byte = gi * 16u;
@@ -1044,12 +1049,9 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
   const uint32_t st = g_stage_mask;
   unsigned launches = 0;
   if (st & kStFwdPack) {
-    k_pack_weights<<<div_up(ps.total_bytes / 16, 256), 256, 0, s>>>(w_sigma, ps, w.wimg_sigma);
+    k_pack_weights<<<dim3(div_up(std::max(ps.total_bytes, pc.total_bytes) / 16, 256), sigma_only ? 1 : 2), 256, 0, s>>>(
+        w_sigma, ps, w.wimg_sigma, w_color, pc, w.wimg_color);
     launches++;
-    if (!sigma_only) {
-      k_pack_weights<<<div_up(pc.total_bytes / 16, 256), 256, 0, s>>>(w_color, pc, w.wimg_color);
-      launches++;
-    }
   }
   TcParams p;
   fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
@@ -1098,9 +1100,9 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   unsigned launches = 0;
   if (saved) carve_handoff(f, M, (char*)const_cast<void*>(saved), &w);  // incl. the forward's packed weight images
   if ((st & kStBwdPack) && !saved) {
-    k_pack_weights<<<div_up(ps.total_bytes / 16, 256), 256, 0, s>>>(w_sigma, ps, w.wimg_sigma);
-    k_pack_weights<<<div_up(pc.total_bytes / 16, 256), 256, 0, s>>>(w_color, pc, w.wimg_color);
-    launches += 2;
+    k_pack_weights<<<dim3(div_up(std::max(ps.total_bytes, pc.total_bytes) / 16, 256), 2), 256, 0, s>>>(
+        w_sigma, ps, w.wimg_sigma, w_color, pc, w.wimg_color);
+    launches++;
   }
   // 1. the geometry features the colour net consumes and the encoded inputs of the sigma net: handed over by the
   //    forward, or regenerated by running the sigma net's forward again

@@ -11,29 +11,40 @@ namespace snerf {
 
 // ------------------------------------------------------------------------------------------------ utils
 
+// raymarching.cu:92-157: slab intersection with the aabb, min_near clamp, miss -> (FLT_MAX, FLT_MAX)
+__device__ __forceinline__ void near_far_of(const float* __restrict__ o, const float* __restrict__ d,
+                                            const float* __restrict__ aabb, float min_near, float& near_out, float& far_out) {
+  const float ox = o[0], oy = o[1], oz = o[2];
+  const float dx = d[0], dy = d[1], dz = d[2];
+  const float rdx = __frcp_rn(dx), rdy = __frcp_rn(dy), rdz = __frcp_rn(dz);
+  const float kMax = 3.402823466e+38f;
+  near_out = kMax;
+  far_out = kMax;
+  float near = fmul(fadd(aabb[0], -ox), rdx), far = fmul(fadd(aabb[3], -ox), rdx);
+  if (near > far) { float c = near; near = far; far = c; }
+  float near_y = fmul(fadd(aabb[1], -oy), rdy), far_y = fmul(fadd(aabb[4], -oy), rdy);
+  if (near_y > far_y) { float c = near_y; near_y = far_y; far_y = c; }
+  if (near > far_y || near_y > far) return;
+  if (near_y > near) near = near_y;
+  if (far_y < far) far = far_y;
+  float near_z = fmul(fadd(aabb[2], -oz), rdz), far_z = fmul(fadd(aabb[5], -oz), rdz);
+  if (near_z > far_z) { float c = near_z; near_z = far_z; far_z = c; }
+  if (near > far_z || near_z > far) return;
+  if (near_z > near) near = near_z;
+  if (far_z < far) far = far_z;
+  if (near < min_near) near = min_near;
+  near_out = near;
+  far_out = far;
+}
+
 __global__ void __launch_bounds__(256) k_near_far_from_aabb(const float* __restrict__ rays_o,
                                                             const float* __restrict__ rays_d,
                                                             const float* __restrict__ aabb, uint32_t N, float min_near,
                                                             float* __restrict__ nears, float* __restrict__ fars) {
   const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
-  const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
-  const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
-  const float rdx = __frcp_rn(dx), rdy = __frcp_rn(dy), rdz = __frcp_rn(dz);
-  float near = fmul(fadd(aabb[0], -ox), rdx), far = fmul(fadd(aabb[3], -ox), rdx);
-  if (near > far) { float c = near; near = far; far = c; }
-  float near_y = fmul(fadd(aabb[1], -oy), rdy), far_y = fmul(fadd(aabb[4], -oy), rdy);
-  if (near_y > far_y) { float c = near_y; near_y = far_y; far_y = c; }
-  const float kMax = 3.402823466e+38f;
-  if (near > far_y || near_y > far) { nears[n] = kMax; fars[n] = kMax; return; }
-  if (near_y > near) near = near_y;
-  if (far_y < far) far = far_y;
-  float near_z = fmul(fadd(aabb[2], -oz), rdz), far_z = fmul(fadd(aabb[5], -oz), rdz);
-  if (near_z > far_z) { float c = near_z; near_z = far_z; far_z = c; }
-  if (near > far_z || near_z > far) { nears[n] = kMax; fars[n] = kMax; return; }
-  if (near_z > near) near = near_z;
-  if (far_z < far) far = far_z;
-  if (near < min_near) near = min_near;
+  float near, far;
+  near_far_of(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, aabb, min_near, near, far);
   nears[n] = near;
   fars[n] = far;
 }
@@ -333,15 +344,25 @@ __global__ void __launch_bounds__(kMarchThreads) k_march_train_count(MarchParams
                                                                      const float* __restrict__ fars,
                                                                      const float* __restrict__ noises,
                                                                      uint32_t* __restrict__ counts,
-                                                                     float* __restrict__ t_scratch) {
+                                                                     float* __restrict__ t_scratch,
+                                                                     const float* __restrict__ aabb, float min_near,
+                                                                     float* __restrict__ nears_out,
+                                                                     float* __restrict__ fars_out) {
   const uint32_t n = blockIdx.x * kMarchRaysPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
   Ray r;
   r.load(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
-  const float far = __ldg(fars + n);
+  float near, far;
+  if (aabb) {  // near/far computed here (every lane, same values) instead of by a launch of its own
+    near_far_of(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, aabb, min_near, near, far);
+    if (lane == 0) { nears_out[n] = near; fars_out[n] = far; }
+  } else {
+    near = __ldg(nears + n);
+    far = __ldg(fars + n);
+  }
   WarpMarch st;
-  st.t_base = ray_t0(p, __ldg(nears + n), __ldg(noises + n));
+  st.t_base = ray_t0(p, near, __ldg(noises + n));
   st.resume_t = -3.402823466e+38f;
   st.last_t = st.t_base;
   st.count = 0;
@@ -374,13 +395,22 @@ constexpr int kMarchThreadBlock = 128;
 __global__ void __launch_bounds__(kMarchThreadBlock) k_march_train_count_thread(
     MarchParams p, const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
     uint32_t N, const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ noises,
-    uint32_t* __restrict__ counts, float* __restrict__ t_scratch) {
+    uint32_t* __restrict__ counts, float* __restrict__ t_scratch, const float* __restrict__ aabb, float min_near,
+    float* __restrict__ nears_out, float* __restrict__ fars_out) {
   const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   Ray r;
   r.load(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
-  const float far = fars[n];
-  float t = ray_t0(p, nears[n], noises[n]);
+  float near, far;
+  if (aabb) {
+    near_far_of(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, aabb, min_near, near, far);
+    nears_out[n] = near;
+    fars_out[n] = far;
+  } else {
+    near = nears[n];
+    far = fars[n];
+  }
+  float t = ray_t0(p, near, noises[n]);
   float x, y, z, dt;
   uint32_t num_steps = 0;
   float* ts = t_scratch ? t_scratch + (size_t)n * p.max_steps : nullptr;
@@ -726,26 +756,44 @@ static float* ws_t_scratch(void* workspace, size_t workspace_bytes, uint32_t N, 
   return (float*)((char*)workspace + snerf_march_rays_train_workspace_bytes(N));
 }
 
+static int march_count_impl(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                            uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, const float* nears, const float* fars,
+                            int32_t* counter, const float* noises, void* workspace, size_t workspace_bytes,
+                            const float* aabb, float min_near, float* nears_out, float* fars_out, cudaStream_t s) {
+  if (workspace_bytes < snerf_march_rays_train_workspace_bytes(N)) return SNERF_E_WORKSPACE;
+  MarchParams p;
+  if (int e = make_march_params(&p, bound, dt_gamma, max_steps, C, H)) return e;
+  uint32_t* counts = (uint32_t*)workspace;
+  const uint32_t nblocks = div_up(N, kMarchRaysPerBlock);
+  float* ts = ws_t_scratch(workspace, workspace_bytes, N, max_steps);
+  if (N <= g_march_warp_max_rays)
+    k_march_train_count<<<nblocks, kMarchThreads, 0, s>>>(p, rays_o, rays_d, grid, N, nears, fars, noises, counts, ts, aabb,
+                                                          min_near, nears_out, fars_out);
+  else
+    k_march_train_count_thread<<<div_up(N, kMarchThreadBlock), kMarchThreadBlock, 0, s>>>(
+        p, rays_o, rays_d, grid, N, nears, fars, noises, counts, ts, aabb, min_near, nears_out, fars_out);
+  k_march_train_scan<<<1, 1024, 0, s>>>(counts, N, ws_offsets(workspace, N), counter);
+  return finish_launch(2);
+}
+
 int snerf_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
                                  float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                                  const float* nears, const float* fars, int32_t* counter, const float* noises,
                                  void* workspace, size_t workspace_bytes, snerf_stream_t stream) {
   if (N == 0) return SNERF_OK;
   if (!rays_o || !rays_d || !grid || !nears || !fars || !counter || !noises || !workspace) return SNERF_E_BADARG;
-  if (workspace_bytes < snerf_march_rays_train_workspace_bytes(N)) return SNERF_E_WORKSPACE;
-  MarchParams p;
-  if (int e = make_march_params(&p, bound, dt_gamma, max_steps, C, H)) return e;
-  uint32_t* counts = (uint32_t*)workspace;
-  const uint32_t nblocks = div_up(N, kMarchRaysPerBlock);
-  cudaStream_t s = (cudaStream_t)stream;
-  float* ts = ws_t_scratch(workspace, workspace_bytes, N, max_steps);
-  if (N <= g_march_warp_max_rays)
-    k_march_train_count<<<nblocks, kMarchThreads, 0, s>>>(p, rays_o, rays_d, grid, N, nears, fars, noises, counts, ts);
-  else
-    k_march_train_count_thread<<<div_up(N, kMarchThreadBlock), kMarchThreadBlock, 0, s>>>(p, rays_o, rays_d, grid, N, nears,
-                                                                                        fars, noises, counts, ts);
-  k_march_train_scan<<<1, 1024, 0, s>>>(counts, N, ws_offsets(workspace, N), counter);
-  return finish_launch(2);
+  return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, counter, noises, workspace,
+                          workspace_bytes, nullptr, 0.f, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int snerf_march_rays_train_count_aabb(const float* rays_o, const float* rays_d, const uint8_t* grid, const float* aabb,
+                                      float min_near, float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                                      uint32_t C, uint32_t H, float* nears, float* fars, int32_t* counter,
+                                      const float* noises, void* workspace, size_t workspace_bytes, snerf_stream_t stream) {
+  if (N == 0) return SNERF_OK;
+  if (!rays_o || !rays_d || !grid || !aabb || !nears || !fars || !counter || !noises || !workspace) return SNERF_E_BADARG;
+  return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nullptr, nullptr, counter, noises,
+                          workspace, workspace_bytes, aabb, min_near, nears, fars, (cudaStream_t)stream);
 }
 
 int snerf_march_rays_train_write(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,

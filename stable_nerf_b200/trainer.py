@@ -169,13 +169,11 @@ class TrainStep:
         if self.perturb:
             b["noises"].uniform_()
         mark("zero_grads")
-        chk(lib.snerf_near_far_from_aabb(P(self.rays_o), P(self.rays_d), P(m.aabb_train), N, float(m.min_near),
-                                         P(b["nears"]), P(b["fars"]), S), "near_far_from_aabb")
-        mark("near_far")
         geom = (float(m.bound), float(self.dt_gamma), int(self.max_steps), N, int(m.cascade), int(m.grid_size))
-        chk(lib.snerf_march_rays_train_count(P(self.rays_o), P(self.rays_d), P(m.density_bitfield), *geom, P(b["nears"]),
-                                             P(b["fars"]), P(counter), P(b["noises"]), P(b["march_ws"]),
-                                             b["march_ws_bytes"], S), "march count")
+        chk(lib.snerf_march_rays_train_count_aabb(P(self.rays_o), P(self.rays_d), P(m.density_bitfield), P(m.aabb_train),
+                                                  float(m.min_near), *geom, P(b["nears"]), P(b["fars"]), P(counter),
+                                                  P(b["noises"]), P(b["march_ws"]), b["march_ws_bytes"], S),
+            "near/far + march count")
         chk(lib.snerf_march_rays_train_write(P(self.rays_o), P(self.rays_d), P(m.density_bitfield), *geom, M,
                                              P(b["nears"]), P(b["fars"]), P(b["xyzs"]), P(b["dirs"]), P(b["deltas"]),
                                              P(b["rays"]), P(b["noises"]), 1, P(b["n_samples"]), P(b["march_ws"]),
