@@ -358,3 +358,53 @@ def test_full_size_properties(built_lib, cuda):
     w2, d2, i2 = rm.composite_rays_train(sig, rgb * 2, deltas, rays, 1e-4, 3)
     assert torch.allclose(i2, i1 * 2, rtol=1e-5, atol=1e-6) and torch.equal(w1, w2)
     assert (w1 <= 1 + 1e-5).all() and (w1 >= 0).all()
+
+
+def test_cfg5_size_thread_grain_and_fused_near_far(built_lib, cuda):
+    """cfg5 size (2^18 rays): the thread-per-ray grain (what batches above 49 152 rays use) against the warp-per-ray
+    grain on the same rays (counts, offsets, positions bit for bit), sample-in-occupied-cell property, and the count
+    entry point with near/far folded in against the stand-alone near_far_from_aabb."""
+    from oracle import oracle as orc
+    from stable_nerf_b200 import raymarching as rm, synthetic as syn
+    from stable_nerf_b200._lib import check, ptr, stream
+    lib = built_lib
+    N, max_steps = 1 << 18, 1024
+    bf_np = syn.pack_bitfield(syn.occupancy_grid(lego_like=True))
+    ro, rd = syn.train_batch(N, n_views=8, seed=4)
+    o, d, bf = dev_t(ro, cuda), dev_t(rd, cuda), dev_t(bf_np, cuda)
+    aabb = torch.tensor([-1., -1, -1, 1, 1, 1], device=cuda)
+    nears, fars = rm.near_far_from_aabb(o, d, aabb, 0.2)
+    noises = torch.zeros(N, device=cuda)
+    nb = lib.snerf_march_rays_train_workspace_bytes_ex(N, max_steps)
+    geom = (1.0, 0.0, max_steps, N, 1, 128)
+    out = {}
+    for name, thr in (("warp", 1 << 30), ("thread", 0)):
+        lib.snerf_debug_set_march_warp_max_rays(thr)
+        try:
+            ws = torch.empty(nb, dtype=torch.uint8, device=cuda)
+            counter = torch.zeros(2, dtype=torch.int32, device=cuda)
+            n2, f2 = torch.empty(N, device=cuda), torch.empty(N, device=cuda)
+            check(lib.snerf_march_rays_train_count_aabb(ptr(o), ptr(d), ptr(bf), ptr(aabb), 0.2, *geom, ptr(n2), ptr(f2),
+                                                        ptr(counter), ptr(noises), ptr(ws), nb, stream()), "count_aabb")
+            total = int(counter[0].item())
+            M = total + 128 - total % 128
+            xyzs, dirs, deltas = torch.empty(M, 3, device=cuda), torch.empty(M, 3, device=cuda), torch.empty(M, 2, device=cuda)
+            rays = torch.empty(N, 3, dtype=torch.int32, device=cuda)
+            check(lib.snerf_march_rays_train_write(ptr(o), ptr(d), ptr(bf), *geom, M, ptr(n2), ptr(f2), ptr(xyzs), ptr(dirs),
+                                                   ptr(deltas), ptr(rays), ptr(noises), 1, None, ptr(ws), nb, stream()), "write")
+            torch.cuda.synchronize()
+            out[name] = (total, rays.cpu().numpy(), xyzs.cpu().numpy(), deltas.cpu().numpy(), n2.cpu().numpy(), f2.cpu().numpy())
+        finally:
+            lib.snerf_debug_set_march_warp_max_rays(49152)
+    tw, tt = out["warp"], out["thread"]
+    assert tw[0] == tt[0] and tw[0] > 10_000_000
+    for a, b, what in zip(tw[1:], tt[1:], ("rays", "xyzs", "deltas", "nears", "fars")):
+        assert_bits_equal(a, b, what + " (warp vs thread grain at 2^18 rays)")
+    assert_bits_equal(tw[4], nears.cpu().numpy(), "nears (folded vs stand-alone)")
+    assert_bits_equal(tw[5], fars.cpu().numpy(), "fars (folded vs stand-alone)")
+    r = tw[1]
+    assert (np.cumsum(r[:, 2].astype(np.int64)) - r[:, 2] == r[:, 1]).all()
+    x = tw[2][:tw[0]]
+    cell = np.clip((x + np.float32(1.0)) * np.float32(64.0), 0, 127).astype(np.uint32)
+    idx = orc.morton3D(cell.astype(np.int32)).astype(np.uint32)
+    assert ((bf_np[idx >> 3] >> (idx & 7)) & 1).all()
