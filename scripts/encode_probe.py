@@ -44,7 +44,7 @@ pts = ((xyzs + 1) * 0.5).contiguous()
 gtab = torch.zeros_like(table)
 # all levels active: sweep of the merging threshold
 genc = torch.randn(M, 32, device=dev)
-for dd in (0, 64, 128, 300, 600, 0x80000000, 0x80000000 + 64, 0x80000000 + 128, 0x80000000 + 300, 0x80000000 + 600):
+for dd in (0, 128, 300, 512, 600, 1024, 2048, 4096):
     lib.snerf_debug_set_dedupe_max_res(dd)
     t = timeit(lambda: chk(lib.snerf_hashgrid_backward(g, P(pts), P(genc), M, P(gtab), S()), "hb"), n=10)
     print(f"all levels, dedupe_max_res {dd & 0x7fffffff} pairing {not (dd >> 31)}: {t:.1f} us")
