@@ -76,6 +76,7 @@ class TrainStep:
         self.fused, self.perturb, self.dt_gamma = bool(fused), bool(perturb), dt_gamma
         self._bufs = None
         self._mark = None
+        self._graph_fwd = self._graph_bwd = None
         # optional optimiser (stable_nerf_b200.optim.FusedAdam/W or any torch optimiser), stepped after every step();
         # one that zeroes the gradients inside its step spares the step's own 49 MB memset
         self.optimizer = optimizer
@@ -144,8 +145,10 @@ class TrainStep:
         self._bufs = b
         return b
 
-    def _body_fused(self):
+    def _body_fused(self, phase="both"):
         """The same step as a straight sequence of C-ABI calls: no autograd graph, no torch glue kernels.
+        phase: "both" (a whole step), or "forward" / "backward" for callers that put their own differentiable stage
+        between the rendered image and the NeRF's backward (``forward()`` / ``backward(grad_image)``).
         near/far -> march (count, scan, write) -> field forward -> composite forward -> L1 loss + its gradient
         (one launch: background blend, depth normalisation, loss, d loss/d image, d loss/d weights_sum) ->
         composite backward -> field backward (accumulates straight into the parameters' .grad).
@@ -159,6 +162,8 @@ class TrainStep:
         sp, cp = m.sigma_net.params, m.color_net.params
         nm = m.sigma_net.n_mlp
         mark = self._mark or (lambda name: None)
+        if phase == "backward":
+            return self._fused_backward(b, M, mark)
         mark("start")
         if not self._opt_zeroes:
             for p in self.params:
@@ -195,6 +200,19 @@ class TrainStep:
                                        P(b["pred"]), P(b["depth"]), P(b["nears"]), P(b["fars"]), P(b["depth_norm"]), S),
             "l1 loss")
         mark("loss")
+        self.outputs = {"image": b["pred"], "depth": b["depth_norm"], "weights_sum": b["ws"]}
+        if phase == "forward":
+            return
+        self._fused_backward(b, M, mark)
+
+    def _fused_backward(self, b, M, mark):
+        m, N, C = self.model, self.n_rays, self.model.channel_dim
+        lib = _lib.load()
+        P, S, chk = _lib.ptr, _lib.stream(), _lib.check
+        prec = _precision_code(m.precision)
+        sp, cp = m.sigma_net.params, m.color_net.params
+        nm = m.sigma_net.n_mlp
+        spd = sp.detach()
         chk(lib.snerf_composite_rays_train_backward_ex(P(b["g_ws"]), P(b["g_img"]), P(b["sigmas"]), P(b["rgbs"]),
                                                        P(b["deltas"]), P(b["rays"]), P(b["ws"]), P(b["image"]), M, N,
                                                        float(self.T_thresh), C, P(b["g_sig"]), P(b["g_rgb"]),
@@ -207,7 +225,6 @@ class TrainStep:
                                         P(b["saved"]), b["saved_bytes"], P(b["field_ws"]), b["field_ws_bytes"],
                                         P(b.get("d_enc")), S), "field backward")
         mark("field_bwd")
-        self.outputs = {"image": b["pred"], "depth": b["depth_norm"], "weights_sum": b["ws"]}
 
     def profile_stages(self, iters=10):
         """Device time of each stage of the fused step (CUDA events on the launch stream, eager launches): returns
@@ -366,6 +383,66 @@ class TrainStep:
             handles.append(dist.all_reduce(grad[lo:hi], async_op=True))
         for h in handles:
             h.wait()
+
+    def forward(self, rays_o=None, rays_d=None, target=None):
+        """First half of a step, for training loops that feed the rendered image into a further differentiable stage
+        (train.py:61-99: the NeRF's latent image conditions the SD U-Net): march -> field -> composite -> blend, L1 loss
+        and its gradient.  Returns ``{'image' [N,C], 'depth' [N], 'weights_sum' [N]}`` (views of persistent buffers)."""
+        if not (self.fused and self.model.mean_count > 0):
+            raise RuntimeError("forward()/backward() need the fused path: call warmup() first")
+        if rays_o is not None:
+            self.rays_o.copy_(rays_o, non_blocking=True)
+            self.rays_d.copy_(rays_d, non_blocking=True)
+            self.target.copy_(target, non_blocking=True)
+        if self.use_graph:
+            if self._graph_fwd is None:
+                self._graph_fwd = self._capture_phase("forward")
+            self._graph_fwd.replay()
+        else:
+            self._body_fused("forward")
+        return self.outputs
+
+    def backward(self, grad_image=None):
+        """Second half: backward of the path.  grad_image [N,C] (optional) is an external d loss / d image -- e.g. what
+        autograd returns for the SD loss w.r.t. ``forward()['image']`` -- added to the L1 loss's own gradient
+        (image = composite + (1 - weights_sum) * bg, so it also feeds d loss / d weights_sum)."""
+        b = self._bufs
+        if grad_image is not None:
+            g = grad_image.detach().to(torch.float32).reshape(self.n_rays, self.model.channel_dim)
+            b["g_img"].add_(g)
+            bg = b["bg"] if b["bg"] is not None else b["bg_scalar"]
+            b["g_ws"].sub_((g * bg).sum(-1))
+        if self.use_graph:
+            if self._graph_bwd is None:
+                self._graph_bwd = self._capture_phase("backward")
+            self._graph_bwd.replay()
+        else:
+            self._body_fused("backward")
+        if self.world_size > 1:
+            if b.get("d_enc") is not None:
+                self._scatter_and_reduce()
+            else:
+                allreduce_gradients(self.params, self.world_size)
+        if self.optimizer is not None:
+            self.optimizer.step()
+        return self.loss
+
+    def _capture_phase(self, phase):
+        m = self.model
+        local_step = m.local_step
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._body_fused(phase)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        m.local_step = local_step
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body_fused(phase)
+        if phase == "forward":
+            m.local_step = local_step  # replays keep writing the step_counter row recorded here
+        return g
 
     def pinned_inputs(self):
         """(rays_o, rays_d, target) views into ONE pinned host buffer laid out like the device inputs.  Filled by the

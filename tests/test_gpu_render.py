@@ -246,3 +246,61 @@ def test_inference_schedule_changes_the_image_by_rounding_only(built_lib, cuda):
     assert outs[4][2] < outs[1][2]
     for k in (4, 8):
         assert rel_err(outs[k][0], outs[1][0]) <= 1e-5 and rel_err(outs[k][1], outs[1][1]) <= 1e-5
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_split_step_with_external_image_gradient(use_graph, built_lib, cuda):
+    """TrainStep.forward() / backward(grad_image): the call pattern of train.py:61-99, where the rendered latent image
+    also feeds a further differentiable stage (the SD U-Net) whose gradient w.r.t. the image comes back from autograd.
+    Reference here: the same total loss  L1 + sum(image * Wext)  through NeRFNetwork.render + torch autograd."""
+    from stable_nerf_b200 import NeRFNetwork, synthetic as syn
+    from stable_nerf_b200.trainer import TrainStep
+    C, N = 4, 512
+    ro, rd = syn.train_batch(N, 100, 100, 138.0, n_views=2, seed=21)
+    rng = np.random.default_rng(2)
+    tgt = rng.random((N, C), dtype=np.float32)
+    wext = (rng.standard_normal((N, C)) * 1e-3).astype(np.float32)
+    grid = syn.occupancy_grid(lego_like=True)
+    t = [torch.from_numpy(a).to(cuda) for a in (ro, rd, tgt)]
+    W = torch.from_numpy(wext).to(cuda)
+
+    def make():
+        model = NeRFNetwork(channel_dim=C, precision="fp32").to(cuda)
+        with torch.no_grad():
+            model.sigma_net.params[model.sigma_net.n_mlp:] *= 1e4
+        model.density_bitfield.copy_(torch.from_numpy(syn.pack_bitfield(grid)))
+        model.train()
+        return model
+    # reference: autograd over the whole thing
+    model = make()
+    ts_ref = TrainStep(model, N, max_steps=128, use_graph=False, fused=False)
+    ts_ref.warmup(*t)  # fixes mean_count like the fused run below
+    for p in model.parameters():
+        if p.grad is not None:
+            p.grad.zero_()
+    out = model.render(t[0][None], t[1][None], bg_color=1, max_steps=128)
+    img = out["image"].view(-1, C)
+    loss_ref = (img - t[2]).abs().mean() + (img * W).sum()
+    loss_ref.backward()
+    g_ref = (model.sigma_net.params.grad.cpu().numpy().copy(), model.color_net.params.grad.cpu().numpy().copy())
+    # split fused step
+    model = make()
+    ts = TrainStep(model, N, max_steps=128, use_graph=use_graph)
+    ts.warmup(*t)
+    for _ in range(2):  # twice: the second call replays the captured halves
+        outs = ts.forward(*t)
+        image = outs["image"].clone().requires_grad_(True)
+        ext = (image * W).sum()  # the "further differentiable stage"
+        ext.backward()
+        l1 = ts.backward(image.grad)
+    torch.cuda.synchronize()
+    assert rel_err(outs["image"].cpu().numpy(), img.detach().cpu().numpy()) <= 1e-5
+    assert abs(float(l1) + float(ext.detach()) - float(loss_ref.detach())) <= 1e-5 * abs(float(loss_ref.detach()))
+    assert rel_err(model.sigma_net.params.grad.cpu().numpy(), g_ref[0]) <= 1e-4
+    assert rel_err(model.color_net.params.grad.cpu().numpy(), g_ref[1]) <= 1e-4
+    # and without an external gradient the two halves are the plain step
+    l_split = float(ts.backward(None) if ts.forward(*t) else 0)
+    g_split = model.sigma_net.params.grad.clone()
+    l_step = float(ts.step(*t))
+    torch.cuda.synchronize()
+    assert abs(l_split - l_step) <= 1e-6 and rel_err(model.sigma_net.params.grad.cpu().numpy(), g_split.cpu().numpy()) <= 1e-5
