@@ -279,26 +279,40 @@ __device__ __forceinline__ void sync_generic_to_async() {
 }
 
 // ------------------------------------------------------------------------------------------------ forward kernel
-// NET 0: sigma net (hash-grid input; outputs sigma, geo).  NET 1: colour net (SH + geo input; outputs rgb).
+// NET 0: sigma net (hash-grid features in; sigma, geo out).  NET 1: colour net (SH + geo in; rgb out).
 //
-// A CTA is kFwdGroups independent tile workers (warpgroups of 128 threads: thread = sample row = TMEM lane) that
-// share the resident weight image and the tensor pipe.  Each worker runs the sequential program
-//   input tile -> [MMA -> epilogue] x layers -> outputs
-// on its own activation buffer, accumulator columns, mbarrier and named barrier; because the workers are out of
-// phase, one worker's gathers and epilogues overlap the others' MMAs.
+// The forward has no use for the activations in shared memory (no weight gradients), so they never go there: a
+// worker's activation tile lives in TENSOR MEMORY as the A operand of the next layer (128 lanes = sample rows, two
+// bf16 per 32-bit column), written by the epilogue with tcgen05.st and read by tcgen05.mma directly.  An SS-mode
+// M128 x N128 x K16 instruction reads 8 KB of operands from shared memory per 64 clk -- all of the 128 B/clk the SM
+// has -- and the epilogue's 32 KB of stores per layer then stall the tensor pipe (measured: the SS version of this
+// kernel sat at 48-53 % tensor-active); with A in TMEM only the 4 KB of weights per instruction come from shared memory.
+//
+// A CTA is kFwdGroups independent tile workers (warpgroups of 128 threads: thread = sample row = TMEM lane) that share
+// the resident weight image and the tensor pipe; each owns 128 accumulator + 64 operand columns.  Each runs
+//   input row -> TMEM -> [MMA -> LDTM -> ReLU/pack -> STTM] x layers -> outputs
+// with its own mbarrier and named barrier; out of phase, one worker's epilogue overlaps the other's MMAs.
 
-constexpr uint32_t kFwdGroups = 3;
+constexpr uint32_t kFwdGroups = 2;
 constexpr uint32_t kFwdThreads = 128 * kFwdGroups;
+constexpr uint32_t kFwdCols = 192;  // per worker: accumulator [0,128) + A operand [128,192)
+
+// D[128 x N] (+)= A[128 x 16*KSTEPS] (tensor memory) . W[N x 16*KSTEPS]^T (K-major weight image in shared memory)
+template <uint32_t N, uint32_t KSTEPS>
+__device__ __forceinline__ void mma_forward_ts(uint32_t d, uint32_t a_tmem, const uint8_t* w) {
+  constexpr uint32_t idesc = make_idesc(kTile, N, false, false);
+  const uint32_t sw = smem_u32(w);
+#pragma unroll
+  for (uint32_t s = 0; s < KSTEPS; s++) mma_ts(d, a_tmem + s * 8u, desc_kmajor(sw, N, s), idesc, s > 0);
+}
 
 template <int NET>
 __global__ void __launch_bounds__(kFwdThreads, 1) k_field_fwd(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* wsm = smem;  // all packed matrices of the net
+  uint8_t* wsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // weights
   __shared__ uint64_t wbar, mbar[kFwdGroups];
   __shared__ uint32_t tmem_base_s;
   const uint32_t tid = threadIdx.x, warp = warp_idx_uniform(), wg = warp >> 2, row = tid & 127u;
-  uint8_t* act = smem + p.net.total_bytes + wg * kActBytes;  // [128 x 128] activation tile (input = chunk 0)
   const uint32_t n_tiles = div_up(p.M, kTile);
 
   if (tid == 0) {
@@ -313,20 +327,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_field_fwd(const TcParams p) 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_s + wg * kTile;            // this worker's 128 accumulator columns
-  const uint32_t tlane = tmem + (((warp & 3u) * 32u) << 16);  // + this warp's TMEM lane quadrant
+  const uint32_t tmem = tmem_base_s + wg * kFwdCols;           // this worker's accumulator columns
+  const uint32_t tlane = tmem + (((warp & 3u) * 32u) << 16);    // + this warp's TMEM lane quadrant
+  const uint32_t a_tmem = tmem + 128u, a_lane = tlane + 128u;   // this worker's A operand columns
   uint32_t mph = 0;
   const int L = p.net.n_mats - 1;
-  auto worker_sync = [&]() {  // generic-proxy writes of this worker -> visible to the tensor pipe
+  auto worker_sync = [&]() {  // this worker's TMEM writes / reads are done; its issuer may go on
     tc_fence_before();
-    fence_proxy_async();
     bar_sync(1u + wg, 128u);
   };
 
   // The row's input, loaded one tile ahead (raw: nothing below depends on a loaded value until the next tile starts,
-  // so the loads stay in flight under the running tile).  NET 0 with precomputed features: the 32 bf16 columns;
+  // so the loads stay in flight under the running tile).  NET 0: the 32 bf16 hash-grid features (k_hashgrid_fwd);
   // NET 1: the direction (SH-4 is evaluated when the tile starts) and the 15 geometry features.
-  const bool prefetch = NET == 1 || p.enc_ready;
   uint4 pre[4];
   float pd[3];
   auto fetch_raw = [&](uint32_t t) {
@@ -349,35 +362,33 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_field_fwd(const TcParams p) 
     }
   };
   const uint32_t t_first = blockIdx.x + gridDim.x * wg, t_step = gridDim.x * kFwdGroups;
-  if (prefetch && t_first < n_tiles) fetch_raw(t_first);
+  if (t_first < n_tiles) fetch_raw(t_first);
 
   for (uint32_t t = t_first; t < n_tiles; t += t_step) {
     const uint32_t m = t * kTile + row;
-    if (prefetch) {
-      if (NET == 1) {
-        if (m < p.M) {
-          float o[16];
-          sh4_eval(fmul(fadd(pd[0], 1.0f), 0.5f), fmul(fadd(pd[1], 1.0f), 0.5f), fmul(fadd(pd[2], 1.0f), 0.5f), o);
-          pre[0] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-          pre[1] = make_uint4(pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]), pack_bf16(o[12], o[13]), pack_bf16(o[14], o[15]));
-          pre[3].w &= 0x0000ffffu;  // column 31 is the zero pad (the slot holds sigma_raw in the geo buffer)
-        }
-      }
-      store_input<0, 4>(pre, row, act);
-    } else {
-      load_input<NET, 0, 4, false>(p, m, row, act);
+    if (NET == 1 && m < p.M) {
+      float o[16];
+      sh4_eval(fmul(fadd(pd[0], 1.0f), 0.5f), fmul(fadd(pd[1], 1.0f), 0.5f), fmul(fadd(pd[2], 1.0f), 0.5f), o);
+      pre[0] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+      pre[1] = make_uint4(pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]), pack_bf16(o[12], o[13]), pack_bf16(o[14], o[15]));
+      pre[3].w &= 0x0000ffffu;  // column 31 is the zero pad (the slot holds sigma_raw in the geo buffer)
+    }
+    {  // 32 input columns = 16 packed words -> A operand columns 0..15
+      const uint32_t in16[16] = {pre[0].x, pre[0].y, pre[0].z, pre[0].w, pre[1].x, pre[1].y, pre[1].z, pre[1].w,
+                                 pre[2].x, pre[2].y, pre[2].z, pre[2].w, pre[3].x, pre[3].y, pre[3].z, pre[3].w};
+      tmem_st16(a_lane, in16);
     }
     worker_sync();
-    if (prefetch && t + t_step < n_tiles) fetch_raw(t + t_step);
+    if (t + t_step < n_tiles) fetch_raw(t + t_step);
     for (int i = 0; i <= L; i++) {
       if ((warp & 3u) == 0) {  // the worker's first warp issues (converged warp, elected lane, uniform operands)
         if (t == t_first) mbar_wait(&wbar, 0);  // weights resident (first tile of the worker)
         tc_fence_after();
         const uint8_t* w = wsm + p.net.img_off[i];
         if (elect_one()) {
-          if (i == 0) mma_forward<kTile, 2>(tmem, act, w);
-          else if (i < L) mma_forward<kTile, 8>(tmem, act, w);
-          else mma_forward<16, 8>(tmem, act, w);
+          if (i == 0) mma_forward_ts<kTile, 2>(tmem, a_tmem, w);
+          else if (i < L) mma_forward_ts<kTile, 8>(tmem, a_tmem, w);
+          else mma_forward_ts<16, 8>(tmem, a_tmem, w);
           mma_commit(&mbar[wg]);
         }
         __syncwarp();
@@ -385,9 +396,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_field_fwd(const TcParams p) 
       mbar_wait(&mbar[wg], mph);
       mph ^= 1u;
       tc_fence_after();
-      if (i < L) {
-        epi_chunk<false>(tlane, act, nullptr, row, 0);
-        epi_chunk<false>(tlane + 64u, act, nullptr, row, 1);
+      if (i < L) {  // accumulator -> ReLU -> bf16 -> the next layer's A operand, all inside tensor memory
+        uint32_t packed[64];
+#pragma unroll
+        for (uint32_t h = 0; h < 2; h++) {
+          uint32_t v[64];
+          tmem_ld64(tlane + h * 64u, v);
+#pragma unroll
+          for (uint32_t j = 0; j < 32; j++)
+            packed[h * 32u + j] = pack_bf16_relu(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        }
+        tmem_st64(a_lane, packed);
         worker_sync();
       } else {
         float v[16];
@@ -998,7 +1017,7 @@ static void fill_common(TcParams& p, const snerf_field_desc* f, const PackedNet&
 }
 
 static uint32_t grid_for(uint32_t M) { return min(div_up(M, kTile), min((uint32_t)sm_count(), kMaxGrid)); }
-static size_t fwd_smem(const PackedNet& n) { return n.total_bytes + (size_t)kFwdGroups * kActBytes + 1024; }
+static size_t fwd_smem(const PackedNet& n) { return n.total_bytes + 1024; }  // the resident weight image, nothing else
 // ring depth of the backward's weight stream: whatever the 227 KiB of shared memory leave after the activations
 static size_t bwd_fixed_smem(const PackedNet& n, int net) {  // activations + gradient tile (+ the sigma net's d-enc tile)
   (void)net;

@@ -153,6 +153,30 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
       : "memory");
 }
 
+// registers -> TMEM: thread (lane l) writes its row's N consecutive 32-bit columns (STTM); waits for completion
+#define SNERF_R4(r, i) "r"(r[i]), "r"(r[i + 1]), "r"(r[i + 2]), "r"(r[i + 3])
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), SNERF_R4(r, 0), SNERF_R4(r, 4), SNERF_R4(r, 8), SNERF_R4(r, 12)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st64(uint32_t taddr, const uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, "
+      "%33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, "
+      "%49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63, %64};"
+      ::"r"(taddr), SNERF_R4(r, 0), SNERF_R4(r, 4), SNERF_R4(r, 8), SNERF_R4(r, 12), SNERF_R4(r, 16), SNERF_R4(r, 20),
+      SNERF_R4(r, 24), SNERF_R4(r, 28), SNERF_R4(r, 32), SNERF_R4(r, 36), SNERF_R4(r, 40), SNERF_R4(r, 44), SNERF_R4(r, 48),
+      SNERF_R4(r, 52), SNERF_R4(r, 56), SNERF_R4(r, 60)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+#undef SNERF_R4
+
 // named barrier over `nthreads` threads (one warpgroup of a multi-worker CTA); id 0 is __syncthreads'
 __device__ __forceinline__ void bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -193,6 +217,16 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows on the 128 lanes, K along the columns, two bf16 per
+// 32-bit column: 8 columns per K = 16 step) comes from tensor memory, only B is read from shared memory
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete

@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(128) k_tc_selftest(const float* __restrict__ A
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  const bool a_tmem = a_mn == 2;  // A operand staged in tensor memory (K along the columns) instead of shared memory
+  if (a_tmem) a_mn = 0;
   const uint32_t a_rows = a_mn ? K : 128u, b_rows = b_mn ? K : N;
   for (uint32_t i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
   __syncthreads();
@@ -32,18 +34,32 @@ __global__ void __launch_bounds__(128) k_tc_selftest(const float* __restrict__ A
     tc::mbar_init(&bar, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 0) tc::tmem_alloc<128>(&tmem_base_s);
+  if (warp == 0) tc::tmem_alloc<256>(&tmem_base_s);
   tc::fence_proxy_async();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  if (a_tmem) {  // thread = row: its K bf16 values, two per 32-bit column, into columns 128.. of its lane
+    for (uint32_t k0 = 0; k0 < K; k0 += 32) {
+      uint32_t r[16];
+      for (uint32_t j = 0; j < 16; j++) {
+        const uint32_t k = k0 + 2 * j;
+        r[j] = k + 1 < K + 1 && k < K ? tc::pack_bf16(A[tid * K + k], A[tid * K + k + 1]) : 0u;
+      }
+      tc::tmem_st16(tmem + ((warp * 32u) << 16) + 128u + k0 / 2u, r);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+  }
   if (tid == 0) {
     const uint32_t idesc = tc::make_idesc(128, N, a_mn != 0, b_mn != 0);
     for (uint32_t s = 0; s < K / 16; s++) {
       const uint64_t ad = a_mn ? tc::desc_mnmajor(tc::smem_u32(sA), a_rows, s) : tc::desc_kmajor(tc::smem_u32(sA), a_rows, s);
       const uint64_t bd = b_mn ? tc::desc_mnmajor(tc::smem_u32(sB), b_rows, s) : tc::desc_kmajor(tc::smem_u32(sB), b_rows, s);
-      tc::mma_ss(tmem, ad, bd, idesc, s > 0);
+      if (a_tmem) tc::mma_ts(tmem, tmem + 128u + s * 8u, bd, idesc, s > 0);
+      else tc::mma_ss(tmem, ad, bd, idesc, s > 0);
     }
     tc::mma_commit(&bar);
   }
@@ -57,7 +73,7 @@ __global__ void __launch_bounds__(128) k_tc_selftest(const float* __restrict__ A
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<128>(tmem);
+  if (warp == 0) tc::tmem_dealloc<256>(tmem);
 }
 
 }  // namespace snerf

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 CASES = [(N, K, a, b) for (N, K), (a, b) in itertools.product(
     [(128, 128), (128, 64), (128, 32), (128, 16), (64, 128), (32, 128), (16, 128), (16, 16), (32, 32)],
-    [(0, 0), (1, 0), (0, 1), (1, 1)])]
+    [(0, 0), (1, 0), (0, 1), (1, 1), (2, 0), (2, 1)])]  # a_mn == 2: A operand staged in tensor memory
 
 
 @pytest.mark.parametrize("N,K,a_mn,b_mn", CASES)
