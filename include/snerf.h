@@ -269,6 +269,17 @@ int snerf_field_backward(const snerf_field_desc* f, const float* xyzs, const flo
 int snerf_get_rays(const float* poses, float fx, float fy, float cx, float cy, uint32_t W, const int64_t* inds,
                    uint32_t B, uint32_t N, int inds_per_batch, float* rays_o, float* rays_d, snerf_stream_t stream);
 
+/* Wire format of the rendered latent towards the diffusion side (train.py:72-82, consumed by
+ * stable_diffusion/network.py:191-199): out [B, C+3, N] with N = E*E.  The first C*N floats of a block are the
+ * [N, C] latent reinterpreted flat as [C, E, E] (the reference's .view -- no transpose) times scale plus shift
+ * (2, -1 for the rendered target latent, :75; 1, 0 for the VAE latent of the reference view, :81); the last 3*N are
+ * rays_d [B,N,3] transposed to [3, N].  rays_d may be NULL (only the latent part is written, the layout of the block
+ * is unchanged).  The backward returns grad_image [B,N,C] = scale * grad_out's latent part. */
+int snerf_pack_sd_condition(const float* image, const float* rays_d, uint32_t B, uint32_t N, uint32_t C, float scale,
+                            float shift, float* out, snerf_stream_t stream);
+int snerf_pack_sd_condition_backward(const float* grad_out, uint32_t B, uint32_t N, uint32_t C, float scale,
+                                     float* grad_image, snerf_stream_t stream);
+
 /* One Adam (decoupled_weight_decay = 0, test_nerf.py:52) or AdamW (= 1, train.py:183) step of torch.optim semantics
  * (no amsgrad) over a flat fp32 parameter tensor: n a multiple of 4, pointers 16-byte aligned; step counts from 1.
  * zero_grad != 0 leaves grads zeroed (the next step's accumulate-into gradients need no memset). */

@@ -311,3 +311,13 @@ def l1_loss_backward(image, weights_sum, target, bg, grad_scale, depth=None, nea
     if depth is not None:
         dn = (np.maximum(np.asarray(depth, np.float32) - nears, 0) / (fars - nears)).astype(np.float32)
     return loss, g_img, g_ws, pred.astype(np.float32), dn
+
+
+def pack_sd_condition(image, rays_d, scale=2.0, shift=-1.0):
+    """Numpy restatement of train.py:72-82: the rendered latent [B,N,C] (N = E*E) is VIEWED as [B,C,E,E] (a flat
+    reinterpretation, no transpose), renormalised to [-1,1] (:75; scale 1, shift 0 gives the reference-view block of :81), and concatenated on the channel axis with the ray
+    directions permuted to [B,3,E,E] (:76,80).  Returns [B, C+3, N] (the flat form of [B, C+3, E, E])."""
+    image, rays_d = np.asarray(image, np.float32), np.asarray(rays_d, np.float32)
+    B, N, C = image.shape
+    latent = image.reshape(B, C, N) * np.float32(scale) + np.float32(shift)
+    return np.concatenate([latent, rays_d.transpose(0, 2, 1)], axis=1).astype(np.float32)

@@ -85,6 +85,8 @@ SIGNATURES = {
     "snerf_field_backward": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_size_t,
                                      _P, c_size_t, _S]),
     "snerf_get_rays": (c_int, [_P, _F, _F, _F, _F, _U, _P, _U, _U, c_int, _P, _P, _S]),
+    "snerf_pack_sd_condition": (c_int, [_P, _P, _U, _U, _U, _F, _F, _P, _S]),
+    "snerf_pack_sd_condition_backward": (c_int, [_P, _U, _U, _U, _F, _P, _S]),
     "snerf_adam_step": (c_int, [_P, _P, _P, _P, _U, _F, _F, _F, _F, _F, c_int, _U, c_int, _S]),
     "snerf_field_backward_ex": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_size_t,
                                         _P, c_size_t, _P, _S]),

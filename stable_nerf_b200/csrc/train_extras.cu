@@ -4,7 +4,10 @@
 //     translation), fused with near/far so that the [N,3] pair is written once;
 //   * the Adam / AdamW update of the 12.3 M fp32 parameters (train.py:183 AdamW, test_nerf.py:52 Adam
 //     betas=(0.9, 0.99) eps=1e-15): one pass of 16 B read + 12 B written per parameter, optionally leaving the
-//     gradient zeroed for the next step (which spares the separate 49 MB memset).
+//     gradient zeroed for the next step (which spares the separate 49 MB memset);
+//   * the wire format the rendered latent leaves the path in (train.py:72-82): per batch item a [C+3, E, E] block for the
+//     IP-adapter projection -- the [N, C] latent REINTERPRETED as [C, E, E] (the reference's .view, no transpose),
+//     renormalised to [-1, 1], followed by the ray directions transposed to [3, E, E].
 #include "common.cuh"
 
 namespace snerf {
@@ -56,6 +59,32 @@ __global__ void __launch_bounds__(256) k_adam_step(float4* __restrict__ p, float
   }
 }
 
+// out[b, 0:C*N] = image[b, 0:N*C] * scale + shift (flat; 2, -1 at train.py:75);  out[b, (C+k)*N + i] = rays_d[b, i, k] (train.py:76)
+__global__ void __launch_bounds__(256) k_pack_sd_condition(const float* __restrict__ image, const float* __restrict__ rays_d,
+                                                           uint32_t N, uint32_t C, float scale, float shift,
+                                                           float* __restrict__ out) {
+  const uint32_t b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* im = image + (size_t)b * N * C;
+  float* ob = out + (size_t)b * N * (C + 3);
+  for (uint32_t c = 0; c < C; c++) ob[(size_t)c * N + i] = fadd(fmul(im[(size_t)c * N + i], scale), shift);
+  if (rays_d) {
+    const float* d = rays_d + ((size_t)b * N + i) * 3;
+#pragma unroll
+    for (uint32_t k = 0; k < 3; k++) ob[(size_t)(C + k) * N + i] = d[k];
+  }
+}
+
+// grad_image[b, flat] = scale * grad_out[b, flat] over the first C*N entries of each block (directions carry no gradient)
+__global__ void __launch_bounds__(256) k_pack_sd_condition_bwd(const float* __restrict__ grad_out, uint32_t N, uint32_t C,
+                                                               float scale, float* __restrict__ grad_image) {
+  const uint32_t b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* g = grad_out + (size_t)b * N * (C + 3);
+  float* gi = grad_image + (size_t)b * N * C;
+  for (uint32_t c = 0; c < C; c++) gi[(size_t)c * N + i] = fmul(g[(size_t)c * N + i], scale);
+}
+
 }  // namespace snerf
 
 using namespace snerf;
@@ -69,6 +98,22 @@ int snerf_get_rays(const float* poses, float fx, float fy, float cx, float cy, u
   if ((uint64_t)B * N > 0xffffffffull) return SNERF_E_BADARG;
   k_get_rays<<<div_up(B * N, 256), 256, 0, (cudaStream_t)stream>>>(poses, fx, fy, cx, cy, W, inds, B, N, inds_per_batch,
                                                                   rays_o, rays_d);
+  return finish_launch();
+}
+
+int snerf_pack_sd_condition(const float* image, const float* rays_d, uint32_t B, uint32_t N, uint32_t C, float scale,
+                            float shift, float* out, snerf_stream_t stream) {
+  if (B == 0 || N == 0) return SNERF_OK;
+  if (!image || !out || C == 0 || C > SNERF_MAX_CHANNELS || B > 65535u) return SNERF_E_BADARG;
+  k_pack_sd_condition<<<dim3(div_up(N, 256), B), 256, 0, (cudaStream_t)stream>>>(image, rays_d, N, C, scale, shift, out);
+  return finish_launch();
+}
+
+int snerf_pack_sd_condition_backward(const float* grad_out, uint32_t B, uint32_t N, uint32_t C, float scale,
+                                     float* grad_image, snerf_stream_t stream) {
+  if (B == 0 || N == 0) return SNERF_OK;
+  if (!grad_out || !grad_image || C == 0 || C > SNERF_MAX_CHANNELS || B > 65535u) return SNERF_E_BADARG;
+  k_pack_sd_condition_bwd<<<dim3(div_up(N, 256), B), 256, 0, (cudaStream_t)stream>>>(grad_out, N, C, scale, grad_image);
   return finish_launch();
 }
 
