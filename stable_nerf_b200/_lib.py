@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsnerf_b200.so")
 
 SNERF_MAX_LEVELS = 16
+SNERF_MAX_CHANNELS = 4
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 

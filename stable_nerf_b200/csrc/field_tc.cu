@@ -835,25 +835,41 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
 #pragma unroll
         for (int k = 0; k < 32; k++) acc_first[k] += v[k];
       }
-      {
-        float v[16];
-        tmem_ld16(tlane + 32u + hc * 16u, v);  // input-gradient columns 16hc .. 16hc+15 of row `row`
-        if (m < p.M) {
-          if (NET == 1) {
-            if (hc == 1) {  // columns 16..30 = d loss / d geo
-              float4* gg = reinterpret_cast<float4*>(p.g_geo + (size_t)m * 16);
-              gg[0] = make_float4(v[0], v[1], v[2], v[3]);
-              gg[1] = make_float4(v[4], v[5], v[6], v[7]);
-              gg[2] = make_float4(v[8], v[9], v[10], v[11]);
-              gg[3] = make_float4(v[12], v[13], v[14], 0.f);
-            }
-          } else {  // d loss / d encoding, columns 16hc .. 16hc+15: scattered into the table by k_hashgrid_bwd
-            float4* ge = reinterpret_cast<float4*>(p.d_enc + (size_t)m * 32 + hc * 16u);
-            ge[0] = make_float4(v[0], v[1], v[2], v[3]);
-            ge[1] = make_float4(v[4], v[5], v[6], v[7]);
-            ge[2] = make_float4(v[8], v[9], v[10], v[11]);
-            ge[3] = make_float4(v[12], v[13], v[14], v[15]);
+      if (NET == 1) {
+        if (hc == 1) {  // input-gradient columns 16..30 of row `row` = d loss / d geo; staged like d_enc below (64 B rows)
+          float v[16];
+          tmem_ld16(tlane + 32u + 16u, v);
+          v[15] = 0.f;
+          uint8_t* stg = a_hid(L);
+#pragma unroll
+          for (uint32_t c = 0; c < 4; c++)
+            *reinterpret_cast<float4*>(stg + row * 64u + ((c ^ ((row >> 1) & 3u)) << 4)) =
+                make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          bar_sync(3u, kBwdComputeThreads / 2);
+          float4* gg = reinterpret_cast<float4*>(p.g_geo + (size_t)t * kTile * 16);
+#pragma unroll
+          for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t id = k * (kBwdComputeThreads / 2) + (tid & 127u), r = id >> 2, j = id & 3u;
+            if (t * kTile + r < p.M) gg[id] = *reinterpret_cast<const float4*>(stg + r * 64u + ((j ^ ((r >> 1) & 3u)) << 4));
           }
+        }
+      } else {
+        // d loss / d encoding (scattered into the table by k_hashgrid_bwd): thread (row, hc) holds columns 16hc..16hc+15.
+        // Stored from there, a warp's store touches 32 lines of 128 B; staged through the (dead) A_L buffer, the tile
+        // leaves as 16 KiB of contiguous full lines.  16-byte chunks are XOR-swizzled by row: no bank conflicts either way.
+        float v[16];
+        tmem_ld16(tlane + 32u + hc * 16u, v);
+        uint8_t* stg = a_hid(L);
+#pragma unroll
+        for (uint32_t c = 0; c < 4; c++)
+          *reinterpret_cast<float4*>(stg + row * 128u + (((hc * 4u + c) ^ (row & 7u)) << 4)) =
+              make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        bar_sync(3u, kBwdComputeThreads);
+        float4* ge = reinterpret_cast<float4*>(p.d_enc + (size_t)t * kTile * 32);
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+          const uint32_t id = k * kBwdComputeThreads + tid, r = id >> 3, j = id & 7u;
+          if (t * kTile + r < p.M) ge[id] = *reinterpret_cast<const float4*>(stg + r * 128u + ((j ^ (r & 7u)) << 4));
         }
       }
       mark(14);
