@@ -109,7 +109,8 @@ struct TcParams {
   // backward
   const float* grad_sigmas;
   const float* grad_rgbs;
-  float* g_geo;          // [M,16] fp32: d loss / d geo (cols 0..14) written by the colour bwd, read by the sigma bwd
+  __nv_bfloat16* g_geo;  // [M,16] bf16: col 0 = 0, cols 1..15 = d loss / d geo 0..14 -- the sigma net's output-gradient
+                         // row without its sigma entry; written by the colour bwd, read by the sigma bwd
   float* grad_w;         // fp32 gradient of this net's flat matrices (accumulated by k_reduce_partials)
   float* dw_part;        // [gridDim.x][n_params] per-CTA partial weight gradients (plain stores, no atomics)
   uint32_t n_params;     // parameters of this net
@@ -721,29 +722,37 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
     // made of, loaded into registers one tile ahead of their use; nothing here depends on a loaded value, so the loads
     // stay in flight under the running phase and are first touched at the start of the next tile.
     uint4 in_regs[2];
-    float4 ug[4];   // NET 0: d loss / d geo (colour backward);   NET 1: [0] = sigmoid outputs y
+    uint4 ug[2];    // NET 0: the row of g_geo (bf16: [0, d loss / d geo 0..14], from the colour backward)
+    float4 uy;      // NET 1: sigmoid outputs y
     float us[4];    // NET 0: [0] = d loss / d sigma;   NET 1: d loss / d rgb
     uint32_t sraw_bits = 0;  // NET 0: sigma_raw as stored by the forward (bf16 bits)
     auto fetch_tile = [&](uint32_t t) {
       const uint32_t mm = t * kTile + row;
       if (NET == 0 && p.enc) {
-        if (hc == 0) fetch_input<NET, 0, 2, true>(p, mm, in_regs);
-        else fetch_input<NET, 2, 2, true>(p, mm, in_regs);
+        // the saved encoding is copied as is: 16-byte chunk id of the tile's 8 KiB (row id/4, group id%4), so that a
+        // warp's load covers four full lines instead of half-rows of sixteen
+#pragma unroll
+        for (uint32_t k = 0; k < 2; k++) {
+          const uint32_t id = k * kBwdComputeThreads + tid, r = t * kTile + (id >> 2);
+          in_regs[k] = r < p.M ? __ldg(reinterpret_cast<const uint4*>(p.enc + (size_t)t * kTile * 32) + id) : make_uint4(0u, 0u, 0u, 0u);
+        }
       } else {
         if (hc == 0) fetch_input<NET, 0, 2, false>(p, mm, in_regs);
         else fetch_input<NET, 2, 2, false>(p, mm, in_regs);
       }
 #pragma unroll
-      for (int k = 0; k < 4; k++) { ug[k] = make_float4(0.f, 0.f, 0.f, 0.f); us[k] = 0.f; }
+      for (int k = 0; k < 4; k++) us[k] = 0.f;
+      ug[0] = ug[1] = make_uint4(0u, 0u, 0u, 0u);
+      uy = make_float4(0.f, 0.f, 0.f, 0.f);
       if (hc == 0 && mm < p.M) {
         if (NET == 0) {
           us[0] = __ldg(p.grad_sigmas + mm);
           sraw_bits = __ldg(reinterpret_cast<const unsigned short*>(p.geo) + (size_t)mm * 16 + 15);
-          const float4* gg = reinterpret_cast<const float4*>(p.g_geo + (size_t)mm * 16);
-#pragma unroll
-          for (int k = 0; k < 4; k++) ug[k] = __ldg(gg + k);
+          const uint4* gg = reinterpret_cast<const uint4*>(p.g_geo + (size_t)mm * 16);
+          ug[0] = __ldg(gg);
+          ug[1] = __ldg(gg + 1);
         } else {
-          ug[0] = __ldg(p.rgb_y + mm);
+          uy = __ldg(p.rgb_y + mm);
 #pragma unroll
           for (int c = 0; c < SNERF_MAX_CHANNELS; c++)
             if ((uint32_t)c < p.C) us[c] = __ldg(p.grad_rgbs + (size_t)mm * p.C + c);
@@ -752,21 +761,19 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
     };
     // gradient of the raw output of this thread's row (16 columns, bf16) from the prefetched pieces
     auto out_grad = [&](uint4 (&og)[2]) {
-      float go[16];
-#pragma unroll
-      for (int k = 0; k < 16; k++) go[k] = 0.f;
-      if (NET == 0) {  // d/d sigma_raw through the ReLU (nerf/network.py:46) + d/d geo from the colour net
-        go[0] = __uint_as_float(sraw_bits << 16) > 0.f ? us[0] : 0.f;
-        go[1] = ug[0].x; go[2] = ug[0].y; go[3] = ug[0].z; go[4] = ug[0].w; go[5] = ug[1].x; go[6] = ug[1].y;
-        go[7] = ug[1].z; go[8] = ug[1].w; go[9] = ug[2].x; go[10] = ug[2].y; go[11] = ug[2].z; go[12] = ug[2].w;
-        go[13] = ug[3].x; go[14] = ug[3].y; go[15] = ug[3].z;
+      if (NET == 0) {  // d/d sigma_raw through the ReLU (nerf/network.py:46) joins the d/d geo row of the colour net
+        const float gs = __uint_as_float(sraw_bits << 16) > 0.f ? us[0] : 0.f;
+        og[0] = ug[0];
+        og[0].x = (ug[0].x & 0xffff0000u) | (pack_bf16(gs, 0.f) & 0xffffu);
+        og[1] = ug[1];
       } else {  // through the sigmoid (nerf/network.py:59): y (1 - y) from the forward's saved outputs
-        const float y[4] = {ug[0].x, ug[0].y, ug[0].z, ug[0].w};
+        const float y[4] = {uy.x, uy.y, uy.z, uy.w};
+        float go[4];
 #pragma unroll
         for (int c = 0; c < SNERF_MAX_CHANNELS; c++) go[c] = us[c] * y[c] * (1.0f - y[c]);
+        og[0] = make_uint4(pack_bf16(go[0], go[1]), pack_bf16(go[2], go[3]), 0u, 0u);
+        og[1] = make_uint4(0u, 0u, 0u, 0u);
       }
-      og[0] = make_uint4(pack_bf16(go[0], go[1]), pack_bf16(go[2], go[3]), pack_bf16(go[4], go[5]), pack_bf16(go[6], go[7]));
-      og[1] = make_uint4(pack_bf16(go[8], go[9]), pack_bf16(go[10], go[11]), pack_bf16(go[12], go[13]), pack_bf16(go[14], go[15]));
     };
     if (blockIdx.x < n_tiles) fetch_tile(blockIdx.x);
 
@@ -774,14 +781,22 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
       const uint32_t m = t * kTile + row;
       mark(0);
       // ---------------- input tile + gradient of the raw output (S), then the forward recompute of a_1 .. a_L
+      if (NET == 0 && p.enc) {
+#pragma unroll
+        for (uint32_t k = 0; k < 2; k++) {
+          const uint32_t id = k * kBwdComputeThreads + tid;
+          st_group(a0, kTile, id >> 2, 0, id & 3u, in_regs[k]);
+        }
+      } else if (hc == 0) {
+        store_input<0, 2>(in_regs, row, a0);
+      } else {
+        store_input<2, 2>(in_regs, row, a0);
+      }
       if (hc == 0) {
         uint4 og[2];
         out_grad(og);
-        store_input<0, 2>(in_regs, row, a0);
         st_group(sbuf, kTile, row, 0, 0, og[0]);
         st_group(sbuf, kTile, row, 0, 1, og[1]);
-      } else {
-        store_input<2, 2>(in_regs, row, a0);
       }
       hand_over();
       mark(1);
@@ -836,21 +851,13 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
         for (int k = 0; k < 32; k++) acc_first[k] += v[k];
       }
       if (NET == 1) {
-        if (hc == 1) {  // input-gradient columns 16..30 of row `row` = d loss / d geo; staged like d_enc below (64 B rows)
+        if (hc == 1) {  // input-gradient columns 16..30 of row `row` = d loss / d geo, stored as the sigma net's bf16 row
           float v[16];
           tmem_ld16(tlane + 32u + 16u, v);
-          v[15] = 0.f;
-          uint8_t* stg = a_hid(L);
-#pragma unroll
-          for (uint32_t c = 0; c < 4; c++)
-            *reinterpret_cast<float4*>(stg + row * 64u + ((c ^ ((row >> 1) & 3u)) << 4)) =
-                make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          bar_sync(3u, kBwdComputeThreads / 2);
-          float4* gg = reinterpret_cast<float4*>(p.g_geo + (size_t)t * kTile * 16);
-#pragma unroll
-          for (uint32_t k = 0; k < 4; k++) {
-            const uint32_t id = k * (kBwdComputeThreads / 2) + (tid & 127u), r = id >> 2, j = id & 3u;
-            if (t * kTile + r < p.M) gg[id] = *reinterpret_cast<const float4*>(stg + r * 64u + ((j ^ ((r >> 1) & 3u)) << 4));
+          if (m < p.M) {
+            uint4* gg = reinterpret_cast<uint4*>(p.g_geo + (size_t)m * 16);
+            gg[0] = make_uint4(pack_bf16(0.f, v[0]), pack_bf16(v[1], v[2]), pack_bf16(v[3], v[4]), pack_bf16(v[5], v[6]));
+            gg[1] = make_uint4(pack_bf16(v[7], v[8]), pack_bf16(v[9], v[10]), pack_bf16(v[11], v[12]), pack_bf16(v[13], v[14]));
           }
         }
       } else {
@@ -943,7 +950,7 @@ struct TcWorkspace {
   __nv_bfloat16* geo;
   __nv_bfloat16* enc;
   float4* rgb_y;
-  float* g_geo;
+  __nv_bfloat16* g_geo;
   float* d_enc;
   float* dw_part;  // per-CTA partial weight gradients of one net at a time (max of the two nets)
 };
@@ -982,7 +989,7 @@ static size_t carve_tc(const snerf_field_desc* f, uint32_t M, int backward, char
   TcWorkspace& o = w ? *w : tmp;
   char* hand = take(field_tc_saved_bytes(f, M));  // used when the caller passes no hand-off buffer
   carve_handoff(f, M, hand, &o);
-  o.g_geo = backward ? (float*)take((size_t)(M ? M : 1) * 16 * sizeof(float)) : nullptr;
+  o.g_geo = backward ? (__nv_bfloat16*)take((size_t)(M ? M : 1) * 16 * sizeof(__nv_bfloat16)) : nullptr;
   o.d_enc = backward ? (float*)take((size_t)(M ? M : 1) * 32 * sizeof(float)) : nullptr;
   o.dw_part = backward ? (float*)take((size_t)kMaxGrid * std::max(sigma_shape(f).n_params, color_shape(f).n_params) * sizeof(float)) : nullptr;
   return off;
@@ -1144,7 +1151,7 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   TcParams p;
   if (!saved) {
     fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
-    p.sigmas = w.g_geo;  // scratch: any M floats, overwritten by step 2
+    p.sigmas = reinterpret_cast<float*>(w.g_geo);  // scratch: any M floats, overwritten by step 2
     p.geo = w.geo;
     if (int e = launch_hashgrid_fwd_bf16(&f->grid, xyzs, f->bound, table, M, w.enc, s)) return e;
     p.enc = w.enc;
