@@ -397,6 +397,10 @@ def run_gpu_arm(args):
                                "channel_dim 3, fwd + L1 + bwd",
                    "rays_per_gpu": RAYS_PER_GPU, "samples_per_step_per_gpu": n_samples, "mlp_precision": args.precision,
                    "cuda_graph": ts.graph is not None, "parallelism": f"ray-sharded dp{world}",
+                   "gradient_exchange": {"none": "none (one rank)", "p2p": "one kernel per rank over NVLink peer memory, inside "
+                                         "the step's CUDA graph (csrc/p2p_reduce.cu)",
+                                         "nccl": "NCCL all-reduce after the graph replay"}[ts.exchange_kind]
+                                        + (f" [peer memory unavailable: {ts.exchange_error}]" if ts.exchange_error else ""),
                    "l2": "not flushed between steps: the step streams params 49 MB + grads 49 MB + samples and "
                          "activations (> 126 MB L2 together); the hash table is meant to stay L2-resident across steps"},
         "e2e": {"value": total_rays * args.steps / (e2e_ms * 1e-3), "unit": "rays/s",

@@ -280,6 +280,41 @@ int snerf_pack_sd_condition(const float* image, const float* rays_d, uint32_t B,
 int snerf_pack_sd_condition_backward(const float* grad_out, uint32_t B, uint32_t N, uint32_t C, float scale,
                                      float* grad_image, snerf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Gradient exchange of the ray-sharded step over peer memory
+ *
+ * The reference never synchronises NeRF gradients (train.py:188 unwraps the model from DDP); the contract is the
+ * single-GPU step on the concatenated batch.  Each rank keeps its flat gradients in an arena from snerf_p2p_alloc,
+ * exports it (and a flag block of snerf_p2p_flag_bytes(), zero-initialised by the allocator) as a 64-byte handle,
+ * and opens the other ranks' handles -- one process per GPU, all on one node.  snerf_p2p_allreduce is then ONE kernel
+ * per rank and step: rank r reads slice r of every arena over NVLink, adds the copies in rank order (bit-identical
+ * sums on all ranks) and stores the result into every arena.  The launch carries no per-step argument (the epoch
+ * lives in the flag block), so it can be captured in the step's CUDA graph.  All ranks must launch it the same
+ * number of times; a rank that never arrives is reported through snerf_p2p_status (timeouts != 0) after a bounded
+ * wait instead of hanging the device.
+ * ---------------------------------------------------------------------------------------------- */
+#define SNERF_P2P_MAX_RANKS 16
+#define SNERF_P2P_HANDLE_BYTES 64
+#define SNERF_P2P_CHANNELS 4 /* independent flag sets: calls on different channels may overlap (different streams) */
+typedef struct {
+  float* buf[SNERF_P2P_MAX_RANKS];      /* arena of rank r as mapped in THIS process (own entry: local memory)    */
+  uint32_t* flags[SNERF_P2P_MAX_RANKS]; /* flag block of rank r, likewise                                          */
+} snerf_p2p_peers;
+
+size_t snerf_p2p_flag_bytes(void);
+int snerf_p2p_alloc(size_t bytes, void** ptr);            /* zero-filled device allocation that can be exported     */
+int snerf_p2p_free(void* ptr);
+int snerf_p2p_export(const void* ptr, void* handle64);    /* -> SNERF_P2P_HANDLE_BYTES bytes to send to the peers   */
+int snerf_p2p_open(const void* handle64, void** ptr);     /* map a peer's allocation (not valid in the exporter)    */
+int snerf_p2p_close(void* ptr);
+/* Sums floats [offset_floats, offset_floats + n_floats) of the arenas (both multiples of 4); n_ctas: CTAs of the
+ * kernel (0 = default 64).  Calls on one channel are ordered by their stream; calls that may run concurrently (a
+ * slice exchanged on a side stream while the next one is still being produced) use different channels. */
+int snerf_p2p_allreduce(const snerf_p2p_peers* peers, uint32_t rank, uint32_t world, size_t offset_floats, size_t n_floats,
+                        uint32_t channel, uint32_t n_ctas, snerf_stream_t stream);
+/* Synchronous read of this rank's flag block: completed calls and bounded waits that ran out, per channel. */
+int snerf_p2p_status(const uint32_t* local_flags, uint32_t channel, uint32_t* epoch, uint32_t* timeouts);
+
 /* One Adam (decoupled_weight_decay = 0, test_nerf.py:52) or AdamW (= 1, train.py:183) step of torch.optim semantics
  * (no amsgrad) over a flat fp32 parameter tensor: n a multiple of 4, pointers 16-byte aligned; step counts from 1.
  * zero_grad != 0 leaves grads zeroed (the next step's accumulate-into gradients need no memset). */

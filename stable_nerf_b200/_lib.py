@@ -40,6 +40,16 @@ class FieldDesc(ctypes.Structure):
     ]
 
 
+SNERF_P2P_MAX_RANKS = 16
+SNERF_P2P_HANDLE_BYTES = 64
+SNERF_P2P_CHANNELS = 4
+
+
+class P2PPeers(ctypes.Structure):
+    """snerf_p2p_peers (include/snerf.h): arenas and flag blocks of all ranks as mapped in this process."""
+    _fields_ = [("buf", c_void_p * SNERF_P2P_MAX_RANKS), ("flags", c_void_p * SNERF_P2P_MAX_RANKS)]
+
+
 _P = c_void_p
 _U = c_uint32
 _F = c_float
@@ -98,6 +108,14 @@ SIGNATURES = {
     "snerf_debug_set_dedupe_max_res": (None, [_U]),
     "snerf_tc_probe": (c_int, [_P, c_int, _S]),
     "snerf_debug_phase_buffer": (None, [_P, c_int]),
+    "snerf_p2p_flag_bytes": (c_size_t, []),
+    "snerf_p2p_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "snerf_p2p_free": (c_int, [_P]),
+    "snerf_p2p_export": (c_int, [_P, _P]),
+    "snerf_p2p_open": (c_int, [_P, POINTER(c_void_p)]),
+    "snerf_p2p_close": (c_int, [_P]),
+    "snerf_p2p_allreduce": (c_int, [POINTER(P2PPeers), _U, _U, c_size_t, c_size_t, _U, _U, _S]),
+    "snerf_p2p_status": (c_int, [_P, _U, POINTER(c_uint32), POINTER(c_uint32)]),
     "snerf_trunc_exp_forward": (c_int, [_P, _U, _P, _S]),
     "snerf_trunc_exp_backward": (c_int, [_P, _P, _U, _P, _S]),
 }

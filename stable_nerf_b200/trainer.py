@@ -68,8 +68,8 @@ class TrainStep:
     """
 
     def __init__(self, model, n_rays, max_steps=1024, bg_color=1, T_thresh=1e-4, use_graph=True, world_size=1,
-                 loss_scale=1.0, fused=True, perturb=False, dt_gamma=0, optimizer=None, overlap_allreduce=True,
-                 scatter_groups=2):
+                 loss_scale=1.0, fused=True, perturb=False, dt_gamma=0, optimizer=None, overlap_allreduce=False,
+                 scatter_groups=2, group=None, exchange="auto"):
         self.model, self.n_rays, self.max_steps = model, int(n_rays), int(max_steps)
         self.bg_color, self.T_thresh, self.world_size = bg_color, T_thresh, world_size
         self.loss_scale = loss_scale
@@ -81,10 +81,12 @@ class TrainStep:
         # one that zeroes the gradients inside its step spares the step's own 49 MB memset
         self.optimizer = optimizer
         self._opt_zeroes = bool(getattr(optimizer, "zero_grad_in_step", False))
-        # several ranks: the table scatter-add runs per group of levels OUTSIDE the graph, and each group's slice of the
-        # gradient starts its all-reduce while the next group is still being scattered (trainer._scatter_and_reduce)
+        # NCCL exchange only, opt-in: the table scatter-add runs per group of levels OUTSIDE the graph, and each group's
+        # slice of the gradient starts its all-reduce while the next group is still being scattered
+        # (trainer._scatter_and_reduce).  Off by default: at 2 ranks it measured slower than scatter-then-all-reduce.
         self.overlap_allreduce = bool(overlap_allreduce) and world_size > 1
         self.scatter_groups = int(scatter_groups)
+        self.group = group  # process group of the gradient exchange (None = the default group)
         dev = next(model.parameters()).device
         C = model.channel_dim
         # one allocation [rays_o | rays_d | target] (and a pinned host mirror of it): a step's inputs arrive in ONE H2D copy
@@ -103,6 +105,40 @@ class TrainStep:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
         model.grads_in_place = True  # the field backward accumulates straight into these .grad tensors
+        # Gradient exchange between ranks: "p2p" = one kernel over NVLink peer memory inside the step's graph
+        # (stable_nerf_b200.p2p / csrc/p2p_reduce.cu), "nccl" = NCCL all-reduce after the replay, "auto" = p2p when the
+        # ranks can map each other's memory (one node, CUDA IPC), else nccl.
+        self.exchange, self.exchange_kind, self.exchange_error = None, ("none" if world_size == 1 else "nccl"), None
+        if world_size > 1 and exchange in ("auto", "p2p") and dev.type == "cuda":
+            try:
+                self._setup_p2p(dev)
+            except RuntimeError as e:
+                if exchange == "p2p":
+                    raise
+                self.exchange_error = str(e)
+
+    def _setup_p2p(self, dev):
+        """Move the parameters' .grad into one peer-mapped arena: [colour MLP | sigma MLP | table], 16-byte aligned, so
+        that "everything but the fine levels of the table" is one contiguous range at the front."""
+        from .p2p import P2PExchange
+        m = self.model
+        order = [p for p in (getattr(m, "color_net", None), getattr(m, "sigma_net", None)) if p is not None]
+        order = [mod.params for mod in order if any(mod.params is q for q in self.params)]
+        order += [p for p in self.params if not any(p is q for q in order)]
+        offs, n = {}, 0
+        for p in order:
+            offs[id(p)] = n
+            n += (p.numel() + 3) // 4 * 4
+        ex = P2PExchange(n, dev, group=self.group)
+        for p in order:
+            o = offs[id(p)]
+            p.grad = ex.tensor[o:o + p.numel()].view_as(p)
+        self.exchange, self.exchange_kind, self._ex_off = ex, "p2p", offs
+        # The scatter-add stays inside the field backward and the exchange follows it as one launch over the whole arena.
+        # Exchanging the fine levels' slice on a (high-priority) side stream while the coarse levels are scattered was
+        # measured at 2 ranks and bought nothing (763 vs 768 us/step), like the NCCL variant of the same overlap
+        # (838 us/step against 805 for scatter-then-all-reduce): the two kernels do not run side by side.
+        self.overlap_allreduce = False
 
     def _body(self):
         m = self.model
@@ -115,6 +151,8 @@ class TrainStep:
         loss = (out['image'].view(-1, m.channel_dim) - self.target).abs().mean()  # utils/loss_utils.py:9-10 l1_loss
         (loss * self.loss_scale).backward()
         self.loss.copy_(loss.detach())
+        if self.exchange is not None:
+            self.exchange.all_reduce()
 
     def _fused_buffers(self, M):
         """Every array of the fused step, allocated once per (M): a captured graph replays on fixed addresses."""
@@ -225,6 +263,8 @@ class TrainStep:
                                         P(b["saved"]), b["saved_bytes"], P(b["field_ws"]), b["field_ws_bytes"],
                                         P(b.get("d_enc")), S), "field backward")
         mark("field_bwd")
+        if self.exchange is not None:  # all ranks' gradients summed in place, same stream: part of the captured step
+            self.exchange.all_reduce()
 
     def profile_stages(self, iters=10):
         """Device time of each stage of the fused step (CUDA events on the launch stream, eager launches): returns
@@ -348,11 +388,11 @@ class TrainStep:
             self.graph.replay()
         else:
             self._body()
-        if self.world_size > 1:
+        if self.world_size > 1 and self.exchange is None:
             if self._bufs is not None and self._bufs.get("d_enc") is not None:
                 self._scatter_and_reduce()
             else:
-                allreduce_gradients(self.params, self.world_size)
+                allreduce_gradients(self.params, self.world_size, group=self.group)
         if self.optimizer is not None:
             self.optimizer.step()
         return self.loss
@@ -371,7 +411,7 @@ class TrainStep:
         g = m.fdesc.grid
         nm, F, L = m.sigma_net.n_mlp, g.n_features, g.n_levels
         grad = m.sigma_net.params.grad
-        handles = [dist.all_reduce(m.color_net.params.grad, async_op=True)]
+        handles = [dist.all_reduce(m.color_net.params.grad, group=self.group, async_op=True)]
         n_groups = max(1, min(self.scatter_groups, L))
         bounds = [round(k * L / n_groups) for k in range(n_groups + 1)]
         for k in range(n_groups - 1, -1, -1):
@@ -380,7 +420,7 @@ class TrainStep:
                                                    lb, le, S), "scatter levels")
             lo = 0 if lb == 0 else nm + g.offset[lb] * F
             hi = nm + (g.offset[le] * F if le < L else g.n_entries * F)
-            handles.append(dist.all_reduce(grad[lo:hi], async_op=True))
+            handles.append(dist.all_reduce(grad[lo:hi], group=self.group, async_op=True))
         for h in handles:
             h.wait()
 
@@ -418,11 +458,11 @@ class TrainStep:
             self._graph_bwd.replay()
         else:
             self._body_fused("backward")
-        if self.world_size > 1:
+        if self.world_size > 1 and self.exchange is None:
             if b.get("d_enc") is not None:
                 self._scatter_and_reduce()
             else:
-                allreduce_gradients(self.params, self.world_size)
+                allreduce_gradients(self.params, self.world_size, group=self.group)
         if self.optimizer is not None:
             self.optimizer.step()
         return self.loss
