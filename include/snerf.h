@@ -308,7 +308,7 @@ int snerf_p2p_export(const void* ptr, void* handle64);    /* -> SNERF_P2P_HANDLE
 int snerf_p2p_open(const void* handle64, void** ptr);     /* map a peer's allocation (not valid in the exporter)    */
 int snerf_p2p_close(void* ptr);
 /* Sums floats [offset_floats, offset_floats + n_floats) of the arenas (both multiples of 4); n_ctas: CTAs of the
- * kernel (0 = default 64).  Calls on one channel are ordered by their stream; calls that may run concurrently (a
+ * kernel (0 = default 128).  Calls on one channel are ordered by their stream; calls that may run concurrently (a
  * slice exchanged on a side stream while the next one is still being produced) use different channels. */
 int snerf_p2p_allreduce(const snerf_p2p_peers* peers, uint32_t rank, uint32_t world, size_t offset_floats, size_t n_floats,
                         uint32_t channel, uint32_t n_ctas, snerf_stream_t stream);

@@ -62,46 +62,77 @@ __device__ __forceinline__ void wait_flag(uint32_t* flag, uint32_t epoch, uint32
   }
 }
 
-constexpr uint32_t kP2PThreads = 512, kP2PUnroll = 4;  // measured at 2 ranks, 49 MB: unroll 4 / 64 CTAs 97 us, unroll 8 116 us
+constexpr uint32_t kP2PThreads = 512;
 
+// W > 0: number of ranks known at compile time -- the loads of one element group from ALL ranks are issued before the
+// first add, so a thread has W x U 16-byte loads in flight instead of U (a peer load is a ~2-3 us round trip; with the
+// rank loop rolled up, 8 ranks meant 8 dependent round trips per element group).  W == 0: any number of ranks.
+// Measured at 2 ranks, 49 MB: U = 4 / 64 CTAs 97 us, U = 8 116 us.
+template <int W, int U>
 __global__ void __launch_bounds__(kP2PThreads) k_p2p_allreduce(const P2PParams p) {
   uint32_t* mine = p.flags[p.rank];
   const uint32_t tid = threadIdx.x;
+  const uint32_t world = W > 0 ? (uint32_t)W : p.world;
   const uint32_t epoch = ld_acquire_sys(mine + kEpoch) + 1u;  // advanced by this rank's last CTA at the end of the call
 
   // ---- arrive: this rank's gradients are complete (stream order); wait for everybody's
-  if (blockIdx.x == 0 && tid < p.world) {
+  if (blockIdx.x == 0 && tid < world) {
     __threadfence_system();
     st_release_sys(p.flags[tid] + kArrive + p.rank, epoch);
   }
-  if (tid < p.world) wait_flag(mine + kArrive + tid, epoch, mine + kTimeouts);
+  if (tid < world) wait_flag(mine + kArrive + tid, epoch, mine + kTimeouts);
   __syncthreads();
 
   // ---- reduce this rank's slice over all ranks (fixed order), store the sum everywhere
-  const size_t chunk = (p.n4 + p.world - 1) / p.world;
+  const size_t chunk = (p.n4 + world - 1) / world;
   const size_t lo = min(p.n4, (size_t)p.rank * chunk), hi = min(p.n4, lo + chunk);
   const size_t stride = (size_t)gridDim.x * kP2PThreads;
-  for (size_t base = lo + (size_t)blockIdx.x * kP2PThreads + tid; base < hi; base += stride * kP2PUnroll) {
-    float4 acc[kP2PUnroll];
+  for (size_t base = lo + (size_t)blockIdx.x * kP2PThreads + tid; base < hi; base += stride * U) {
+    float4 acc[U];
+    if (W > 0) {
+      float4 v[W > 0 ? W : 1][U];
 #pragma unroll
-    for (uint32_t u = 0; u < kP2PUnroll; u++) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t r = 0; r < p.world; r++) {
-      float4 v[kP2PUnroll];
+      for (int r = 0; r < W; r++) {
 #pragma unroll
-      for (uint32_t u = 0; u < kP2PUnroll; u++) {
-        const size_t i = base + u * stride;
-        v[u] = i < hi ? ld_data(p.buf[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < U; u++) {
+          const size_t i = base + u * stride;
+          v[r][u] = i < hi ? ld_data(p.buf[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
 #pragma unroll
-      for (uint32_t u = 0; u < kP2PUnroll; u++) {
-        acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
+      for (int u = 0; u < U; u++) {
+        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < W; r++) {
+          acc[u].x += v[r][u].x; acc[u].y += v[r][u].y; acc[u].z += v[r][u].z; acc[u].w += v[r][u].w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; u++) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (uint32_t r = 0; r < world; r++) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t i = base + u * stride;
+          v[u] = i < hi ? ld_data(p.buf[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
+        }
       }
     }
-    for (uint32_t r = 0; r < p.world; r++) {
 #pragma unroll
-      for (uint32_t u = 0; u < kP2PUnroll; u++) {
-        const size_t i = base + u * stride;
-        if (i < hi) p.buf[r][i] = acc[u];
+    for (int u = 0; u < U; u++) {
+      const size_t i = base + u * stride;
+      if (i < hi) {
+        if (W > 0) {
+#pragma unroll
+          for (int r = 0; r < W; r++) p.buf[r][i] = acc[u];
+        } else {
+          for (uint32_t r = 0; r < world; r++) p.buf[r][i] = acc[u];
+        }
       }
     }
   }
@@ -113,7 +144,7 @@ __global__ void __launch_bounds__(kP2PThreads) k_p2p_allreduce(const P2PParams p
   if (tid == 0) last = atomicAdd(mine + kCounter, 1u) == gridDim.x - 1 ? 1u : 0u;
   __syncthreads();
   if (last) {
-    if (tid < p.world) {
+    if (tid < world) {
       __threadfence_system();
       st_release_sys(p.flags[tid] + kDone + p.rank, epoch);
       wait_flag(mine + kDone + tid, epoch, mine + kTimeouts);
@@ -175,8 +206,15 @@ int snerf_p2p_allreduce(const snerf_p2p_peers* peers, uint32_t rank, uint32_t wo
   p.rank = rank;
   p.world = world;
   p.n4 = n_floats / 4;
-  if (n_ctas == 0) n_ctas = 64;
-  k_p2p_allreduce<<<n_ctas, kP2PThreads, 0, (cudaStream_t)stream>>>(p);
+  if (n_ctas == 0) n_ctas = 128;
+  const cudaStream_t s = (cudaStream_t)stream;
+  switch (world) {
+    case 2: k_p2p_allreduce<2, 4><<<n_ctas, kP2PThreads, 0, s>>>(p); break;
+    case 3: k_p2p_allreduce<3, 4><<<n_ctas, kP2PThreads, 0, s>>>(p); break;
+    case 4: k_p2p_allreduce<4, 4><<<n_ctas, kP2PThreads, 0, s>>>(p); break;
+    case 8: k_p2p_allreduce<8, 2><<<n_ctas, kP2PThreads, 0, s>>>(p); break;
+    default: k_p2p_allreduce<0, 4><<<n_ctas, kP2PThreads, 0, s>>>(p); break;
+  }
   return finish_launch();
 }
 

@@ -34,7 +34,7 @@ def status(lib, flags, channel=0):
     return e.value, t.value
 
 
-@pytest.mark.parametrize("world,n", [(2, 4 * 4096), (3, 4 * 1001), (8, 4 * 50000), (4, 4 * 3)])
+@pytest.mark.parametrize("world,n", [(2, 4 * 4096), (3, 4 * 1001), (8, 4 * 50000), (4, 4 * 3), (5, 4 * 7777)])
 def test_allreduce_is_the_rank_ordered_sum_on_every_rank(world, n, built_lib, cuda):
     arenas, flags, peers = make_ranks(world, n, cuda, seed=world * 7 + n)
     streams = [torch.cuda.Stream() for _ in range(world)]
