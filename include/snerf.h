@@ -281,6 +281,33 @@ int snerf_pack_sd_condition_backward(const float* grad_out, uint32_t B, uint32_t
                                      float* grad_image, snerf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * The inference loop of NeRFRenderer.run_cuda as one call (nerf/renderer.py:116-166)
+ *
+ * rays_alive = arange(N), rays_t = nears; while step < max_steps and rays are left:
+ *   n_step = max(min(N // n_alive, 8), min_n_step, 1)                                   (:130; min_n_step 1 = reference)
+ *   march_rays -> field forward (sigma * density_scale) -> composite_rays -> compaction -> n_alive read back (:158)
+ * Same kernels and the same schedule as calling the five entry points from the host language, iteration for
+ * iteration; buffers come from `workspace` (sized for the largest iteration), weights_sum/depth/image [N],[N],[N,C]
+ * are zero-filled here.  noises [N] (may be NULL) perturbs the first iteration only (:135).  host_count: one pinned
+ * int32 for the per-iteration read (NULL = a pageable local).  This entry point synchronises `stream` once per
+ * iteration, as the reference's loop does; background blend and depth normalisation (:164-167) stay with the caller.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t iterations;
+  uint32_t reserved;
+  uint64_t rows;    /* network-evaluated rows including the padding to 128 */
+  uint64_t samples; /* n_alive * n_step summed over the iterations          */
+} snerf_render_stats;
+
+size_t snerf_render_rays_workspace_bytes(const snerf_field_desc* f, uint32_t N, uint32_t min_n_step, int precision);
+int snerf_render_rays(const snerf_field_desc* f, const float* rays_o, const float* rays_d, uint32_t N, const uint8_t* grid,
+                      uint32_t C, uint32_t H, float bound, float dt_gamma, uint32_t max_steps, const float* nears,
+                      const float* fars, const float* noises, const float* table, const float* w_sigma,
+                      const float* w_color, int precision, float density_scale, float T_thresh, uint32_t min_n_step,
+                      float* weights_sum, float* depth, float* image, int32_t* host_count, snerf_render_stats* stats,
+                      void* workspace, size_t workspace_bytes, snerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Gradient exchange of the ray-sharded step over peer memory
  *
  * The reference never synchronises NeRF gradients (train.py:188 unwraps the model from DDP); the contract is the

@@ -50,6 +50,11 @@ class P2PPeers(ctypes.Structure):
     _fields_ = [("buf", c_void_p * SNERF_P2P_MAX_RANKS), ("flags", c_void_p * SNERF_P2P_MAX_RANKS)]
 
 
+class RenderStats(ctypes.Structure):
+    """snerf_render_stats (include/snerf.h)."""
+    _fields_ = [("iterations", c_uint32), ("reserved", c_uint32), ("rows", c_uint64), ("samples", c_uint64)]
+
+
 _P = c_void_p
 _U = c_uint32
 _F = c_float
@@ -108,6 +113,9 @@ SIGNATURES = {
     "snerf_debug_set_dedupe_max_res": (None, [_U]),
     "snerf_tc_probe": (c_int, [_P, c_int, _S]),
     "snerf_debug_phase_buffer": (None, [_P, c_int]),
+    "snerf_render_rays_workspace_bytes": (c_size_t, [POINTER(FieldDesc), _U, _U, c_int]),
+    "snerf_render_rays": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _U, _U, _F, _F, _U, _P, _P, _P, _P, _P, _P, c_int, _F,
+                                  _F, _U, _P, _P, _P, _P, POINTER(RenderStats), _P, c_size_t, _S]),
     "snerf_p2p_flag_bytes": (c_size_t, []),
     "snerf_p2p_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "snerf_p2p_free": (c_int, [_P]),

@@ -17,13 +17,14 @@ Differences that do not change results:
   schedule moves sample positions by an ulp: images agree to ~1e-6, not bit for bit -- hence opt-in;
 * the module does not force ``.cuda()`` in the constructor (nerf/renderer.py:30); buffers move with ``.to(device)``.
 """
+import ctypes
 import math
 
 import numpy as np
 import torch
 import torch.nn as nn
 
-from . import raymarching
+from . import _lib, raymarching
 
 
 class NeRFRenderer(nn.Module):
@@ -38,6 +39,8 @@ class NeRFRenderer(nn.Module):
         self.density_thresh = density_thresh
         self.bg_radius = bg_radius
         self.min_n_step = 1  # inference: lower bound of the samples marched per alive ray and iteration (1 = reference)
+        self.native_loop = True  # inference loop issued by the library (snerf_render_rays) when the field is the fused one
+        self._host_count = None
 
         aabb = torch.tensor([-bound, -bound, -bound, bound, bound, bound], dtype=torch.float32)
         self.register_buffer('aabb_train', aabb)
@@ -77,6 +80,39 @@ class NeRFRenderer(nn.Module):
         depth = torch.clamp(depth - nears, min=0) / (fars - nears)
         return image.view(*prefix, self.channel_dim), depth.view(*prefix)
 
+    @torch.no_grad()
+    def _render_native(self, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh):
+        """The inference loop below as ONE library call (``snerf_render_rays``, csrc/render_loop.cu): the same kernels and
+        the reference's schedule iteration for iteration, with the launches and the per-iteration count read issued from
+        native code instead of through ~15 Python wrapper calls per iteration.  Needs the fused field (a subclass that
+        overrides ``forward`` sets ``native_loop = False`` and gets the generic loop)."""
+        from .field import _precision_code
+        lib = _lib.load()
+        P = _lib.ptr
+        dev = rays_o.device
+        N = rays_o.shape[0]
+        prec = _precision_code(self.precision)
+        weights_sum = torch.empty(N, dtype=torch.float32, device=dev)
+        depth = torch.empty(N, dtype=torch.float32, device=dev)
+        image = torch.empty(N, self.channel_dim, dtype=torch.float32, device=dev)
+        noises = torch.rand(N, dtype=torch.float32, device=dev) if perturb else None
+        mns = max(int(self.min_n_step), 1)
+        nbytes = lib.snerf_render_rays_workspace_bytes(self.fdesc, N, mns, prec)
+        ws = _lib.workspace.get("render_loop", nbytes, dev)
+        if self._host_count is None:
+            self._host_count = torch.zeros(1, dtype=torch.int32).pin_memory()
+        st = _lib.RenderStats()
+        sp = self.sigma_net.params.detach()
+        nm = self.sigma_net.n_mlp
+        _lib.check(lib.snerf_render_rays(
+            self.fdesc, P(rays_o), P(rays_d), N, P(self.density_bitfield), int(self.cascade), int(self.grid_size),
+            float(self.bound), float(dt_gamma), int(max_steps), P(nears), P(fars), P(noises), P(sp[nm:]), P(sp[:nm]),
+            P(self.color_net.params.detach()), prec, float(self.density_scale), float(T_thresh), mns, P(weights_sum),
+            P(depth), P(image), ctypes.c_void_p(self._host_count.data_ptr()), ctypes.byref(st), P(ws), nbytes, _lib.stream()),
+            "render_rays")
+        self.last_render_stats = {"iterations": int(st.iterations), "rows": int(st.rows), "samples": int(st.samples)}
+        return weights_sum, depth, image
+
     def run_cuda(self, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False, max_steps=1024,
                  T_thresh=1e-4, **kwargs):
         """rays_o, rays_d [B,N,3] -> {'image' [B,N,C], 'depth' [B,N], 'weights_sum' [B*N] (training only)}."""
@@ -109,6 +145,13 @@ class NeRFRenderer(nn.Module):
                 sigmas.to(torch.float32), rgbs.to(torch.float32), deltas, rays, T_thresh, self.channel_dim)
             results['weights_sum'] = weights_sum
         else:
+            if self.native_loop and hasattr(self, "fdesc") and N > 0:
+                weights_sum, depth, image = self._render_native(rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps,
+                                                                T_thresh)
+                image, depth = self._finish(image, depth, weights_sum, nears, fars, bg_color, prefix)
+                results['depth'] = depth
+                results['image'] = image
+                return results
             weights_sum = torch.zeros(N, dtype=torch.float32, device=device)
             depth = torch.zeros(N, dtype=torch.float32, device=device)
             image = torch.zeros(N, self.channel_dim, dtype=torch.float32, device=device)

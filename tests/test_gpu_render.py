@@ -248,6 +248,37 @@ def test_inference_schedule_changes_the_image_by_rounding_only(built_lib, cuda):
         assert rel_err(outs[k][0], outs[1][0]) <= 1e-5 and rel_err(outs[k][1], outs[1][1]) <= 1e-5
 
 
+@pytest.mark.parametrize("precision,channels,min_n_step,density_scale", [("fp32", 3, 1, 1.0), ("bf16", 3, 1, 1.0),
+                                                                          ("bf16", 4, 4, 0.5), ("fp32", 1, 8, 2.0)])
+def test_native_inference_loop_equals_the_wrapper_loop(precision, channels, min_n_step, density_scale, built_lib, cuda):
+    """snerf_render_rays (the whole eval loop of nerf/renderer.py:116-166 issued by the library) against the same loop
+    spelled with the reference's operator calls (march_rays / forward / composite_rays / compaction) in Python: same
+    kernels, same schedule -> identical bits, identical iteration / row / sample counts."""
+    from stable_nerf_b200 import NeRFNetwork, synthetic as syn
+    model = NeRFNetwork(precision=precision, channel_dim=channels, density_scale=density_scale).to(cuda)
+    with torch.no_grad():
+        model.sigma_net.params[model.sigma_net.n_mlp:] *= 1e4
+    model.density_bitfield.copy_(torch.from_numpy(syn.pack_bitfield(syn.occupancy_grid(lego_like=True))))
+    model.eval()
+    model.min_n_step = min_n_step
+    ro, rd = syn.train_batch(2500, 100, 100, 138.0, n_views=2, seed=5)
+    o, d = torch.from_numpy(ro).to(cuda)[None], torch.from_numpy(rd).to(cuda)[None]
+    outs = {}
+    with torch.no_grad():
+        for native in (True, False, True):
+            model.native_loop = native
+            r = model.render(o, d, bg_color=1, max_steps=256)
+            outs[native] = (r["image"].clone(), r["depth"].clone(), dict(model.last_render_stats))
+    assert outs[True][2] == outs[False][2] and outs[True][2]["iterations"] > 3
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
+    assert outs[True][0].shape == (1, 2500, channels) and float(outs[True][0].std()) > 0
+    # nothing alive: every ray misses the box
+    far_o = o + 100.0
+    model.native_loop = True
+    r = model.render(far_o, d, bg_color=1, max_steps=64)
+    assert model.last_render_stats["iterations"] <= 1 and torch.equal(r["image"], torch.ones_like(r["image"]))
+
+
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_split_step_with_external_image_gradient(use_graph, built_lib, cuda):
     """TrainStep.forward() / backward(grad_image): the call pattern of train.py:61-99, where the rendered latent image
