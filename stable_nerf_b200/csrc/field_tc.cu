@@ -103,7 +103,6 @@ struct TcParams {
   float* geo_f32;        // optional [M,15] fp32 (density())
   __nv_bfloat16* geo;    // [M,16] bf16: (geo0..geo14, sigma_raw) written by the sigma net, read by the colour net
   __nv_bfloat16* enc;    // [M,32] bf16 hash-grid features (k_hashgrid_fwd): input of the sigma net, forward and backward
-  int enc_ready;         // forward: enc already holds the features (otherwise the kernel gathers them itself)
   float4* rgb_y;         // [M] colour net outputs after the sigmoid (padded to 4): written by the colour forward,
                          // read by its backward instead of recomputing the output layer
   // backward
@@ -1105,7 +1104,6 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
     if (int e = launch_hashgrid_fwd_bf16(&f->grid, xyzs, f->bound, table, M, w.enc, s)) return e;
   }
   p.enc = w.enc;
-  p.enc_ready = 1;
   p.geo_f32 = geo_feat;
   if (st & kStFwdSigma) {
     if (int e = set_smem(k_field_fwd<0>, fwd_smem(ps))) return e;
@@ -1155,8 +1153,7 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
     p.geo = w.geo;
     if (int e = launch_hashgrid_fwd_bf16(&f->grid, xyzs, f->bound, table, M, w.enc, s)) return e;
     p.enc = w.enc;
-    p.enc_ready = 1;
-    if (int e = set_smem(k_field_fwd<0>, fwd_smem(ps))) return e;
+      if (int e = set_smem(k_field_fwd<0>, fwd_smem(ps))) return e;
     k_field_fwd<0><<<grid_for(M), kFwdThreads, fwd_smem(ps), s>>>(p);
     // ... and the colour net's, for its post-sigmoid outputs (the rgb scratch is the not-yet-used d_enc buffer)
     fill_common(p, f, pc, M, xyzs, dirs, table, w.wimg_color);

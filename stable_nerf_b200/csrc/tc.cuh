@@ -162,16 +162,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), SNERF_R4(r, 0), SNERF_R4(r, 4), SNERF_R4(r, 8), SNERF_R4(r, 12), SNERF_R4(r, 16), SNERF_R4(r, 20),
-      SNERF_R4(r, 24), SNERF_R4(r, 28)
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tmem_st64(uint32_t taddr, const uint32_t (&r)[64]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], "
