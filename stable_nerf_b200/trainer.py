@@ -140,6 +140,15 @@ class TrainStep:
         # (838 us/step against 805 for scatter-then-all-reduce): the two kernels do not run side by side.
         self.overlap_allreduce = False
 
+    def _check_arena(self):
+        """The exchange sums the arena, not whatever .grad points at: refuse to run if a gradient was re-created
+        elsewhere (e.g. ``zero_grad(set_to_none=True)`` followed by autograd allocating a fresh tensor)."""
+        base = self.exchange.tensor.data_ptr()
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != base + 4 * self._ex_off[id(p)]:
+                raise RuntimeError("a parameter's .grad no longer lives in the peer-mapped gradient arena; keep the "
+                                   "tensors TrainStep installed (zero them in place, do not set them to None)")
+
     def _body(self):
         m = self.model
         if self.fused and m.training and m.mean_count > 0 and m.bg_radius <= 0 and hasattr(m, "fdesc"):
@@ -384,6 +393,8 @@ class TrainStep:
             self.rays_o.copy_(rays_o, non_blocking=True)
             self.rays_d.copy_(rays_d, non_blocking=True)
             self.target.copy_(target, non_blocking=True)
+        if self.exchange is not None:
+            self._check_arena()
         if self.graph is not None:
             self.graph.replay()
         else:
@@ -447,6 +458,8 @@ class TrainStep:
         autograd returns for the SD loss w.r.t. ``forward()['image']`` -- added to the L1 loss's own gradient
         (image = composite + (1 - weights_sum) * bg, so it also feeds d loss / d weights_sum)."""
         b = self._bufs
+        if self.exchange is not None:
+            self._check_arena()
         if grad_image is not None:
             g = grad_image.detach().to(torch.float32).reshape(self.n_rays, self.model.channel_dim)
             b["g_img"].add_(g)
