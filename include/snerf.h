@@ -280,6 +280,18 @@ int snerf_pack_sd_condition(const float* image, const float* rays_d, uint32_t B,
 int snerf_pack_sd_condition_backward(const float* grad_out, uint32_t B, uint32_t N, uint32_t C, float scale,
                                      float* grad_image, snerf_stream_t stream);
 
+/* composite forward + snerf_l1_loss_backward + composite backward of one training step in ONE launch (train.py:61-70
+ * over raymarching.py:241-288): same outputs as the three calls -- weights_sum/depth/image (before the background
+ * blend), pred_image, depth_norm (may be NULL), loss (same bits: same summation order), grad_sigmas/grad_rgbs with every
+ * row written -- without the intermediate d loss/d image arrays.  n_samples: device int32 from the march (rows past it
+ * are padding); counter: one zero-initialised device uint32 the kernel leaves at zero. */
+int snerf_composite_l1_train(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays, uint32_t M,
+                             uint32_t N, float T_thresh, uint32_t channel_dim, const float* target, const float* bg_color,
+                             float bg_scalar, float grad_scale, const float* nears, const float* fars, float* weights_sum,
+                             float* depth, float* image, float* pred_image, float* depth_norm, float* loss,
+                             float* grad_sigmas, float* grad_rgbs, const int32_t* n_samples, uint32_t* counter,
+                             snerf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * The inference loop of NeRFRenderer.run_cuda as one call (nerf/renderer.py:116-166)
  *

@@ -113,6 +113,8 @@ SIGNATURES = {
     "snerf_debug_set_dedupe_max_res": (None, [_U]),
     "snerf_tc_probe": (c_int, [_P, c_int, _S]),
     "snerf_debug_phase_buffer": (None, [_P, c_int]),
+    "snerf_composite_l1_train": (c_int, [_P, _P, _P, _P, _U, _U, _F, _U, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                         _P, _P, _S]),
     "snerf_render_rays_workspace_bytes": (c_size_t, [POINTER(FieldDesc), _U, _U, c_int]),
     "snerf_render_rays": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _U, _U, _F, _F, _U, _P, _P, _P, _P, _P, _P, c_int, _F,
                                   _F, _U, _P, _P, _P, _P, POINTER(RenderStats), _P, c_size_t, _S]),

@@ -43,24 +43,16 @@ __device__ __forceinline__ void store_rgb(float* __restrict__ out, size_t i, con
 
 // ------------------------------------------------------------------------------------------------ train forward
 
+// One ray's front-to-back compositing by a warp (raymarching.cu:501-601): on return every lane holds weights_sum,
+// depth and the channels of the ray.
 template <int C>
-__global__ void __launch_bounds__(kCompThreads) k_composite_train_fwd(const float* __restrict__ sigmas,
-                                                                      const float* __restrict__ rgbs,
-                                                                      const float* __restrict__ deltas,
-                                                                      const int32_t* __restrict__ rays, uint32_t M,
-                                                                      uint32_t N, float T_thresh,
-                                                                      float* __restrict__ weights_sum,
-                                                                      float* __restrict__ depth,
-                                                                      float* __restrict__ image) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (n >= N) return;
-  const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
-
-  float ws = 0.f, d = 0.f, ch[C];
+__device__ __forceinline__ void composite_ray_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                  const float* __restrict__ deltas, uint32_t offset, uint32_t num_steps,
+                                                  uint32_t M, float T_thresh, int lane, float& ws, float& d, float (&ch)[C]) {
+  ws = 0.f;
+  d = 0.f;
 #pragma unroll
   for (int k = 0; k < C; k++) ch[k] = 0.f;
-
   if (num_steps != 0 && offset + num_steps <= M) {
     float T_run = 1.f, t_run = 0.f;
     for (uint32_t base = 0; base < num_steps; base += 32) {
@@ -97,6 +89,24 @@ __global__ void __launch_bounds__(kCompThreads) k_composite_train_fwd(const floa
 #pragma unroll
     for (int k = 0; k < C; k++) ch[k] = warp_sum(ch[k]);
   }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kCompThreads) k_composite_train_fwd(const float* __restrict__ sigmas,
+                                                                      const float* __restrict__ rgbs,
+                                                                      const float* __restrict__ deltas,
+                                                                      const int32_t* __restrict__ rays, uint32_t M,
+                                                                      uint32_t N, float T_thresh,
+                                                                      float* __restrict__ weights_sum,
+                                                                      float* __restrict__ depth,
+                                                                      float* __restrict__ image) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+
+  float ws, d, ch[C];
+  composite_ray_fwd<C>(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane, ws, d, ch);
   if (lane == 0) {
     weights_sum[index] = ws;
     depth[index] = d;
@@ -106,28 +116,14 @@ __global__ void __launch_bounds__(kCompThreads) k_composite_train_fwd(const floa
 
 // ------------------------------------------------------------------------------------------------ train backward
 
-// Every sample row owned by a ray is written (zeros after the termination point and for dropped rays), so the
-// caller does not have to memset the gradients the way raymarching.py:283-284 does.
+// One ray's compositing backward by a warp (raymarching.cu:614-726): gi = d loss / d image of the ray, fin = its
+// composited channels, gws_term = d loss / d weights_sum * (1 - weights_sum).  Writes every sample row the ray owns.
 template <int C>
-__global__ void __launch_bounds__(kCompThreads) k_composite_train_bwd(
-    const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image, const float* __restrict__ sigmas,
-    const float* __restrict__ rgbs, const float* __restrict__ deltas, const int32_t* __restrict__ rays,
-    const float* __restrict__ weights_sum, const float* __restrict__ image, uint32_t M, uint32_t N, float T_thresh,
-    float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, const int32_t* __restrict__ n_samples) {
-  const int lane = threadIdx.x & 31;
-  if (n_samples) {  // rows [*n_samples, M): alignment padding that no ray owns
-    float z[C];
-#pragma unroll
-    for (int k = 0; k < C; k++) z[k] = 0.f;
-    for (uint32_t i = (uint32_t)max(0, *n_samples) + blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
-      grad_sigmas[i] = 0.f;
-      store_rgb<C>(grad_rgbs, i, z);
-    }
-  }
-  const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (n >= N) return;
-  const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
-  if (num_steps == 0 || offset >= M) return;
+__device__ __forceinline__ void composite_ray_bwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                  const float* __restrict__ deltas, uint32_t offset, uint32_t num_steps,
+                                                  uint32_t M, float T_thresh, int lane, float gws_term, const float (&gi)[C],
+                                                  const float (&fin)[C], float* __restrict__ grad_sigmas,
+                                                  float* __restrict__ grad_rgbs) {
   float zero[C];
 #pragma unroll
   for (int k = 0; k < C; k++) zero[k] = 0.f;
@@ -138,10 +134,7 @@ __global__ void __launch_bounds__(kCompThreads) k_composite_train_bwd(
     }
     return;
   }
-  const float gws_term = __ldg(grad_weights_sum + index) * (1.0f - __ldg(weights_sum + index));
-  float gi[C], fin[C], acc_run[C];
-  load_rgb<C>(grad_image, index, gi);
-  load_rgb<C>(image, index, fin);
+  float acc_run[C];
 #pragma unroll
   for (int k = 0; k < C; k++) acc_run[k] = 0.f;
 
@@ -192,6 +185,39 @@ __global__ void __launch_bounds__(kCompThreads) k_composite_train_bwd(
     if (term) done = true;
     T_run = __shfl_sync(kFull, T_after, 31);
   }
+}
+
+// Every sample row owned by a ray is written (zeros after the termination point and for dropped rays), so the
+// caller does not have to memset the gradients the way raymarching.py:283-284 does.
+template <int C>
+__global__ void __launch_bounds__(kCompThreads) k_composite_train_bwd(
+    const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image, const float* __restrict__ sigmas,
+    const float* __restrict__ rgbs, const float* __restrict__ deltas, const int32_t* __restrict__ rays,
+    const float* __restrict__ weights_sum, const float* __restrict__ image, uint32_t M, uint32_t N, float T_thresh,
+    float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, const int32_t* __restrict__ n_samples) {
+  const int lane = threadIdx.x & 31;
+  if (n_samples) {  // rows [*n_samples, M): alignment padding that no ray owns
+    float z[C];
+#pragma unroll
+    for (int k = 0; k < C; k++) z[k] = 0.f;
+    for (uint32_t i = (uint32_t)max(0, *n_samples) + blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+      grad_sigmas[i] = 0.f;
+      store_rgb<C>(grad_rgbs, i, z);
+    }
+  }
+  const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+  if (num_steps == 0 || offset >= M) return;
+  float gws_term = 0.f, gi[C], fin[C];
+#pragma unroll
+  for (int k = 0; k < C; k++) gi[k] = fin[k] = 0.f;
+  if (offset + num_steps <= M) {
+    gws_term = __ldg(grad_weights_sum + index) * (1.0f - __ldg(weights_sum + index));
+    load_rgb<C>(grad_image, index, gi);
+    load_rgb<C>(image, index, fin);
+  }
+  composite_ray_bwd<C>(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane, gws_term, gi, fin, grad_sigmas, grad_rgbs);
 }
 
 // zero rows [*n_samples, M) of the gradients (alignment padding that no ray owns)
@@ -258,6 +284,93 @@ __global__ void __launch_bounds__(1024) k_l1_loss_backward(const float* __restri
     float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
     v = warp_sum(v);
     if (threadIdx.x == 0) *loss = v / ((float)N * (float)C);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fused train step tail
+//
+// composite forward -> background blend + L1 loss and its gradient -> composite backward, one launch (the three
+// kernels above back to back are launch-bound at 4096 rays).  The L1 gradient of a ray depends on that ray only
+// (sign(pred - target) * scale), so the warp that composited a ray goes straight on to its backward with the ray's
+// channels still in registers.  The loss VALUE is a sum over all rays: the last CTA to finish adds |pred - target| in
+// exactly the order of k_l1_loss_backward's single 1024-thread block (32 virtual warps), so the number is reproducible
+// and equal to the unfused path's bit for bit.
+template <int C>
+__global__ void __launch_bounds__(kCompThreads) k_composite_l1_train(
+    const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+    const int32_t* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh, const float* __restrict__ target,
+    const float* __restrict__ bg_color, float bg_scalar, float grad_scale, const float* __restrict__ nears,
+    const float* __restrict__ fars, float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
+    float* __restrict__ pred_image, float* __restrict__ depth_norm, float* __restrict__ loss, float* __restrict__ grad_sigmas,
+    float* __restrict__ grad_rgbs, const int32_t* __restrict__ n_samples, uint32_t* __restrict__ counter) {
+  const int lane = threadIdx.x & 31;
+  {  // rows [*n_samples, M): alignment padding that no ray owns
+    float z[C];
+#pragma unroll
+    for (int k = 0; k < C; k++) z[k] = 0.f;
+    for (uint32_t i = (uint32_t)max(0, *n_samples) + blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+      grad_sigmas[i] = 0.f;
+      store_rgb<C>(grad_rgbs, i, z);
+    }
+  }
+  const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n < N) {
+    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+    float ws, d, ch[C];
+    composite_ray_fwd<C>(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane, ws, d, ch);
+    // blend, loss gradient (k_l1_loss_backward's arithmetic, op for op); every lane computes the same values
+    float bg[C], pred[C], tgt[C], g[C], gws = 0.f;
+#pragma unroll
+    for (int k = 0; k < C; k++) bg[k] = bg_color ? __ldg(bg_color + k) : bg_scalar;
+    load_rgb<C>(target, index, tgt);
+    const float om = fadd(1.0f, -ws);
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+      pred[k] = fadd(ch[k], fmul(om, bg[k]));
+      const float df = fadd(pred[k], -tgt[k]);
+      g[k] = df > 0.f ? grad_scale : (df < 0.f ? -grad_scale : 0.f);
+      gws -= g[k] * bg[k];
+    }
+    if (lane == 0) {
+      weights_sum[index] = ws;
+      depth[index] = d;
+      store_rgb<C>(image, index, ch);
+      store_rgb<C>(pred_image, index, pred);
+      if (depth_norm) {
+        const float nr = __ldg(nears + index);
+        depth_norm[index] = __fdiv_rn(fmaxf(fadd(d, -nr), 0.f), fadd(__ldg(fars + index), -nr));
+      }
+    }
+    if (num_steps != 0 && offset < M)
+      composite_ray_bwd<C>(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane, gws * (1.0f - ws), g, ch, grad_sigmas,
+                           grad_rgbs);
+  }
+
+  // ---- loss value: the last CTA sums, in the order of k_l1_loss_backward's 1024-thread block
+  __shared__ float part[32];
+  __shared__ uint32_t is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (uint32_t vw = threadIdx.x >> 5; vw < 32u; vw += kCompThreads / 32) {
+    float acc = 0.f;
+    for (uint32_t r = vw * 32u + lane; r < N; r += 1024u) {
+#pragma unroll
+      for (int k = 0; k < C; k++) acc += fabsf(fadd(__ldcg(pred_image + (size_t)r * C + k), -__ldg(target + (size_t)r * C + k)));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) part[vw] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const float v = warp_sum(part[threadIdx.x]);
+    if (threadIdx.x == 0) {
+      *loss = v / ((float)N * (float)C);
+      *counter = 0u;
+    }
   }
 }
 
@@ -392,6 +505,25 @@ int snerf_l1_loss_backward(const float* image, const float* weights_sum, const f
   SNERF_DISPATCH_C(channel_dim, (k_l1_loss_backward<kC><<<1, 1024, 0, (cudaStream_t)stream>>>(
                                     image, weights_sum, target, bg_color, bg_scalar, N, grad_scale, loss, grad_image,
                                     grad_weights_sum, pred_image, depth, nears, fars, depth_norm)));
+  return finish_launch();
+}
+
+int snerf_composite_l1_train(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays, uint32_t M,
+                             uint32_t N, float T_thresh, uint32_t channel_dim, const float* target, const float* bg_color,
+                             float bg_scalar, float grad_scale, const float* nears, const float* fars, float* weights_sum,
+                             float* depth, float* image, float* pred_image, float* depth_norm, float* loss,
+                             float* grad_sigmas, float* grad_rgbs, const int32_t* n_samples, uint32_t* counter,
+                             snerf_stream_t stream) {
+  if (N == 0) return SNERF_OK;
+  if (!rays || !target || !weights_sum || !depth || !image || !pred_image || !loss || !n_samples || !counter)
+    return SNERF_E_BADARG;
+  if (M > 0 && (!sigmas || !rgbs || !deltas || !grad_sigmas || !grad_rgbs)) return SNERF_E_BADARG;
+  if (depth_norm && (!nears || !fars)) return SNERF_E_BADARG;
+  const uint32_t blocks = div_up(N, kCompThreads / 32);
+  SNERF_DISPATCH_C(channel_dim, (k_composite_l1_train<kC><<<blocks, kCompThreads, 0, (cudaStream_t)stream>>>(
+                                    sigmas, rgbs, deltas, rays, M, N, T_thresh, target, bg_color, bg_scalar, grad_scale, nears,
+                                    fars, weights_sum, depth, image, pred_image, depth_norm, loss, grad_sigmas, grad_rgbs,
+                                    n_samples, counter)));
   return finish_launch();
 }
 

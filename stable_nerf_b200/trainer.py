@@ -74,6 +74,7 @@ class TrainStep:
         self.bg_color, self.T_thresh, self.world_size = bg_color, T_thresh, world_size
         self.loss_scale = loss_scale
         self.fused, self.perturb, self.dt_gamma = bool(fused), bool(perturb), dt_gamma
+        self.fuse_tail = True  # whole steps: composite forward + L1 + composite backward in one launch
         self._bufs = None
         self._mark = None
         self._graph_fwd = self._graph_bwd = None
@@ -176,7 +177,7 @@ class TrainStep:
         b = dict(M=M, nears=e(N), fars=e(N), noises=torch.zeros(N, **f32), rays=torch.empty(N, 3, dtype=torch.int32, device=dev),
                  n_samples=torch.empty(1, dtype=torch.int32, device=dev), xyzs=e(M, 3), dirs=e(M, 3), deltas=e(M, 2),
                  sigmas=e(M), rgbs=e(M, C), ws=e(N), depth=e(N), image=e(N, C), g_img=e(N, C), g_ws=e(N), g_sig=e(M),
-                 g_rgb=e(M, C), pred=e(N, C), depth_norm=e(N))
+                 g_rgb=e(M, C), pred=e(N, C), depth_norm=e(N), tail_counter=torch.zeros(1, dtype=torch.int32, device=dev))
         b["march_ws_bytes"] = march_train_workspace_bytes(lib, N, self.max_steps)
         b["march_ws"] = torch.empty(b["march_ws_bytes"], dtype=torch.uint8, device=dev)
         b["field_ws_bytes"] = max(lib.snerf_field_workspace_bytes(m.fdesc, M, prec, 0),
@@ -238,6 +239,18 @@ class TrainStep:
         if m.density_scale != 1:
             b["sigmas"].mul_(m.density_scale)
         mark("field_fwd")
+        if phase == "both" and self.fuse_tail:
+            # composite forward + blend/L1 + composite backward as ONE launch: the L1 gradient of a ray depends on that ray
+            # only, so the warp that composited it carries straight on into its backward (csrc/composite.cu)
+            chk(lib.snerf_composite_l1_train(P(b["sigmas"]), P(b["rgbs"]), P(b["deltas"]), P(b["rays"]), M, N,
+                                             float(self.T_thresh), C, P(self.target), P(b["bg"]), b["bg_scalar"],
+                                             float(self.loss_scale) / (N * C), P(b["nears"]), P(b["fars"]), P(b["ws"]),
+                                             P(b["depth"]), P(b["image"]), P(b["pred"]), P(b["depth_norm"]), P(self.loss),
+                                             P(b["g_sig"]), P(b["g_rgb"]), P(b["n_samples"]), P(b["tail_counter"]), S),
+                "composite + L1 + composite backward")
+            mark("composite_l1_fused")
+            self.outputs = {"image": b["pred"], "depth": b["depth_norm"], "weights_sum": b["ws"]}
+            return self._fused_backward(b, M, mark, composite=False)
         chk(lib.snerf_composite_rays_train_forward(P(b["sigmas"]), P(b["rgbs"]), P(b["deltas"]), P(b["rays"]), M, N,
                                                    float(self.T_thresh), C, P(b["ws"]), P(b["depth"]), P(b["image"]), S),
             "composite forward")
@@ -252,7 +265,7 @@ class TrainStep:
             return
         self._fused_backward(b, M, mark)
 
-    def _fused_backward(self, b, M, mark):
+    def _fused_backward(self, b, M, mark, composite=True):
         m, N, C = self.model, self.n_rays, self.model.channel_dim
         lib = _lib.load()
         P, S, chk = _lib.ptr, _lib.stream(), _lib.check
@@ -260,13 +273,15 @@ class TrainStep:
         sp, cp = m.sigma_net.params, m.color_net.params
         nm = m.sigma_net.n_mlp
         spd = sp.detach()
-        chk(lib.snerf_composite_rays_train_backward_ex(P(b["g_ws"]), P(b["g_img"]), P(b["sigmas"]), P(b["rgbs"]),
-                                                       P(b["deltas"]), P(b["rays"]), P(b["ws"]), P(b["image"]), M, N,
-                                                       float(self.T_thresh), C, P(b["g_sig"]), P(b["g_rgb"]),
-                                                       P(b["n_samples"]), S), "composite backward")
+        if composite:
+            chk(lib.snerf_composite_rays_train_backward_ex(P(b["g_ws"]), P(b["g_img"]), P(b["sigmas"]), P(b["rgbs"]),
+                                                           P(b["deltas"]), P(b["rays"]), P(b["ws"]), P(b["image"]), M, N,
+                                                           float(self.T_thresh), C, P(b["g_sig"]), P(b["g_rgb"]),
+                                                           P(b["n_samples"]), S), "composite backward")
         if m.density_scale != 1:
             b["g_sig"].mul_(m.density_scale)
-        mark("composite_bwd")
+        if composite:
+            mark("composite_bwd")
         chk(lib.snerf_field_backward_ex(m.fdesc, P(b["xyzs"]), P(b["dirs"]), M, P(spd[nm:]), P(spd[:nm]), P(cp.detach()),
                                         P(b["g_sig"]), P(b["g_rgb"]), prec, P(sp.grad[nm:]), P(sp.grad[:nm]), P(cp.grad),
                                         P(b["saved"]), b["saved_bytes"], P(b["field_ws"]), b["field_ws_bytes"],
@@ -279,22 +294,28 @@ class TrainStep:
         """Device time of each stage of the fused step (CUDA events on the launch stream, eager launches): returns
         ({stage: ms}, n_samples, M)."""
         acc = {}
-        for it in range(iters + 2):
-            evs = []
+        fuse_tail = self.fuse_tail
+        # first the three kernels of the step's tail one by one (their own rooflines), then the one-launch form the step runs
+        for fuse in (False, True):
+            self.fuse_tail = fuse
+            for it in range(iters + 2):
+                evs = []
 
-            def mark(name):
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                evs.append((name, e))
-            self._mark = mark
-            try:
-                self._body_fused()
-            finally:
-                self._mark = None
-            torch.cuda.synchronize()
-            if it >= 2:
-                for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
-                    acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1) / iters
+                def mark(name):
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record()
+                    evs.append((name, e))
+                self._mark = mark
+                try:
+                    self._body_fused()
+                finally:
+                    self._mark = None
+                torch.cuda.synchronize()
+                if it >= 2:
+                    for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
+                        if not fuse or n1 == "composite_l1_fused":
+                            acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1) / iters
+        self.fuse_tail = fuse_tail
         n_samples = int(self._bufs["n_samples"].item())
         return acc, n_samples, self._bufs["M"]
 

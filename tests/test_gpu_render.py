@@ -188,6 +188,59 @@ def test_cuda_graph_train_step_matches_eager(built_lib, cuda):
     assert abs(ts.step_from_host(*hs) - res[True][0]) <= 1e-6
 
 
+@pytest.mark.parametrize("C,bg,M_cap", [(3, 1.0, None), (4, "tensor", None), (1, 0.0, None), (3, 1.0, 20000)])
+def test_one_launch_tail_equals_the_three_kernels(C, bg, M_cap, built_lib, cuda):
+    """snerf_composite_l1_train against composite forward -> snerf_l1_loss_backward -> composite backward on the same
+    marched samples: every output identical, the loss bit for bit (same summation order); M_cap drops the rays that
+    do not fit (their rows carry zero gradients either way)."""
+    from stable_nerf_b200 import _lib, raymarching, synthetic as syn
+    from stable_nerf_b200._lib import check, ptr, stream
+    N = 1500
+    ro, rd = syn.train_batch(N, 100, 100, 138.0, n_views=2, seed=4)
+    o, d = torch.from_numpy(ro).to(cuda), torch.from_numpy(rd).to(cuda)
+    bitfield = torch.from_numpy(syn.pack_bitfield(syn.occupancy_grid(lego_like=True))).to(cuda)
+    aabb = torch.tensor([-1, -1, -1, 1, 1, 1], dtype=torch.float32, device=cuda)
+    nears, fars = raymarching.near_far_from_aabb(o, d, aabb, 0.2)
+    counter = torch.zeros(2, dtype=torch.int32, device=cuda)
+    xyzs, dirs, deltas, rays = raymarching.march_rays_train(o, d, 1, bitfield, 1, 128, nears, fars, counter, -1, False, 128,
+                                                             False, 0, 256)
+    n_samples = counter[:1].clone()
+    M = xyzs.shape[0]
+    if M_cap is not None:  # a buffer smaller than the march needs: rays past it are dropped (raymarching.cu:529)
+        M = M_cap
+        deltas = deltas[:M].contiguous()
+        n_samples.clamp_(max=M)
+    g = torch.Generator().manual_seed(C)
+    sig = (torch.rand(M, generator=g) * 30).to(cuda)
+    rgb = torch.rand(M, C, generator=g).to(cuda)
+    tgt = torch.rand(N, C, generator=g).to(cuda)
+    bgt = torch.tensor([0.2, 0.4, 0.6, 1.0][:C], device=cuda) if bg == "tensor" else None
+    bgs = 0.0 if bg == "tensor" else float(bg)
+    scale = 0.5 / (N * C)
+    lib = built_lib
+    e = lambda *shape: torch.full(shape, float("nan"), device=cuda)
+    A = dict(ws=e(N), depth=e(N), image=e(N, C), pred=e(N, C), dn=e(N), loss=e(1), gs=e(M), gr=e(M, C), gi=e(N, C), gw=e(N))
+    check(lib.snerf_composite_rays_train_forward(ptr(sig), ptr(rgb), ptr(deltas), ptr(rays), M, N, 1e-4, C, ptr(A["ws"]),
+                                                 ptr(A["depth"]), ptr(A["image"]), stream()), "fwd")
+    check(lib.snerf_l1_loss_backward(ptr(A["image"]), ptr(A["ws"]), ptr(tgt), ptr(bgt), bgs, N, C, scale, ptr(A["loss"]),
+                                     ptr(A["gi"]), ptr(A["gw"]), ptr(A["pred"]), ptr(A["depth"]), ptr(nears), ptr(fars),
+                                     ptr(A["dn"]), stream()), "loss")
+    check(lib.snerf_composite_rays_train_backward_ex(ptr(A["gw"]), ptr(A["gi"]), ptr(sig), ptr(rgb), ptr(deltas), ptr(rays),
+                                                     ptr(A["ws"]), ptr(A["image"]), M, N, 1e-4, C, ptr(A["gs"]), ptr(A["gr"]),
+                                                     ptr(n_samples), stream()), "bwd")
+    B = dict(ws=e(N), depth=e(N), image=e(N, C), pred=e(N, C), dn=e(N), loss=e(1), gs=e(M), gr=e(M, C))
+    cnt = torch.zeros(1, dtype=torch.int32, device=cuda)
+    for _ in range(2):  # twice: the kernel leaves its counter ready for the next launch
+        check(lib.snerf_composite_l1_train(ptr(sig), ptr(rgb), ptr(deltas), ptr(rays), M, N, 1e-4, C, ptr(tgt), ptr(bgt), bgs,
+                                           scale, ptr(nears), ptr(fars), ptr(B["ws"]), ptr(B["depth"]), ptr(B["image"]),
+                                           ptr(B["pred"]), ptr(B["dn"]), ptr(B["loss"]), ptr(B["gs"]), ptr(B["gr"]),
+                                           ptr(n_samples), ptr(cnt), stream()), "fused tail")
+    torch.cuda.synchronize()
+    assert int(cnt) == 0 and float(A["ws"].max()) > 0.5 and float(A["gs"].abs().max()) > 0
+    for k in B:
+        assert torch.equal(A[k], B[k]), f"{k}: max diff {float((A[k] - B[k]).abs().max())}"
+
+
 @pytest.mark.parametrize("precision,C,bg", [("fp32", 3, 1), ("bf16", 3, 1), ("fp32", 4, "tensor")])
 def test_fused_train_step_matches_autograd_step(precision, C, bg, built_lib, cuda):
     """TrainStep's fused body (a straight sequence of C-ABI calls with the L1 loss kernel) against the same step through
