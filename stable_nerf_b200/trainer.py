@@ -110,6 +110,10 @@ class TrainStep:
         # (stable_nerf_b200.p2p / csrc/p2p_reduce.cu), "nccl" = NCCL all-reduce after the replay, "auto" = p2p when the
         # ranks can map each other's memory (one node, CUDA IPC), else nccl.
         self.exchange, self.exchange_kind, self.exchange_error = None, ("none" if world_size == 1 else "nccl"), None
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError(f"exchange must be 'auto', 'p2p' or 'nccl', got {exchange!r}")
+        if exchange == "p2p" and world_size > 1 and dev.type != "cuda":
+            raise RuntimeError("exchange='p2p' needs CUDA devices (peer memory over NVLink); use 'auto' or 'nccl'")
         if world_size > 1 and exchange in ("auto", "p2p") and dev.type == "cuda":
             try:
                 self._setup_p2p(dev)

@@ -99,3 +99,24 @@ def test_synthetic_workloads_are_deterministic_and_shaped():
     # the centre pixel looks at the origin
     c = fd[32 * 64 + 32]
     assert np.dot(c, -fo[0] / np.linalg.norm(fo[0])) > 0.999
+
+
+def test_train_step_exchange_argument_on_cpu():
+    """The peer-memory gradient exchange needs CUDA devices: on the CPU an explicit request is refused, 'auto' keeps the
+    torch.distributed all-reduce, and the gradients stay ordinary tensors."""
+    import pytest
+    from stable_nerf_b200 import NeRFNetwork
+    from stable_nerf_b200.config import BaseNeRFConfig
+    from stable_nerf_b200.trainer import TrainStep
+    cfg = BaseNeRFConfig().as_dict()
+    cfg["encoding_sigma"]["n_levels"] = 2
+    cfg["encoding_sigma"]["log2_hashmap_size"] = 10
+    m = NeRFNetwork(config=cfg)
+    with pytest.raises(RuntimeError, match="needs CUDA"):
+        TrainStep(m, 16, world_size=2, use_graph=False, exchange="p2p")
+    with pytest.raises(ValueError):
+        TrainStep(m, 16, world_size=2, use_graph=False, exchange="mpi")
+    ts = TrainStep(m, 16, world_size=2, use_graph=False, exchange="auto")
+    assert ts.exchange is None and ts.exchange_kind == "nccl" and not ts.overlap_allreduce
+    assert TrainStep(m, 16, world_size=1, use_graph=False).exchange_kind == "none"
+    assert all(p.grad is not None and p.grad.shape == p.shape for p in ts.params)
