@@ -52,48 +52,115 @@ __device__ __forceinline__ float corner_weight(const Cell& c, uint32_t corner) {
   return fmul(fmul(wx, wy), wz);
 }
 
+// The 8 corner entries of a cell, corner k = x + 2y + 4z.  Same arithmetic as grid_index per corner, with the shared
+// terms computed once (the products of the hash / the dense strides) and the wrap into the level written as a
+// conditional subtraction (corner coordinates are at most res for positions in [0,1], so a dense index stays below
+// twice the level size; anything larger -- positions outside the unit cube -- takes the modulo).
+__device__ __forceinline__ void corner_indices(const LevelInfo& li, const Cell& c, uint32_t (&idx)[8]) {
+  if (li.hashed) {
+    const uint32_t hy0 = c.c[1] * 2654435761u, hy1 = (c.c[1] + 1u) * 2654435761u;
+    const uint32_t hz0 = c.c[2] * 805459861u, hz1 = (c.c[2] + 1u) * 805459861u;
+    const uint32_t h[4] = {hy0 ^ hz0, hy1 ^ hz0, hy0 ^ hz1, hy1 ^ hz1};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      idx[2 * k] = c.c[0] ^ h[k];
+      idx[2 * k + 1] = (c.c[0] + 1u) ^ h[k];
+    }
+  } else {
+    const uint32_t r = li.res, r2 = r * r;
+    const uint32_t base = c.c[0] + c.c[1] * r + c.c[2] * r2;
+    const uint32_t o[4] = {0u, r, r2, r + r2};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      idx[2 * k] = base + o[k];
+      idx[2 * k + 1] = base + o[k] + 1u;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    uint32_t i = idx[k];
+    if (li.pow2_mask) {
+      i &= li.pow2_mask;
+    } else if (i >= li.size) {
+      i -= li.size;
+      if (i >= li.size) i %= li.size;
+    }
+    idx[k] = li.offset + i;
+  }
+}
+
+// trilinear weights of the 8 corners, each rounded as ((wx * wy) * wz) like corner_weight
+__device__ __forceinline__ void corner_weights(const Cell& c, float (&w)[8]) {
+  const float wx[2] = {fadd(1.0f, -c.w[0]), c.w[0]}, wy[2] = {fadd(1.0f, -c.w[1]), c.w[1]};
+  const float wz[2] = {fadd(1.0f, -c.w[2]), c.w[2]};
+  const float wxy[4] = {fmul(wx[0], wy[0]), fmul(wx[1], wy[0]), fmul(wx[0], wy[1]), fmul(wx[1], wy[1])};
+#pragma unroll
+  for (int k = 0; k < 8; k++) w[k] = fmul(wxy[k & 3], wz[k >> 2]);
+}
+
 // ---------------------------------------------------------------------------------------------- table scatter-add
 // One (sample, level) gradient per lane, 32 consecutive samples of ONE level per warp (warp-uniform control flow).
-// The SM retires about one reduction LANE per cycle and same-address reductions serialise at the L2, so the warp issues
-// fewer lanes: runs of lanes with equal (index0, index1) -- consecutive samples of a ray in the same cell -- are summed
-// with a segmented scan first and only the last lane of a run issues (`dedupe`); the two corners that differ in x are
-// adjacent entries whenever index0 is even: one 16-byte red.global.add.v4.f32 instead of two v2's (`pairing`).
-__device__ __forceinline__ void red_pair(float2* __restrict__ grad_table, uint32_t i0, uint32_t i1, float4 v, bool pairing) {
-  if (pairing && i1 == i0 + 1u && (i0 & 1u) == 0u) {
-    atomicAdd(reinterpret_cast<float4*>(grad_table + i0), v);
-  } else {
-    atomicAdd(grad_table + i0, make_float2(v.x, v.y));
-    atomicAdd(grad_table + i1, make_float2(v.z, v.w));
-  }
+// The kernel is instruction-bound (ncu: 74 % issue utilisation, reductions 2 % of the instructions), and same-address
+// reductions serialise at the L2, so the code below is written for few instructions and few reduction lanes:
+//  * runs of consecutive lanes in the same cell -- consecutive samples of a ray -- are summed with ONE segmented scan
+//    over all 16 corner values (one run structure and one flag per round for the 8 corners) and only the last lane of
+//    a run issues (`dedupe`, levels with resolution <= dedupe_max_res);
+//  * the two corners that differ in x are adjacent entries whenever index0 is even: one 16-byte
+//    red.global.add.v4.f32 instead of two v2's (`pairing`); the choice is predicated, not branched.
+__device__ __forceinline__ void red_pair(float2* __restrict__ grad_table, uint32_t i0, uint32_t i1, float4 v, bool pairing,
+                                         bool on) {
+  const bool pair = pairing && i1 == i0 + 1u && (i0 & 1u) == 0u;
+  asm volatile(
+      "{\n"
+      ".reg .pred pq, ps;\n"
+      "setp.ne.u32 pq, %6, 0;\n"
+      "setp.ne.u32 ps, %7, 0;\n"
+      "@pq red.global.add.v4.f32 [%0], {%2, %3, %4, %5};\n"
+      "@ps red.global.add.v2.f32 [%0], {%2, %3};\n"
+      "@ps red.global.add.v2.f32 [%1], {%4, %5};\n"
+      "}"
+      ::"l"(grad_table + i0), "l"(grad_table + i1), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
+        "r"((uint32_t)(on && pair)), "r"((uint32_t)(on && !pair))
+      : "memory");
 }
 
 __device__ __forceinline__ void scatter_level(const LevelInfo& li, const Cell& c, float2 gv, bool active, bool dedupe,
                                               bool pairing, int lane, float2* __restrict__ grad_table) {
+  uint32_t idx[8];
+  float w[8], v[16];
+  corner_indices(li, c, idx);
+  corner_weights(c, w);
 #pragma unroll
-  for (uint32_t kp = 0; kp < 4; kp++) {  // corner pair (x, x+1) at (y + kp&1, z + kp>>1)
-    const uint32_t cy = c.c[1] + (kp & 1u), cz = c.c[2] + (kp >> 1);
-    uint32_t i0 = grid_index(li, c.c[0], cy, cz), i1 = grid_index(li, c.c[0] + 1u, cy, cz);
-    const float w0 = corner_weight(c, kp * 2u), w1 = corner_weight(c, kp * 2u + 1u);
-    float4 v = make_float4(w0 * gv.x, w0 * gv.y, w1 * gv.x, w1 * gv.y);
-    if (!dedupe) {
-      if (active) red_pair(grad_table, i0, i1, v, pairing);
-      continue;
-    }
-    if (!active) { i0 = 0xffffffffu - (uint32_t)lane; i1 = i0; }  // a run of its own, value zero
-    const uint32_t p0 = __shfl_up_sync(kFull, i0, 1), p1 = __shfl_up_sync(kFull, i1, 1);
-    const bool head = lane == 0 || p0 != i0 || p1 != i1;
+  for (int k = 0; k < 8; k++) {
+    v[2 * k] = w[k] * gv.x;
+    v[2 * k + 1] = w[k] * gv.y;
+  }
+  bool issue = active;
+  if (dedupe) {
+    // a lane without a gradient is a run of its own; equal cells imply equal corner entries
+    const uint32_t k0 = active ? (c.c[0] | (c.c[1] << 16)) : 0xffffffffu, k1 = active ? c.c[2] : (uint32_t)lane;
+    const uint32_t p0 = __shfl_up_sync(kFull, k0, 1), p1 = __shfl_up_sync(kFull, k1, 1);
+    const bool head = lane == 0 || p0 != k0 || p1 != k1;
     bool f = head;  // a run head lies inside the span summed so far
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const float ux = __shfl_up_sync(kFull, v.x, d), uy = __shfl_up_sync(kFull, v.y, d);
-      const float uz = __shfl_up_sync(kFull, v.z, d), uw = __shfl_up_sync(kFull, v.w, d);
+      float u[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) u[k] = __shfl_up_sync(kFull, v[k], d);
       const bool uf = __shfl_up_sync(kFull, (int)f, d) != 0;
-      if (lane >= d && !f) { v.x += ux; v.y += uy; v.z += uz; v.w += uw; f = uf; }
+      if (lane >= d && !f) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] += u[k];
+        f = uf;
+      }
     }
     const bool next_head = __shfl_down_sync(kFull, (int)head, 1) != 0;
-    const bool tail = lane == 31 || next_head;
-    if (tail && active) red_pair(grad_table, i0, i1, v, pairing);
+    issue = active && (lane == 31 || next_head);
   }
+#pragma unroll
+  for (int kp = 0; kp < 4; kp++)  // corner pair (x, x+1) at (y + kp&1, z + kp>>1)
+    red_pair(grad_table, idx[2 * kp], idx[2 * kp + 1], make_float4(v[4 * kp], v[4 * kp + 1], v[4 * kp + 2], v[4 * kp + 3]),
+             pairing, issue);
 }
 
 // swizzled position of the float2 slot (sample s, level l) inside a [rows][16] float2 tile

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_fwd(snerf_grid_desc g,
     if (s >= ns) continue;
     const LevelInfo li = level_info(g, l);
     const Cell c = grid_cell(xs[s * 3], xs[s * 3 + 1], xs[s * 3 + 2], li.scale);
+    // (per-corner index / weight arithmetic on purpose: with the shared-term form of corner_indices the compiler keeps
+    // fewer of the 8 gathers in flight -- measured 64 us against 58 us)
     float2 v[8];
 #pragma unroll
     for (uint32_t k = 0; k < 8; k++)
