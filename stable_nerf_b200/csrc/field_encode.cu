@@ -107,9 +107,13 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g,
   const float2* gin = reinterpret_cast<const float2*>(grad_enc) + (size_t)m0 * L;
   for (uint32_t i = threadIdx.x; i < ns * L; i += kEncThreads) tile[tile_slot(i / L, i % L)] = __ldg(gin + i);
   __syncthreads();
-  // kEncTile is a multiple of 32: a warp's 32 items share the level, so everything below is warp-uniform control flow
-  for (uint32_t item = level_begin * kEncTile + threadIdx.x; item < kEncTile * level_end; item += kEncThreads) {
-    const uint32_t s = item % kEncTile, l = item / kEncTile;
+  // A warp works on 32 consecutive samples of ONE level.  The level is derived from a warp index the compiler knows to
+  // be uniform (a shuffle's result), so the level table sits in uniform registers, `dedupe` is a uniform branch and the
+  // scan's shuffles need no convergence brackets (with a per-thread item index every SHFL came with a WARPSYNC pair).
+  const uint32_t warp = __shfl_sync(kFull, threadIdx.x >> 5, 0);
+  constexpr uint32_t kBlocks = kEncTile / 32;  // 32-sample blocks of the tile
+  for (uint32_t it = level_begin * kBlocks + warp; it < level_end * kBlocks; it += kEncThreads / 32) {
+    const uint32_t l = it / kBlocks, s = (it % kBlocks) * 32u + (uint32_t)lane;
     float2 gv = make_float2(0.f, 0.f);
     if (s < ns) gv = tile[tile_slot(s, l)];
     const bool active = gv.x != 0.f || gv.y != 0.f;  // padded / terminated samples carry exact zeros
