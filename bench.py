@@ -38,43 +38,127 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed regions run.  NVML in a thread (2 ms period: a 30-step
+    timed region is only ~20 ms, too short for nvidia-smi's 200 ms loop to land a sample in it); nvidia-smi -lms as
+    the fall-back when NVML cannot be opened.  `mark()` brackets the timed regions: the summary is taken over the
+    samples inside them (or, if none landed inside, over every sample of the sampler's lifetime, and says so)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index=0, uuid=None):
+        self.index, self.uuid = index, uuid
+        self.rows = []          # (t, sm_mhz, set of reasons)
+        self.marks = []         # (t0, t1) of the timed regions
+        self.sm_max, self.source = None, None
+        self.proc = self.thread = None
+        self._stop = threading.Event()
+
+    # ---- NVML
+    def _nvml_open(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            u = self.uuid if str(self.uuid).startswith("GPU-") else "GPU-" + str(self.uuid)
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(u)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByUUID(u.encode())
+        else:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip()]
+            phys = int(ids[self.index]) if ids and all(v.strip().isdigit() for v in ids) and self.index < len(ids) else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)  # raises here, not in the thread, if unsupported
+        return pynvml, h
+
+    def _nvml_loop(self, nv, h):
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(reasons_fn(h))
+                except Exception:
+                    mask = 0
+                self.rows.append((time.perf_counter(), mhz, {n for n, b in self.BITS if mask & b}))
+            except Exception:
+                pass
+            self._stop.wait(0.002)
+
+    # ---- nvidia-smi fall-back
+    def _smi_loop(self):
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            if len(r) >= 8 and r[0].replace(".", "").isdigit():
+                if self.sm_max is None and r[1].replace(".", "").isdigit():
+                    self.sm_max = float(r[1])
+                names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+                self.rows.append((time.perf_counter(), float(r[0]),
+                                  {n for k, n in enumerate(names) if r[4 + k].lower().startswith("active")}))
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            nv, h = self._nvml_open()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            try:
+                sel = [f"--id={self.uuid if str(self.uuid).startswith('GPU-') else 'GPU-' + str(self.uuid)}"] if self.uuid else [f"--id={self.index}"]
+                self.proc = subprocess.Popen(["nvidia-smi", *sel, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                              "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.source = "nvidia-smi"
+                self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+                self.thread.start()
+            except Exception:
+                self.proc = self.thread = None
+        # do not start the timed region before the sampler delivers (nvidia-smi needs ~1 s to come up)
+        t_end = time.perf_counter() + 5.0
+        while self.thread is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.01)
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def mark(self):
+        """Context manager bracketing one timed region."""
+        sampler = self
+
+        class _M:
+            def __enter__(self):
+                self.t0 = time.perf_counter()
+
+            def __exit__(self, *a):
+                sampler.marks.append((self.t0, time.perf_counter()))
+        return _M()
 
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.25)
+        if self.source == "nvidia-smi" and self.proc:
+            time.sleep(0.15)
             self.proc.terminate()
+        self._stop.set()
+        if self.thread:
             self.thread.join(timeout=2)
+        return False
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 8 and r[4 + k].lower().startswith("active") for r in self.rows)]
-        busy = [x for x in sm if x >= 0.5 * max(sm)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+        try:
+            return self._summary()
+        except Exception as e:  # the sampler must never take the bench line down with it
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"], "source": self.source,
+                    "error": repr(e)[:200]}
+
+    def _summary(self):
+        rows = list(self.rows)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"], "source": self.source}
+        inside = [r for r in rows if any(t0 <= r[0] <= t1 for t0, t1 in self.marks)]
+        window = "timed regions" if inside else "sampler lifetime (no sample landed inside a timed region)"
+        use = inside or rows
+        sm = [r[1] for r in use]
+        reasons = sorted(set().union(*[r[2] for r in use]))
+        return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(sm), "window": window, "source": self.source}
 
 
 def workload(n_rays, seed):
@@ -365,26 +449,32 @@ def run_gpu_arm(args):
     barrier()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    with ClockSampler(local, uuid) as clocks:
         barrier()
-        e0.record()
-        for _ in range(args.steps):
-            ts.step()
-        e1.record()
-        barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = (ts.launches_per_step if ts.graph is not None else (_lib.launch_count() - launches0) // args.steps)
-    n_samples = int(model.step_counter[(model.local_step - 1) % 16, 0].item())
+        with clocks.mark():
+            e0.record()
+            for _ in range(args.steps):
+                ts.step()
+            e1.record()
+            barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        launches = (ts.launches_per_step if ts.graph is not None else (_lib.launch_count() - launches0) // args.steps)
+        n_samples = int(model.step_counter[(model.local_step - 1) % 16, 0].item())
 
-    # ---- end to end: pinned host inputs -> H2D -> step -> loss D2H, wall clock between device-complete points
-    for _ in range(args.warmup):
-        ts.step_from_host(h_o, h_d, h_t)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        loss = ts.step_from_host(h_o, h_d, h_t)
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        # ---- end to end: pinned host inputs -> H2D -> step -> loss D2H, wall clock between device-complete points
+        for _ in range(args.warmup):
+            ts.step_from_host(h_o, h_d, h_t)
+        barrier()
+        with clocks.mark():
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                loss = ts.step_from_host(h_o, h_d, h_t)
+            barrier()
+            e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
 
     total_rays = RAYS_PER_GPU * world
     out = {
