@@ -389,6 +389,11 @@ void snerf_debug_set_march_warp_max_rays(uint32_t n);
  * 64 sigma net, 128 table scatter-add.  Default 0xffffffff (all); results are only meaningful with all bits set. */
 void snerf_debug_set_field_stage_mask(uint32_t mask);
 
+/* Measurement aid: 1 (default) = the sums of the per-CTA weight-gradient partials of snerf_field_backward[_ex] run on
+ * a library-owned side stream, forked after their net's kernel and joined before the call returns (events only: the
+ * fork and join are captured with a CUDA graph like any other dependency); 0 = in line on the caller's stream. */
+void snerf_debug_set_side_reduce(uint32_t on);
+
 /* Measurement aid: levels with resolution <= res merge equal cells inside a warp before the scatter-add (default 300). */
 void snerf_debug_set_dedupe_max_res(uint32_t res);
 

@@ -110,6 +110,7 @@ SIGNATURES = {
     "snerf_tc_selftest": (c_int, [_P, _P, _P, _U, _U, c_int, c_int, _S]),
     "snerf_debug_set_march_warp_max_rays": (None, [_U]),
     "snerf_debug_set_field_stage_mask": (None, [_U]),
+    "snerf_debug_set_side_reduce": (None, [_U]),
     "snerf_debug_set_dedupe_max_res": (None, [_U]),
     "snerf_tc_probe": (c_int, [_P, c_int, _S]),
     "snerf_debug_phase_buffer": (None, [_P, c_int]),

@@ -75,6 +75,7 @@ size_t field_tc_workspace_bytes(const snerf_field_desc* f, uint32_t M, int backw
 size_t field_tc_saved_bytes(const snerf_field_desc* f, uint32_t M);
 void field_tc_set_phase_buffer(void* dev_buffer, int net);
 void field_tc_set_stage_mask(uint32_t mask);
+void field_tc_set_side_reduce(uint32_t on);
 int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                      const float* w_sigma, const float* w_color, float* sigmas, float* rgbs, float* geo_feat,
                      bool sigma_only, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, cudaStream_t s);

@@ -951,7 +951,8 @@ struct TcWorkspace {
   float4* rgb_y;
   __nv_bfloat16* g_geo;
   float* d_enc;
-  float* dw_part;  // per-CTA partial weight gradients of one net at a time (max of the two nets)
+  float* dw_part_color;  // per-CTA partial weight gradients, one buffer per net: the colour net's are still being
+  float* dw_part_sigma;  // summed (side stream) while the sigma kernel writes its own
 };
 
 // forward -> backward hand-off: [packed sigma weights][packed colour weights][geo: M x 16 bf16][enc: M x 32 bf16]
@@ -990,7 +991,8 @@ static size_t carve_tc(const snerf_field_desc* f, uint32_t M, int backward, char
   carve_handoff(f, M, hand, &o);
   o.g_geo = backward ? (__nv_bfloat16*)take((size_t)(M ? M : 1) * 16 * sizeof(__nv_bfloat16)) : nullptr;
   o.d_enc = backward ? (float*)take((size_t)(M ? M : 1) * 32 * sizeof(float)) : nullptr;
-  o.dw_part = backward ? (float*)take((size_t)kMaxGrid * std::max(sigma_shape(f).n_params, color_shape(f).n_params) * sizeof(float)) : nullptr;
+  o.dw_part_color = backward ? (float*)take((size_t)kMaxGrid * color_shape(f).n_params * sizeof(float)) : nullptr;
+  o.dw_part_sigma = backward ? (float*)take((size_t)kMaxGrid * sigma_shape(f).n_params * sizeof(float)) : nullptr;
   return off;
 }
 
@@ -1055,8 +1057,35 @@ static size_t bwd_smem(const PackedNet& n, int net) {
   return bwd_fixed_smem(n, net) + (size_t)bwd_slots(n, net) * kSlotBytes + 1024;
 }
 
+// The sums of the per-CTA weight-gradient partials (7-8 us each, HBM reads) depend on their own net's kernel only and
+// nothing but the end of the call depends on them: they run on a side stream forked after that kernel (events, so the
+// fork/join is captured with the step's graph like any other dependency) under the next tensor-core kernel / the table
+// scatter-add, and the caller's stream joins them before the call returns.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork[2] = {nullptr, nullptr}, join = nullptr;
+  bool ok = false;
+};
+static SideStream g_side[16];
+static SideStream* side_stream() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& ss = g_side[dev];
+  if (!ss.ok) {
+    if (ss.stream) return nullptr;  // creation failed before: stay on the caller's stream
+    if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    for (cudaEvent_t* e : {&ss.fork[0], &ss.fork[1], &ss.join})
+      if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ss.ok = true;
+  }
+  return &ss;
+}
+static uint32_t g_side_reduce = 1;  // measurement aid: 0 = the sums stay on the caller's stream
+void field_tc_set_side_reduce(uint32_t on) { g_side_reduce = on; }
+
+// s_reduce == s: in line.  Otherwise s_reduce waits for the kernel just launched on s (fork event k).
 template <int NET>
-static int launch_bwd(const TcParams& p, const PackedNet& n, uint32_t M, cudaStream_t s) {
+static int launch_bwd(const TcParams& p, const PackedNet& n, uint32_t M, cudaStream_t s, SideStream* side) {
   const uint32_t slots = bwd_slots(n, NET);
   const size_t smem = bwd_smem(n, NET);
   // sigma net: first/last-matrix weight gradients live in TMEM columns [384, 432) next to (n_mats - 2) hidden accumulators
@@ -1073,7 +1102,13 @@ static int launch_bwd(const TcParams& p, const PackedNet& n, uint32_t M, cudaStr
   } else {
     return SNERF_E_UNSUPPORTED;  // the activations of a tile leave no room for the weight ring
   }
-  k_reduce_partials<<<dim3(div_up(p.n_params / 4, 256), kReduceGroups), 256, 0, s>>>(p.dw_part, grid_for(M), p.n_params, p.grad_w);
+  cudaStream_t sr = s;
+  if (side) {
+    if (cudaEventRecord(side->fork[NET], s) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork[NET], 0) != cudaSuccess)
+      return (int)cudaGetLastError();
+    sr = side->stream;
+  }
+  k_reduce_partials<<<dim3(div_up(p.n_params / 4, 256), kReduceGroups), 256, 0, sr>>>(p.dw_part, grid_for(M), p.n_params, p.grad_w);
   return SNERF_OK;
 }
 
@@ -1171,12 +1206,15 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   p.grad_rgbs = grad_rgbs;
   p.g_geo = w.g_geo;
   p.grad_w = grad_w_color;
-  p.dw_part = w.dw_part;
+  p.dw_part = w.dw_part_color;
   p.n_params = sc.n_params;
   p.dbg = g_phase_net == 1 ? g_phase_dbg : nullptr;
+  SideStream* side = g_side_reduce ? side_stream() : nullptr;
+  bool forked = false;
   if (st & kStBwdColor) {
-    if (int e = launch_bwd<1>(p, pc, M, s)) return e;
+    if (int e = launch_bwd<1>(p, pc, M, s, side)) return e;
     launches += 2;
+    forked = side != nullptr;
   }
   // 3. sigma net: recompute from the saved encoding + dgrad + wgrad + table scatter-add
   fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
@@ -1185,19 +1223,24 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   p.grad_sigmas = grad_sigmas;
   p.g_geo = w.g_geo;
   p.grad_w = grad_w_sigma;
-  p.dw_part = w.dw_part;
+  p.dw_part = w.dw_part_sigma;
   p.n_params = ss.n_params;
   p.d_enc = d_enc_out ? d_enc_out : w.d_enc;  // caller-owned: it scatters the levels itself (snerf_hashgrid_backward_levels)
   p.dbg = g_phase_net == 0 ? g_phase_dbg : nullptr;
   if (st & kStBwdSigma) {
-    if (int e = launch_bwd<0>(p, ps, M, s)) return e;
+    if (int e = launch_bwd<0>(p, ps, M, s, side)) return e;
     launches += 2;
+    forked = side != nullptr;
   }
   // 4. table scatter-add of d loss / d encoding: its own full-occupancy kernel.  Running it inside the sigma kernel
   //    (dedicated warps, or in the compute warps' MMA waits) was measured and did not overlap: the reductions retire at
   //    ~1 lane/clk/SM and hold up the epilogues' shared-memory traffic, so the two costs add up either way.
   if ((st & kStBwdScatter) && !d_enc_out) {
     if (int e = launch_hashgrid_bwd(&f->grid, xyzs, true, f->bound, w.d_enc, M, grad_table, s)) return e;
+  }
+  if (forked) {  // join: the caller's stream continues once the sums have landed in grad_w_*
+    if (cudaEventRecord(side->join, side->stream) != cudaSuccess || cudaStreamWaitEvent(s, side->join, 0) != cudaSuccess)
+      return (int)cudaGetLastError();
   }
   return finish_launch(launches);
 }
