@@ -361,15 +361,23 @@ int snerf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_
                     float beta2, float eps, float weight_decay, int decoupled_weight_decay, uint32_t step, int zero_grad,
                     snerf_stream_t stream);
 
-/* Same, for callers that overlap the table's gradient all-reduce with its scatter-add (ray-sharded training): with
- * d_enc_out != NULL (f32 [M, 2*n_levels], 16-byte aligned; bf16 precision only) the backward stops after writing
- * d loss / d encoding there, and the caller scatters groups of levels with snerf_hashgrid_backward_levels, starting
- * the all-reduce of a group's (contiguous) table slice as soon as its launch is queued. */
+/* Same, with two extras.
+ * d_enc_out != NULL (f32 [M, 2*n_levels], 16-byte aligned; bf16 precision only): for callers that overlap the table's
+ * gradient all-reduce with its scatter-add (ray-sharded training) the backward stops after writing d loss / d encoding
+ * there, and the caller scatters groups of levels with snerf_hashgrid_backward_levels, starting the all-reduce of a
+ * group's (contiguous) table slice as soon as its launch is queued.
+ * flags & SNERF_BWD_ZERO_TABLE_GRAD: grad_table (n_entries*n_features floats, 46.5 MiB) is zero-filled BY THE CALL
+ * before anything is added to it, so the caller's per-step memset of the table gradient goes away: on the bf16 path
+ * the fill runs on the library's side stream under the colour/sigma kernels (which do not touch the table gradient)
+ * and is joined before the scatter-add -- or before the call returns when d_enc_out is given.  grad_w_* are still
+ * accumulated into. */
+#define SNERF_BWD_ZERO_TABLE_GRAD 1u
 int snerf_field_backward_ex(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M,
                             const float* table, const float* w_sigma, const float* w_color,
                             const float* grad_sigmas, const float* grad_rgbs, int precision, float* grad_table,
                             float* grad_w_sigma, float* grad_w_color, const void* saved, size_t saved_bytes,
-                            void* workspace, size_t workspace_bytes, float* d_enc_out, snerf_stream_t stream);
+                            void* workspace, size_t workspace_bytes, float* d_enc_out, uint32_t flags,
+                            snerf_stream_t stream);
 /* Scatter-add of levels [level_begin, level_end) only: xyzs [M,3] world space (normalised with bound in-kernel). */
 int snerf_hashgrid_backward_levels(const snerf_grid_desc* g, const float* xyzs, float bound, const float* grad_enc,
                                    uint32_t M, float* grad_table, uint32_t level_begin, uint32_t level_end,

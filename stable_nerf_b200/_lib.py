@@ -17,6 +17,7 @@ SNERF_MAX_LEVELS = 16
 SNERF_MAX_CHANNELS = 4
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
+BWD_ZERO_TABLE_GRAD = 1  # snerf_field_backward_ex flags (include/snerf.h)
 
 
 class GridDesc(ctypes.Structure):
@@ -105,7 +106,7 @@ SIGNATURES = {
     "snerf_pack_sd_condition_backward": (c_int, [_P, _U, _U, _U, _F, _P, _S]),
     "snerf_adam_step": (c_int, [_P, _P, _P, _P, _U, _F, _F, _F, _F, _F, c_int, _U, c_int, _S]),
     "snerf_field_backward_ex": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_size_t,
-                                        _P, c_size_t, _P, _S]),
+                                        _P, c_size_t, _P, _U, _S]),
     "snerf_hashgrid_backward_levels": (c_int, [POINTER(GridDesc), _P, _F, _P, _U, _P, _U, _U, _S]),
     "snerf_tc_selftest": (c_int, [_P, _P, _P, _U, _U, c_int, c_int, _S]),
     "snerf_debug_set_march_warp_max_rays": (None, [_U]),

@@ -76,23 +76,33 @@ int snerf_field_backward(const snerf_field_desc* f, const float* xyzs, const flo
                          int precision, float* grad_table, float* grad_w_sigma, float* grad_w_color, const void* saved,
                          size_t saved_bytes, void* workspace, size_t workspace_bytes, snerf_stream_t stream) {
   return snerf_field_backward_ex(f, xyzs, dirs, M, table, w_sigma, w_color, grad_sigmas, grad_rgbs, precision, grad_table,
-                                 grad_w_sigma, grad_w_color, saved, saved_bytes, workspace, workspace_bytes, nullptr, stream);
+                                 grad_w_sigma, grad_w_color, saved, saved_bytes, workspace, workspace_bytes, nullptr, 0u, stream);
 }
 
 int snerf_field_backward_ex(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                             const float* w_sigma, const float* w_color, const float* grad_sigmas, const float* grad_rgbs,
                             int precision, float* grad_table, float* grad_w_sigma, float* grad_w_color, const void* saved,
                             size_t saved_bytes, void* workspace, size_t workspace_bytes, float* d_enc_out,
-                            snerf_stream_t stream) {
+                            uint32_t flags, snerf_stream_t stream) {
   if (int e = check_field_desc(f)) return e;
-  if (M == 0) return SNERF_OK;
+  if (flags & ~SNERF_BWD_ZERO_TABLE_GRAD) return SNERF_E_BADARG;
+  const bool zero_table = (flags & SNERF_BWD_ZERO_TABLE_GRAD) != 0;
+  const size_t table_bytes = (size_t)f->grid.n_entries * f->grid.n_features * sizeof(float);
+  if (M == 0) {  // nothing to add, but the promise to leave a defined table gradient stands
+    if (zero_table && grad_table && cudaMemsetAsync(grad_table, 0, table_bytes, (cudaStream_t)stream) != cudaSuccess)
+      return (int)cudaGetLastError();
+    return SNERF_OK;
+  }
   if (!xyzs || !dirs || !table || !w_sigma || !w_color || !grad_sigmas || !grad_rgbs || !grad_table || !grad_w_sigma ||
       !grad_w_color || !workspace)
     return SNERF_E_BADARG;
   if (precision == SNERF_PRECISION_BF16)
     return field_tc_backward(f, xyzs, dirs, M, table, w_sigma, w_color, grad_sigmas, grad_rgbs, grad_table, grad_w_sigma,
-                             grad_w_color, saved, saved_bytes, workspace, workspace_bytes, (cudaStream_t)stream, d_enc_out);
+                             grad_w_color, saved, saved_bytes, workspace, workspace_bytes, (cudaStream_t)stream, d_enc_out,
+                             zero_table);
   if (precision != SNERF_PRECISION_FP32 || d_enc_out) return SNERF_E_UNSUPPORTED;
+  if (zero_table && cudaMemsetAsync(grad_table, 0, table_bytes, (cudaStream_t)stream) != cudaSuccess)
+    return (int)cudaGetLastError();
   return field_fp32_backward(f, xyzs, dirs, M, table, w_sigma, w_color, grad_sigmas, grad_rgbs, grad_table, grad_w_sigma,
                              grad_w_color, workspace, workspace_bytes, (cudaStream_t)stream);
 }

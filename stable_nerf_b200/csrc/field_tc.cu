@@ -1063,7 +1063,7 @@ static size_t bwd_smem(const PackedNet& n, int net) {
 // scatter-add, and the caller's stream joins them before the call returns.
 struct SideStream {
   cudaStream_t stream = nullptr;
-  cudaEvent_t fork[2] = {nullptr, nullptr}, join = nullptr;
+  cudaEvent_t fork[2] = {nullptr, nullptr}, join = nullptr, start = nullptr, zeroed = nullptr;
   bool ok = false;
 };
 static SideStream g_side[16];
@@ -1074,7 +1074,7 @@ static SideStream* side_stream() {
   if (!ss.ok) {
     if (ss.stream) return nullptr;  // creation failed before: stay on the caller's stream
     if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    for (cudaEvent_t* e : {&ss.fork[0], &ss.fork[1], &ss.join})
+    for (cudaEvent_t* e : {&ss.fork[0], &ss.fork[1], &ss.join, &ss.start, &ss.zeroed})
       if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     ss.ok = true;
   }
@@ -1083,9 +1083,19 @@ static SideStream* side_stream() {
 static uint32_t g_side_reduce = 1;  // measurement aid: 0 = the sums stay on the caller's stream
 void field_tc_set_side_reduce(uint32_t on) { g_side_reduce = on; }
 
-// s_reduce == s: in line.  Otherwise s_reduce waits for the kernel just launched on s (fork event k).
+// reduce_part == false: the net's kernel on s; true: the sum of its partials (on the side stream when there is one)
 template <int NET>
-static int launch_bwd(const TcParams& p, const PackedNet& n, uint32_t M, cudaStream_t s, SideStream* side) {
+static int launch_bwd(const TcParams& p, const PackedNet& n, uint32_t M, cudaStream_t s, SideStream* side, bool reduce_part) {
+  if (reduce_part) {
+    cudaStream_t sr = s;
+    if (side) {
+      if (cudaEventRecord(side->fork[NET], s) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork[NET], 0) != cudaSuccess)
+        return (int)cudaGetLastError();
+      sr = side->stream;
+    }
+    k_reduce_partials<<<dim3(div_up(p.n_params / 4, 256), kReduceGroups), 256, 0, sr>>>(p.dw_part, grid_for(M), p.n_params, p.grad_w);
+    return SNERF_OK;
+  }
   const uint32_t slots = bwd_slots(n, NET);
   const size_t smem = bwd_smem(n, NET);
   // sigma net: first/last-matrix weight gradients live in TMEM columns [384, 432) next to (n_mats - 2) hidden accumulators
@@ -1102,13 +1112,6 @@ static int launch_bwd(const TcParams& p, const PackedNet& n, uint32_t M, cudaStr
   } else {
     return SNERF_E_UNSUPPORTED;  // the activations of a tile leave no room for the weight ring
   }
-  cudaStream_t sr = s;
-  if (side) {
-    if (cudaEventRecord(side->fork[NET], s) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork[NET], 0) != cudaSuccess)
-      return (int)cudaGetLastError();
-    sr = side->stream;
-  }
-  k_reduce_partials<<<dim3(div_up(p.n_params / 4, 256), kReduceGroups), 256, 0, sr>>>(p.dw_part, grid_for(M), p.n_params, p.grad_w);
   return SNERF_OK;
 }
 
@@ -1160,7 +1163,7 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
 int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                       const float* w_sigma, const float* w_color, const float* grad_sigmas, const float* grad_rgbs,
                       float* grad_table, float* grad_w_sigma, float* grad_w_color, const void* saved, size_t saved_bytes,
-                      void* ws, size_t ws_bytes, cudaStream_t s, float* d_enc_out) {
+                      void* ws, size_t ws_bytes, cudaStream_t s, float* d_enc_out, bool zero_table) {
   if (ws_bytes < field_tc_workspace_bytes(f, M, 1)) return SNERF_E_WORKSPACE;
   if ((uintptr_t)d_enc_out & 15u) return SNERF_E_BADARG;
   if (saved && (saved_bytes < field_tc_saved_bytes(f, M) || ((uintptr_t)saved & 15u))) return SNERF_E_BADARG;
@@ -1210,11 +1213,25 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   p.n_params = sc.n_params;
   p.dbg = g_phase_net == 1 ? g_phase_dbg : nullptr;
   SideStream* side = g_side_reduce ? side_stream() : nullptr;
-  bool forked = false;
+  bool forked = false, zero_pending = false;
+  const size_t table_bytes = (size_t)f->grid.n_entries * f->grid.n_features * sizeof(float);
+  if (zero_table && !side && cudaMemsetAsync(grad_table, 0, table_bytes, s) != cudaSuccess) return (int)cudaGetLastError();
+  if (zero_table && side && cudaEventRecord(side->start, s) != cudaSuccess) return (int)cudaGetLastError();
   if (st & kStBwdColor) {
-    if (int e = launch_bwd<1>(p, pc, M, s, side)) return e;
+    if (int e = launch_bwd<1>(p, pc, M, s, nullptr, false)) return e;  // the kernel first: the fill takes the slots it leaves
+  }
+  if (zero_table && side) {
+    // the table gradient's zero fill: ordered after whatever preceded the call (start), not after the colour kernel
+    if (cudaStreamWaitEvent(side->stream, side->start, 0) != cudaSuccess ||
+        cudaMemsetAsync(grad_table, 0, table_bytes, side->stream) != cudaSuccess ||
+        cudaEventRecord(side->zeroed, side->stream) != cudaSuccess)
+      return (int)cudaGetLastError();
+    zero_pending = forked = true;
+  }
+  if (st & kStBwdColor) {
+    if (int e = launch_bwd<1>(p, pc, M, s, side, true)) return e;
     launches += 2;
-    forked = side != nullptr;
+    forked = forked || side != nullptr;
   }
   // 3. sigma net: recompute from the saved encoding + dgrad + wgrad + table scatter-add
   fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
@@ -1228,14 +1245,16 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   p.d_enc = d_enc_out ? d_enc_out : w.d_enc;  // caller-owned: it scatters the levels itself (snerf_hashgrid_backward_levels)
   p.dbg = g_phase_net == 0 ? g_phase_dbg : nullptr;
   if (st & kStBwdSigma) {
-    if (int e = launch_bwd<0>(p, ps, M, s, side)) return e;
+    if (int e = launch_bwd<0>(p, ps, M, s, nullptr, false)) return e;
+    if (int e = launch_bwd<0>(p, ps, M, s, side, true)) return e;
     launches += 2;
-    forked = side != nullptr;
+    forked = forked || side != nullptr;
   }
   // 4. table scatter-add of d loss / d encoding: its own full-occupancy kernel.  Running it inside the sigma kernel
   //    (dedicated warps, or in the compute warps' MMA waits) was measured and did not overlap: the reductions retire at
   //    ~1 lane/clk/SM and hold up the epilogues' shared-memory traffic, so the two costs add up either way.
   if ((st & kStBwdScatter) && !d_enc_out) {
+    if (zero_pending && cudaStreamWaitEvent(s, side->zeroed, 0) != cudaSuccess) return (int)cudaGetLastError();
     if (int e = launch_hashgrid_bwd(&f->grid, xyzs, true, f->bound, w.d_enc, M, grad_table, s)) return e;
   }
   if (forked) {  // join: the caller's stream continues once the sums have landed in grad_w_*

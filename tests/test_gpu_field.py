@@ -238,7 +238,7 @@ def test_backward_ex_with_level_grouped_scatter(setup, built_lib, cuda):
     d_enc = torch.empty(M, 32, device=cuda)
     check(lib.snerf_field_backward_ex(f, ptr(t["x"]), ptr(t["d"]), M, ptr(t["tab"]), ptr(t["ws"]), ptr(t["wc"]), ptr(t["gs"]),
                                       ptr(t["gr"]), 1, ptr(gt2), ptr(gws2), ptr(gwc2), ptr(saved), ns, ptr(wsb), nb,
-                                      ptr(d_enc), stream()), "bwd ex")
+                                      ptr(d_enc), 0, stream()), "bwd ex")
     torch.cuda.synchronize()
     assert float(gt2.abs().max()) == 0.0  # the table is the caller's job now
     for lb, le in ((0, 5), (5, 6), (6, 16)):
@@ -247,3 +247,63 @@ def test_backward_ex_with_level_grouped_scatter(setup, built_lib, cuda):
     torch.cuda.synchronize()
     assert rel_err(gt2.cpu().numpy(), gt) <= 1e-5 and rel_err(gws2.cpu().numpy(), gws) <= 1e-5
     assert rel_err(gwc2.cpu().numpy(), gwc) <= 1e-5
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("side_reduce", [1, 0])
+def test_backward_ex_zero_table_grad_flag(setup, built_lib, cuda, precision, side_reduce):
+    """SNERF_BWD_ZERO_TABLE_GRAD: the call zero-fills the table gradient itself (bf16 path: on the side stream under the
+    colour/sigma kernels) -- a table gradient full of garbage on entry gives what a caller-zeroed one gives; the weight
+    gradients are still accumulated into.  Also inside a CUDA graph (the fork and join are captured), replayed twice."""
+    from stable_nerf_b200._lib import BWD_ZERO_TABLE_GRAD, check, ptr, stream
+    lib = built_lib
+    C, M = 3, 2500
+    f, of, ws, table, wc = setup[C]
+    x, dirs = sample_points(M, seed=17)
+    rng = np.random.default_rng(6)
+    g_sig = rng.standard_normal(M).astype(np.float32)
+    g_rgb = rng.standard_normal((M, C)).astype(np.float32)
+    _, _, (gt, gws, gwc) = run_cuda_field(f, x, dirs, ws, table, wc, precision, g_sig, g_rgb, cuda)
+    t = {k: dev_t(v, cuda) for k, v in dict(x=x, d=dirs, ws=ws, tab=table, wc=wc, gs=g_sig, gr=g_rgb).items()}
+    nb = max(lib.snerf_field_workspace_bytes(f, M, precision, 0), lib.snerf_field_workspace_bytes(f, M, precision, 1))
+    wsb = torch.empty(max(nb, 256), dtype=torch.uint8, device=cuda)
+    gt2 = torch.full_like(t["tab"], 123.0)  # garbage on entry
+    gws2, gwc2 = torch.zeros_like(t["ws"]), torch.zeros_like(t["wc"])
+
+    def bwd():
+        check(lib.snerf_field_backward_ex(f, ptr(t["x"]), ptr(t["d"]), M, ptr(t["tab"]), ptr(t["ws"]), ptr(t["wc"]),
+                                          ptr(t["gs"]), ptr(t["gr"]), precision, ptr(gt2), ptr(gws2), ptr(gwc2), None, 0,
+                                          ptr(wsb), nb, None, BWD_ZERO_TABLE_GRAD, stream()), "bwd ex, zero flag")
+    # unknown flag bits are refused
+    rc = lib.snerf_field_backward_ex(f, ptr(t["x"]), ptr(t["d"]), M, ptr(t["tab"]), ptr(t["ws"]), ptr(t["wc"]), ptr(t["gs"]),
+                                     ptr(t["gr"]), precision, ptr(gt2), ptr(gws2), ptr(gwc2), None, 0, ptr(wsb), nb, None,
+                                     2, stream())
+    assert rc != 0
+    lib.snerf_debug_set_side_reduce(side_reduce)
+    try:
+        bwd()
+        torch.cuda.synchronize()
+        tol = 1e-5 if precision == 0 else 1e-4
+        assert rel_err(gt2.cpu().numpy(), gt) <= tol
+        assert rel_err(gws2.cpu().numpy(), gws) <= tol and rel_err(gwc2.cpu().numpy(), gwc) <= tol
+        if precision == 0:
+            return
+        # captured: table overwritten on every replay, weight gradients accumulated over the two replays
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        gt2.fill_(-7.0)
+        gws2.zero_()
+        gwc2.zero_()
+        g.replay()
+        gt2_first = gt2.clone()
+        g.replay()
+        torch.cuda.synchronize()
+        assert rel_err(gt2_first.cpu().numpy(), gt) <= tol and rel_err(gt2.cpu().numpy(), gt) <= tol
+        assert rel_err(gws2.cpu().numpy() / 2, gws) <= tol and rel_err(gwc2.cpu().numpy() / 2, gwc) <= tol
+    finally:
+        lib.snerf_debug_set_side_reduce(1)
