@@ -369,9 +369,11 @@ int snerf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_
  * flags & SNERF_BWD_ZERO_TABLE_GRAD: grad_table (n_entries*n_features floats, 46.5 MiB) is zero-filled BY THE CALL
  * before anything is added to it, so the caller's per-step memset of the table gradient goes away: on the bf16 path
  * the fill runs on the library's side stream under the colour/sigma kernels (which do not touch the table gradient)
- * and is joined before the scatter-add -- or before the call returns when d_enc_out is given.  grad_w_* are still
- * accumulated into. */
+ * and is joined before the scatter-add -- or before the call returns when d_enc_out is given.
+ * flags & SNERF_BWD_ZERO_W_GRADS: the same for grad_w_sigma and grad_w_color (zero-filled before the sums of the
+ * per-CTA partials are added).  Without a flag the respective gradient is accumulated into. */
 #define SNERF_BWD_ZERO_TABLE_GRAD 1u
+#define SNERF_BWD_ZERO_W_GRADS 2u
 int snerf_field_backward_ex(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M,
                             const float* table, const float* w_sigma, const float* w_color,
                             const float* grad_sigmas, const float* grad_rgbs, int precision, float* grad_table,

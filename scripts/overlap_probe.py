@@ -20,7 +20,7 @@ def main():
     bitfield, rays_o, rays_d, target = bench.workload(bench.RAYS_PER_GPU, seed=0)
     d_o, d_d, d_t = (torch.from_numpy(a).to(dev) for a in (rays_o, rays_d, target))
     steps = {}
-    for zero_side in (0, 1):   # TrainStep.zero_table_in_backward (SNERF_BWD_ZERO_TABLE_GRAD)
+    for zero_side in (0, 1):   # TrainStep.zero_in_backward (SNERF_BWD_ZERO_*)
         for red_side in (0, 1):
             torch.manual_seed(0)
             model = NeRFNetwork(channel_dim=bench.CHANNELS, precision="bf16").to(dev)
@@ -30,7 +30,7 @@ def main():
             model.train()
             lib.snerf_debug_set_side_reduce(red_side)
             ts = TrainStep(model, bench.RAYS_PER_GPU, max_steps=bench.MAX_STEPS)
-            ts.zero_table_in_backward = bool(zero_side)
+            ts.zero_in_backward = bool(zero_side)
             ts.warmup(d_o, d_d, d_t)   # the graph is captured with the current settings
             steps[(zero_side, red_side)] = (ts, model)
     lib.snerf_debug_set_side_reduce(1)
@@ -54,7 +54,7 @@ def main():
         for p, q in zip(model.parameters(), ref_model.parameters()):
             if p.numel():
                 diffs.append(float((p.grad - q.grad).abs().max() / (q.grad.abs().max() + 1e-30)))
-        print(f"zero_table_in_backward={k[0]} reduce_side={k[1]}: ms/step min {min(v):.4f} median {sorted(v)[len(v)//2]:.4f}  "
+        print(f"zero_in_backward={k[0]} reduce_side={k[1]}: ms/step min {min(v):.4f} median {sorted(v)[len(v)//2]:.4f}  "
               f"loss {float(ts.loss):.6f}  max rel grad diff vs (0,0) {max(diffs):.2e}", flush=True)
 
 

@@ -18,6 +18,7 @@ SNERF_MAX_CHANNELS = 4
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 BWD_ZERO_TABLE_GRAD = 1  # snerf_field_backward_ex flags (include/snerf.h)
+BWD_ZERO_W_GRADS = 2
 
 
 class GridDesc(ctypes.Structure):

@@ -85,24 +85,28 @@ int snerf_field_backward_ex(const snerf_field_desc* f, const float* xyzs, const 
                             size_t saved_bytes, void* workspace, size_t workspace_bytes, float* d_enc_out,
                             uint32_t flags, snerf_stream_t stream) {
   if (int e = check_field_desc(f)) return e;
-  if (flags & ~SNERF_BWD_ZERO_TABLE_GRAD) return SNERF_E_BADARG;
-  const bool zero_table = (flags & SNERF_BWD_ZERO_TABLE_GRAD) != 0;
+  if (flags & ~(SNERF_BWD_ZERO_TABLE_GRAD | SNERF_BWD_ZERO_W_GRADS)) return SNERF_E_BADARG;
   const size_t table_bytes = (size_t)f->grid.n_entries * f->grid.n_features * sizeof(float);
-  if (M == 0) {  // nothing to add, but the promise to leave a defined table gradient stands
-    if (zero_table && grad_table && cudaMemsetAsync(grad_table, 0, table_bytes, (cudaStream_t)stream) != cudaSuccess)
-      return (int)cudaGetLastError();
-    return SNERF_OK;
-  }
+  auto zero_fills = [&]() {  // the fp32 path and the empty call: in line on the caller's stream
+    cudaError_t e = cudaSuccess;
+    cudaStream_t z = (cudaStream_t)stream;
+    if ((flags & SNERF_BWD_ZERO_W_GRADS) && grad_w_color)
+      e = cudaMemsetAsync(grad_w_color, 0, (size_t)color_shape(f).n_params * sizeof(float), z);
+    if ((flags & SNERF_BWD_ZERO_W_GRADS) && grad_w_sigma && e == cudaSuccess)
+      e = cudaMemsetAsync(grad_w_sigma, 0, (size_t)sigma_shape(f).n_params * sizeof(float), z);
+    if ((flags & SNERF_BWD_ZERO_TABLE_GRAD) && grad_table && e == cudaSuccess) e = cudaMemsetAsync(grad_table, 0, table_bytes, z);
+    return e == cudaSuccess ? SNERF_OK : (int)cudaGetLastError();
+  };
+  if (M == 0) return zero_fills();  // nothing to add, but the promise to leave defined gradients stands
   if (!xyzs || !dirs || !table || !w_sigma || !w_color || !grad_sigmas || !grad_rgbs || !grad_table || !grad_w_sigma ||
       !grad_w_color || !workspace)
     return SNERF_E_BADARG;
   if (precision == SNERF_PRECISION_BF16)
     return field_tc_backward(f, xyzs, dirs, M, table, w_sigma, w_color, grad_sigmas, grad_rgbs, grad_table, grad_w_sigma,
                              grad_w_color, saved, saved_bytes, workspace, workspace_bytes, (cudaStream_t)stream, d_enc_out,
-                             zero_table);
+                             flags);
   if (precision != SNERF_PRECISION_FP32 || d_enc_out) return SNERF_E_UNSUPPORTED;
-  if (zero_table && cudaMemsetAsync(grad_table, 0, table_bytes, (cudaStream_t)stream) != cudaSuccess)
-    return (int)cudaGetLastError();
+  if (int e = zero_fills()) return e;
   return field_fp32_backward(f, xyzs, dirs, M, table, w_sigma, w_color, grad_sigmas, grad_rgbs, grad_table, grad_w_sigma,
                              grad_w_color, workspace, workspace_bytes, (cudaStream_t)stream);
 }

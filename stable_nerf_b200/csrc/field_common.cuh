@@ -82,6 +82,6 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
 int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                       const float* w_sigma, const float* w_color, const float* grad_sigmas, const float* grad_rgbs,
                       float* grad_table, float* grad_w_sigma, float* grad_w_color, const void* saved, size_t saved_bytes,
-                      void* ws, size_t ws_bytes, cudaStream_t s, float* d_enc_out = nullptr, bool zero_table = false);
+                      void* ws, size_t ws_bytes, cudaStream_t s, float* d_enc_out = nullptr, uint32_t flags = 0);
 
 }  // namespace snerf

@@ -1127,10 +1127,23 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
   const PackedNet ps = make_packed(sigma_shape(f)), pc = make_packed(color_shape(f));
   const uint32_t st = g_stage_mask;
   unsigned launches = 0;
+  // Training forward (hand-off given; the step is replayed as a graph, so the extra stream calls cost nothing per step):
+  // the weight packing depends on the parameters only and runs on the side stream under the gather.  The inference
+  // loop's calls stay on one stream: they are launch-bound and three more API calls per call would show.
+  SideStream* side = (saved && g_side_reduce) ? side_stream() : nullptr;
+  bool pack_forked = false;
   if (st & kStFwdPack) {
-    k_pack_weights<<<dim3(div_up(std::max(ps.total_bytes, pc.total_bytes) / 16, 256), sigma_only ? 1 : 2), 256, 0, s>>>(
+    cudaStream_t sp = s;
+    if (side) {
+      if (cudaEventRecord(side->start, s) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->start, 0) != cudaSuccess)
+        return (int)cudaGetLastError();
+      sp = side->stream;
+      pack_forked = true;
+    }
+    k_pack_weights<<<dim3(div_up(std::max(ps.total_bytes, pc.total_bytes) / 16, 256), sigma_only ? 1 : 2), 256, 0, sp>>>(
         w_sigma, ps, w.wimg_sigma, w_color, pc, w.wimg_color);
     launches++;
+    if (pack_forked && cudaEventRecord(side->join, side->stream) != cudaSuccess) return (int)cudaGetLastError();
   }
   TcParams p;
   fill_common(p, f, ps, M, xyzs, dirs, table, w.wimg_sigma);
@@ -1143,6 +1156,7 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
   }
   p.enc = w.enc;
   p.geo_f32 = geo_feat;
+  if (pack_forked && cudaStreamWaitEvent(s, side->join, 0) != cudaSuccess) return (int)cudaGetLastError();
   if (st & kStFwdSigma) {
     if (int e = set_smem(k_field_fwd<0>, fwd_smem(ps))) return e;
     k_field_fwd<0><<<grid_for(M), kFwdThreads, fwd_smem(ps), s>>>(p);
@@ -1163,7 +1177,7 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
 int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                       const float* w_sigma, const float* w_color, const float* grad_sigmas, const float* grad_rgbs,
                       float* grad_table, float* grad_w_sigma, float* grad_w_color, const void* saved, size_t saved_bytes,
-                      void* ws, size_t ws_bytes, cudaStream_t s, float* d_enc_out, bool zero_table) {
+                      void* ws, size_t ws_bytes, cudaStream_t s, float* d_enc_out, uint32_t flags) {
   if (ws_bytes < field_tc_workspace_bytes(f, M, 1)) return SNERF_E_WORKSPACE;
   if ((uintptr_t)d_enc_out & 15u) return SNERF_E_BADARG;
   if (saved && (saved_bytes < field_tc_saved_bytes(f, M) || ((uintptr_t)saved & 15u))) return SNERF_E_BADARG;
@@ -1215,15 +1229,24 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   SideStream* side = g_side_reduce ? side_stream() : nullptr;
   bool forked = false, zero_pending = false;
   const size_t table_bytes = (size_t)f->grid.n_entries * f->grid.n_features * sizeof(float);
-  if (zero_table && !side && cudaMemsetAsync(grad_table, 0, table_bytes, s) != cudaSuccess) return (int)cudaGetLastError();
-  if (zero_table && side && cudaEventRecord(side->start, s) != cudaSuccess) return (int)cudaGetLastError();
+  const bool zero_table = (flags & SNERF_BWD_ZERO_TABLE_GRAD) != 0, zero_w = (flags & SNERF_BWD_ZERO_W_GRADS) != 0;
+  auto zero_fills = [&](cudaStream_t z) {  // the call's own zero fills: table 46.5 MiB, MLP weights 0.4 MB
+    cudaError_t e = cudaSuccess;
+    if (zero_w) e = cudaMemsetAsync(grad_w_color, 0, (size_t)sc.n_params * sizeof(float), z);
+    if (zero_w && e == cudaSuccess) e = cudaMemsetAsync(grad_w_sigma, 0, (size_t)ss.n_params * sizeof(float), z);
+    if (zero_table && e == cudaSuccess) e = cudaMemsetAsync(grad_table, 0, table_bytes, z);
+    return e;
+  };
+  const bool zero_any = zero_table || zero_w;
+  if (zero_any && !side && zero_fills(s) != cudaSuccess) return (int)cudaGetLastError();
+  if (zero_any && side && cudaEventRecord(side->start, s) != cudaSuccess) return (int)cudaGetLastError();
   if (st & kStBwdColor) {
     if (int e = launch_bwd<1>(p, pc, M, s, nullptr, false)) return e;  // the kernel first: the fill takes the slots it leaves
   }
-  if (zero_table && side) {
-    // the table gradient's zero fill: ordered after whatever preceded the call (start), not after the colour kernel
-    if (cudaStreamWaitEvent(side->stream, side->start, 0) != cudaSuccess ||
-        cudaMemsetAsync(grad_table, 0, table_bytes, side->stream) != cudaSuccess ||
+  if (zero_any && side) {
+    // the zero fills: ordered after whatever preceded the call (start), not after the colour kernel; the sums of the
+    // partials follow them on the same (in-order) side stream
+    if (cudaStreamWaitEvent(side->stream, side->start, 0) != cudaSuccess || zero_fills(side->stream) != cudaSuccess ||
         cudaEventRecord(side->zeroed, side->stream) != cudaSuccess)
       return (int)cudaGetLastError();
     zero_pending = forked = true;

@@ -75,7 +75,7 @@ class TrainStep:
         self.loss_scale = loss_scale
         self.fused, self.perturb, self.dt_gamma = bool(fused), bool(perturb), dt_gamma
         self.fuse_tail = True  # whole steps: composite forward + L1 + composite backward in one launch
-        self.zero_table_in_backward = True  # the table gradient's zero fill belongs to the field backward call
+        self.zero_in_backward = True  # the gradients' zero fills belong to the field backward call
         self._bufs = None
         self._mark = None
         self._graph_fwd = self._graph_bwd = None
@@ -219,14 +219,12 @@ class TrainStep:
             return self._fused_backward(b, M, mark)
         mark("start")
         if not self._opt_zeroes:
-            # The MLP gradients (0.4 MB) are zeroed here; the table's 46.5 MiB are zero-filled by the field backward
-            # itself (SNERF_BWD_ZERO_TABLE_GRAD), on the library's side stream under the colour/sigma kernels.
+            # The field's gradients (table 46.5 MiB, MLP weights 0.4 MB) are zero-filled by the field backward itself
+            # (SNERF_BWD_ZERO_*), on the library's side stream under the colour kernel; anything else is zeroed here.
             # (Zeroing everything on a side stream under the march was measured: +5 us/step -- the fills slow the
             # latency-bound march down by more than their own 12 us.)
             for p in self.params:
-                if self.zero_table_in_backward and p is m.sigma_net.params:
-                    p.grad[:nm].zero_()
-                else:
+                if not (self.zero_in_backward and (p is sp or p is cp)):
                     p.grad.zero_()
         counter = m.step_counter[m.local_step % 16]
         counter.zero_()
@@ -294,7 +292,7 @@ class TrainStep:
             b["g_sig"].mul_(m.density_scale)
         if composite:
             mark("composite_bwd")
-        flags = _lib.BWD_ZERO_TABLE_GRAD if (self.zero_table_in_backward and not self._opt_zeroes) else 0
+        flags = (_lib.BWD_ZERO_TABLE_GRAD | _lib.BWD_ZERO_W_GRADS) if (self.zero_in_backward and not self._opt_zeroes) else 0
         chk(lib.snerf_field_backward_ex(m.fdesc, P(b["xyzs"]), P(b["dirs"]), M, P(spd[nm:]), P(spd[:nm]), P(cp.detach()),
                                         P(b["g_sig"]), P(b["g_rgb"]), prec, P(sp.grad[nm:]), P(sp.grad[:nm]), P(cp.grad),
                                         P(b["saved"]), b["saved_bytes"], P(b["field_ws"]), b["field_ws_bytes"],

@@ -251,11 +251,15 @@ def test_backward_ex_with_level_grouped_scatter(setup, built_lib, cuda):
 
 @pytest.mark.parametrize("precision", [0, 1])
 @pytest.mark.parametrize("side_reduce", [1, 0])
-def test_backward_ex_zero_table_grad_flag(setup, built_lib, cuda, precision, side_reduce):
+@pytest.mark.parametrize("flags", [1, 3])
+def test_backward_ex_zero_table_grad_flag(setup, built_lib, cuda, precision, side_reduce, flags):
     """SNERF_BWD_ZERO_TABLE_GRAD: the call zero-fills the table gradient itself (bf16 path: on the side stream under the
     colour/sigma kernels) -- a table gradient full of garbage on entry gives what a caller-zeroed one gives; the weight
-    gradients are still accumulated into.  Also inside a CUDA graph (the fork and join are captured), replayed twice."""
-    from stable_nerf_b200._lib import BWD_ZERO_TABLE_GRAD, check, ptr, stream
+    gradients are accumulated into unless SNERF_BWD_ZERO_W_GRADS is set too.  Also inside a CUDA graph (the fork and join
+    are captured), replayed twice."""
+    from stable_nerf_b200._lib import BWD_ZERO_TABLE_GRAD, BWD_ZERO_W_GRADS, check, ptr, stream
+    assert (BWD_ZERO_TABLE_GRAD, BWD_ZERO_W_GRADS) == (1, 2)
+    zero_w = bool(flags & BWD_ZERO_W_GRADS)
     lib = built_lib
     C, M = 3, 2500
     f, of, ws, table, wc = setup[C]
@@ -269,15 +273,18 @@ def test_backward_ex_zero_table_grad_flag(setup, built_lib, cuda, precision, sid
     wsb = torch.empty(max(nb, 256), dtype=torch.uint8, device=cuda)
     gt2 = torch.full_like(t["tab"], 123.0)  # garbage on entry
     gws2, gwc2 = torch.zeros_like(t["ws"]), torch.zeros_like(t["wc"])
+    if zero_w:
+        gws2.fill_(55.0)
+        gwc2.fill_(-55.0)
 
     def bwd():
         check(lib.snerf_field_backward_ex(f, ptr(t["x"]), ptr(t["d"]), M, ptr(t["tab"]), ptr(t["ws"]), ptr(t["wc"]),
                                           ptr(t["gs"]), ptr(t["gr"]), precision, ptr(gt2), ptr(gws2), ptr(gwc2), None, 0,
-                                          ptr(wsb), nb, None, BWD_ZERO_TABLE_GRAD, stream()), "bwd ex, zero flag")
+                                          ptr(wsb), nb, None, flags, stream()), "bwd ex, zero flag")
     # unknown flag bits are refused
     rc = lib.snerf_field_backward_ex(f, ptr(t["x"]), ptr(t["d"]), M, ptr(t["tab"]), ptr(t["ws"]), ptr(t["wc"]), ptr(t["gs"]),
                                      ptr(t["gr"]), precision, ptr(gt2), ptr(gws2), ptr(gwc2), None, 0, ptr(wsb), nb, None,
-                                     2, stream())
+                                     4, stream())
     assert rc != 0
     lib.snerf_debug_set_side_reduce(side_reduce)
     try:
@@ -304,6 +311,7 @@ def test_backward_ex_zero_table_grad_flag(setup, built_lib, cuda, precision, sid
         g.replay()
         torch.cuda.synchronize()
         assert rel_err(gt2_first.cpu().numpy(), gt) <= tol and rel_err(gt2.cpu().numpy(), gt) <= tol
-        assert rel_err(gws2.cpu().numpy() / 2, gws) <= tol and rel_err(gwc2.cpu().numpy() / 2, gwc) <= tol
+        k = 1 if zero_w else 2
+        assert rel_err(gws2.cpu().numpy() / k, gws) <= tol and rel_err(gwc2.cpu().numpy() / k, gwc) <= tol
     finally:
         lib.snerf_debug_set_side_reduce(1)
