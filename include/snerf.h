@@ -407,6 +407,10 @@ void snerf_debug_set_side_reduce(uint32_t on);
 /* Measurement aid: levels with resolution <= res merge equal cells inside a warp before the scatter-add (default 300). */
 void snerf_debug_set_dedupe_max_res(uint32_t res);
 
+/* Round-2 candidate, off by default (unmeasured): 1 = the scatter-add's segmented scan stops at the depth the warp's
+ * longest run of equal cells needs instead of always five steps; the sums are the same bits. */
+void snerf_debug_set_scatter_adaptive_scan(uint32_t on);
+
 /* Timing probe of the tcgen05 building blocks (one CTA, clock64): out = 32 int64 on the device.  Not on the hot path. */
 int snerf_tc_probe(long long* out, int variant, snerf_stream_t stream);
 

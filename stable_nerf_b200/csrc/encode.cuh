@@ -124,6 +124,11 @@ __device__ __forceinline__ void red_pair(float2* __restrict__ grad_table, uint32
       : "memory");
 }
 
+// kAdaptive: the scan stops at the depth the warp's longest run needs.  Step d adds something only to a lane whose last d
+// lanes all continue a run, so with z = ballot(!head) and r_1 = z, r_2d = r_d & (r_d >> d) (bit i of r_d: lanes
+// i..i+d-1 all continue), step d and every later one are no-ops for the whole warp once r_d == 0: same bits, fewer
+// shuffles on the levels whose cells are a march step or two wide.  (Round-2 candidate: unmeasured, off by default.)
+template <bool kAdaptive = false>
 __device__ __forceinline__ void scatter_level(const LevelInfo& li, const Cell& c, float2 gv, bool active, bool dedupe,
                                               bool pairing, int lane, float2* __restrict__ grad_table) {
   uint32_t idx[8];
@@ -142,8 +147,13 @@ __device__ __forceinline__ void scatter_level(const LevelInfo& li, const Cell& c
     const uint32_t p0 = __shfl_up_sync(kFull, k0, 1), p1 = __shfl_up_sync(kFull, k1, 1);
     const bool head = lane == 0 || p0 != k0 || p1 != k1;
     bool f = head;  // a run head lies inside the span summed so far
+    uint32_t zr = kAdaptive ? ~__ballot_sync(kFull, head) : 0u;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
+      if (kAdaptive) {
+        if (zr == 0u) break;  // warp-uniform: no lane has d continuing lanes behind it
+        zr &= zr >> d;
+      }
       float u[16];
 #pragma unroll
       for (int k = 0; k < 16; k++) u[k] = __shfl_up_sync(kFull, v[k], d);

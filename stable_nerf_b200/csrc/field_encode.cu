@@ -87,7 +87,9 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_fwd(snerf_grid_desc g,
 //   * samples whose gradient is exactly zero (padding, terminated rays) issue nothing.
 static uint32_t g_dedupe_max_res = 300;  // tunable through snerf_debug_set_dedupe_max_res (measurement aid)
 
-template <bool kNormalize>
+static uint32_t g_scatter_adaptive = 0;   // snerf_debug_set_scatter_adaptive_scan: scan depth follows the longest run
+
+template <bool kNormalize, bool kAdaptive = false>
 __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g, const float* __restrict__ x,
                                                               float bound, const float* __restrict__ grad_enc,
                                                               uint32_t M, float2* __restrict__ grad_table,
@@ -121,7 +123,8 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g,
     const LevelInfo li = level_info(g, l);
     const uint32_t sc = s < ns ? s : 0u;
     const Cell c = grid_cell(xs[sc * 3], xs[sc * 3 + 1], xs[sc * 3 + 2], li.scale);
-    scatter_level(li, c, gv, active, li.res <= (dedupe_max_res & 0x7fffffffu), !(dedupe_max_res >> 31), lane, grad_table);
+    scatter_level<kAdaptive>(li, c, gv, active, li.res <= (dedupe_max_res & 0x7fffffffu), !(dedupe_max_res >> 31), lane,
+                             grad_table);
   }
 }
 
@@ -176,7 +179,10 @@ int launch_hashgrid_bwd(const snerf_grid_desc* g, const float* x, bool normalize
   const uint32_t blocks = div_up(M, kEncTile);
   level_end = min(level_end, g->n_levels);
   if (level_begin >= level_end) return SNERF_OK;
-  if (normalize)
+  if (normalize && g_scatter_adaptive)
+    k_hashgrid_bwd<true, true><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, grad_enc, M, reinterpret_cast<float2*>(grad_table),
+                                                               g_dedupe_max_res, level_begin, level_end);
+  else if (normalize)
     k_hashgrid_bwd<true><<<blocks, kEncThreads, 0, s>>>(*g, x, bound, grad_enc, M, reinterpret_cast<float2*>(grad_table),
                                                          g_dedupe_max_res, level_begin, level_end);
   else
@@ -192,6 +198,7 @@ using namespace snerf;
 extern "C" {
 
 void snerf_debug_set_dedupe_max_res(uint32_t res) { g_dedupe_max_res = res; }
+void snerf_debug_set_scatter_adaptive_scan(uint32_t on) { g_scatter_adaptive = on; }
 
 int snerf_hashgrid_forward(const snerf_grid_desc* g, const float* x01, const float* table, uint32_t M, float* enc,
                            snerf_stream_t stream) {

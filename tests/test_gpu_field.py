@@ -315,3 +315,37 @@ def test_backward_ex_zero_table_grad_flag(setup, built_lib, cuda, precision, sid
         assert rel_err(gws2.cpu().numpy() / k, gws) <= tol and rel_err(gwc2.cpu().numpy() / k, gwc) <= tol
     finally:
         lib.snerf_debug_set_side_reduce(1)
+
+
+def test_scatter_adaptive_scan_depth_gives_the_same_sums(setup, built_lib, cuda):
+    """snerf_debug_set_scatter_adaptive_scan (round-2 candidate, off by default): the segmented scan that merges equal
+    cells stops at the depth the warp's longest run needs.  Samples along rays (long runs on coarse levels, short ones
+    on fine levels, isolated and zero-gradient samples in between) must give the sums of the five-step scan; the two
+    launches differ in the order of their fp32 reductions only."""
+    from stable_nerf_b200._lib import check, ptr, stream
+    lib = built_lib
+    f = setup[3][0]
+    rng = np.random.default_rng(21)
+    n_rays, per = 96, 40
+    o = rng.uniform(-0.9, 0.9, (n_rays, 1, 3))
+    d = rng.standard_normal((n_rays, 1, 3))
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    step = rng.choice([0.0005, 0.0034, 0.02], (n_rays, 1, 1))       # far below / at / above a fine cell's width
+    x = np.clip(o + d * step * np.arange(per)[None, :, None], -1, 1).reshape(-1, 3).astype(np.float32)
+    M = x.shape[0]
+    g = rng.standard_normal((M, 32)).astype(np.float32)
+    g[rng.random(M) < 0.2] = 0                                          # terminated samples carry exact zeros
+    t_x, t_g = dev_t(x, cuda), dev_t(g, cuda)
+    out = {}
+    try:
+        for adaptive in (0, 1):
+            lib.snerf_debug_set_scatter_adaptive_scan(adaptive)
+            gt = torch.zeros(f.grid.n_entries * 2, device=cuda)
+            check(lib.snerf_hashgrid_backward_levels(f.grid, ptr(t_x), f.bound, ptr(t_g), M, ptr(gt), 0, 16, stream()),
+                  "scatter levels")
+            torch.cuda.synchronize()
+            out[adaptive] = gt.cpu().numpy()
+    finally:
+        lib.snerf_debug_set_scatter_adaptive_scan(0)
+    assert np.abs(out[0]).max() > 0
+    assert rel_err(out[1], out[0]) <= 1e-5
