@@ -411,6 +411,10 @@ void snerf_debug_set_dedupe_max_res(uint32_t res);
  * longest run of equal cells needs instead of always five steps; the sums are the same bits. */
 void snerf_debug_set_scatter_adaptive_scan(uint32_t on);
 
+/* Round-2 candidate, off by default (unmeasured): 1 = snerf_composite_l1_train requests a ray's next 32 sample rows
+ * before the scans of the current 32 (the loads move, the arithmetic and its bits do not). */
+void snerf_debug_set_tail_prefetch(uint32_t on);
+
 /* Timing probe of the tcgen05 building blocks (one CTA, clock64): out = 32 int64 on the device.  Not on the hot path. */
 int snerf_tc_probe(long long* out, int variant, snerf_stream_t stream);
 

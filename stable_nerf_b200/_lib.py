@@ -115,6 +115,7 @@ SIGNATURES = {
     "snerf_debug_set_side_reduce": (None, [_U]),
     "snerf_debug_set_dedupe_max_res": (None, [_U]),
     "snerf_debug_set_scatter_adaptive_scan": (None, [_U]),
+    "snerf_debug_set_tail_prefetch": (None, [_U]),
     "snerf_tc_probe": (c_int, [_P, c_int, _S]),
     "snerf_debug_phase_buffer": (None, [_P, c_int]),
     "snerf_composite_l1_train": (c_int, [_P, _P, _P, _P, _U, _U, _F, _U, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,

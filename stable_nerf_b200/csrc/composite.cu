@@ -43,9 +43,26 @@ __device__ __forceinline__ void store_rgb(float* __restrict__ out, size_t i, con
 
 // ------------------------------------------------------------------------------------------------ train forward
 
+// The raw inputs of one round of 32 samples (kPrefetch: fetched a round ahead of their use)
+template <int C>
+struct SampleRow {
+  float sigma;
+  float2 dl;
+  float c[C];
+  __device__ __forceinline__ void load(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                       const float* __restrict__ deltas, size_t row) {
+    dl = __ldg(reinterpret_cast<const float2*>(deltas) + row);
+    sigma = __ldg(sigmas + row);
+    load_rgb<C>(rgbs, row, c);
+  }
+};
+
 // One ray's front-to-back compositing by a warp (raymarching.cu:501-601): on return every lane holds weights_sum,
 // depth and the channels of the ray.
-template <int C>
+// kPrefetch (round-2 candidate, unmeasured, off by default): a long ray is a serial chain of rounds, each starting with
+// a trip to L2/HBM; with the next round's rows requested before the current round's scans the trips overlap the scans.
+// Only the loads move: every arithmetic operation and its operands are the same, so are the bits.
+template <int C, bool kPrefetch = false>
 __device__ __forceinline__ void composite_ray_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                                   const float* __restrict__ deltas, uint32_t offset, uint32_t num_steps,
                                                   uint32_t M, float T_thresh, int lane, float& ws, float& d, float (&ch)[C]) {
@@ -55,13 +72,24 @@ __device__ __forceinline__ void composite_ray_fwd(const float* __restrict__ sigm
   for (int k = 0; k < C; k++) ch[k] = 0.f;
   if (num_steps != 0 && offset + num_steps <= M) {
     float T_run = 1.f, t_run = 0.f;
+    SampleRow<C> nxt{};
+    if (kPrefetch && (uint32_t)lane < num_steps) nxt.load(sigmas, rgbs, deltas, (size_t)offset + lane);
     for (uint32_t base = 0; base < num_steps; base += 32) {
       const uint32_t i = base + lane;
       const bool valid = i < num_steps;
       float alpha = 0.f, dz = 0.f, c[C];
 #pragma unroll
       for (int k = 0; k < C; k++) c[k] = 0.f;
-      if (valid) {
+      if (kPrefetch) {
+        const SampleRow<C> cur = nxt;
+        if (i + 32u < num_steps) nxt.load(sigmas, rgbs, deltas, (size_t)offset + i + 32u);
+        if (valid) {
+          alpha = alpha_of(cur.sigma, cur.dl.x);
+          dz = cur.dl.y;
+#pragma unroll
+          for (int k = 0; k < C; k++) c[k] = cur.c[k];
+        }
+      } else if (valid) {
         const float2 dl = __ldg(reinterpret_cast<const float2*>(deltas) + offset + i);
         alpha = alpha_of(__ldg(sigmas + offset + i), dl.x);
         dz = dl.y;
@@ -118,7 +146,7 @@ __global__ void __launch_bounds__(kCompThreads) k_composite_train_fwd(const floa
 
 // One ray's compositing backward by a warp (raymarching.cu:614-726): gi = d loss / d image of the ray, fin = its
 // composited channels, gws_term = d loss / d weights_sum * (1 - weights_sum).  Writes every sample row the ray owns.
-template <int C>
+template <int C, bool kPrefetch = false>
 __device__ __forceinline__ void composite_ray_bwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                                   const float* __restrict__ deltas, uint32_t offset, uint32_t num_steps,
                                                   uint32_t M, float T_thresh, int lane, float gws_term, const float (&gi)[C],
@@ -140,6 +168,8 @@ __device__ __forceinline__ void composite_ray_bwd(const float* __restrict__ sigm
 
   float T_run = 1.f;
   bool done = false;
+  SampleRow<C> nxt{};
+  if (kPrefetch && (uint32_t)lane < num_steps) nxt.load(sigmas, rgbs, deltas, (size_t)offset + lane);
   for (uint32_t base = 0; base < num_steps; base += 32) {
     const uint32_t i = base + lane;
     const bool valid = i < num_steps;
@@ -153,7 +183,16 @@ __device__ __forceinline__ void composite_ray_bwd(const float* __restrict__ sigm
     float alpha = 0.f, d0 = 0.f, c[C];
 #pragma unroll
     for (int k = 0; k < C; k++) c[k] = 0.f;
-    if (valid) {
+    if (kPrefetch) {
+      const SampleRow<C> cur = nxt;
+      if (i + 32u < num_steps) nxt.load(sigmas, rgbs, deltas, (size_t)offset + i + 32u);
+      if (valid) {
+        d0 = cur.dl.x;
+        alpha = alpha_of(cur.sigma, d0);
+#pragma unroll
+        for (int k = 0; k < C; k++) c[k] = cur.c[k];
+      }
+    } else if (valid) {
       d0 = __ldg(reinterpret_cast<const float2*>(deltas) + offset + i).x;
       alpha = alpha_of(__ldg(sigmas + offset + i), d0);
       load_rgb<C>(rgbs, (size_t)offset + i, c);
@@ -295,7 +334,7 @@ __global__ void __launch_bounds__(1024) k_l1_loss_backward(const float* __restri
 // channels still in registers.  The loss VALUE is a sum over all rays: the last CTA to finish adds |pred - target| in
 // exactly the order of k_l1_loss_backward's single 1024-thread block (32 virtual warps), so the number is reproducible
 // and equal to the unfused path's bit for bit.
-template <int C>
+template <int C, bool kPrefetch = false>
 __global__ void __launch_bounds__(kCompThreads) k_composite_l1_train(
     const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
     const int32_t* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh, const float* __restrict__ target,
@@ -317,7 +356,7 @@ __global__ void __launch_bounds__(kCompThreads) k_composite_l1_train(
   if (n < N) {
     const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
     float ws, d, ch[C];
-    composite_ray_fwd<C>(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane, ws, d, ch);
+    composite_ray_fwd<C, kPrefetch>(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane, ws, d, ch);
     // blend, loss gradient (k_l1_loss_backward's arithmetic, op for op); every lane computes the same values
     float bg[C], pred[C], tgt[C], g[C], gws = 0.f;
 #pragma unroll
@@ -342,8 +381,8 @@ __global__ void __launch_bounds__(kCompThreads) k_composite_l1_train(
       }
     }
     if (num_steps != 0 && offset < M)
-      composite_ray_bwd<C>(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane, gws * (1.0f - ws), g, ch, grad_sigmas,
-                           grad_rgbs);
+      composite_ray_bwd<C, kPrefetch>(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane, gws * (1.0f - ws), g, ch,
+                                      grad_sigmas, grad_rgbs);
   }
 
   // ---- loss value: the last CTA sums, in the order of k_l1_loss_backward's 1024-thread block
@@ -429,7 +468,11 @@ using namespace snerf;
     default: return SNERF_E_CHANNELS;                \
   }
 
+static uint32_t g_tail_prefetch = 0;  // snerf_debug_set_tail_prefetch: the one-launch tail fetches its rows a round ahead
+
 extern "C" {
+
+void snerf_debug_set_tail_prefetch(uint32_t on) { g_tail_prefetch = on; }
 
 int snerf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays,
                                        uint32_t M, uint32_t N, float T_thresh, uint32_t channel_dim, float* weights_sum,
@@ -520,6 +563,13 @@ int snerf_composite_l1_train(const float* sigmas, const float* rgbs, const float
   if (M > 0 && (!sigmas || !rgbs || !deltas || !grad_sigmas || !grad_rgbs)) return SNERF_E_BADARG;
   if (depth_norm && (!nears || !fars)) return SNERF_E_BADARG;
   const uint32_t blocks = div_up(N, kCompThreads / 32);
+  if (g_tail_prefetch) {
+    SNERF_DISPATCH_C(channel_dim, (k_composite_l1_train<kC, true><<<blocks, kCompThreads, 0, (cudaStream_t)stream>>>(
+                                      sigmas, rgbs, deltas, rays, M, N, T_thresh, target, bg_color, bg_scalar, grad_scale,
+                                      nears, fars, weights_sum, depth, image, pred_image, depth_norm, loss, grad_sigmas,
+                                      grad_rgbs, n_samples, counter)));
+    return finish_launch();
+  }
   SNERF_DISPATCH_C(channel_dim, (k_composite_l1_train<kC><<<blocks, kCompThreads, 0, (cudaStream_t)stream>>>(
                                     sigmas, rgbs, deltas, rays, M, N, T_thresh, target, bg_color, bg_scalar, grad_scale, nears,
                                     fars, weights_sum, depth, image, pred_image, depth_norm, loss, grad_sigmas, grad_rgbs,

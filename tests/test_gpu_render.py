@@ -239,6 +239,19 @@ def test_one_launch_tail_equals_the_three_kernels(C, bg, M_cap, built_lib, cuda)
     assert int(cnt) == 0 and float(A["ws"].max()) > 0.5 and float(A["gs"].abs().max()) > 0
     for k in B:
         assert torch.equal(A[k], B[k]), f"{k}: max diff {float((A[k] - B[k]).abs().max())}"
+    # the round-2 candidate of the same kernel (rows fetched a round ahead, off by default): only the loads move
+    B2 = {k: torch.full_like(v, float("nan")) for k, v in B.items()}
+    lib.snerf_debug_set_tail_prefetch(1)
+    try:
+        check(lib.snerf_composite_l1_train(ptr(sig), ptr(rgb), ptr(deltas), ptr(rays), M, N, 1e-4, C, ptr(tgt), ptr(bgt), bgs,
+                                           scale, ptr(nears), ptr(fars), ptr(B2["ws"]), ptr(B2["depth"]), ptr(B2["image"]),
+                                           ptr(B2["pred"]), ptr(B2["dn"]), ptr(B2["loss"]), ptr(B2["gs"]), ptr(B2["gr"]),
+                                           ptr(n_samples), ptr(cnt), stream()), "fused tail, prefetch")
+        torch.cuda.synchronize()
+    finally:
+        lib.snerf_debug_set_tail_prefetch(0)
+    for k in B2:
+        assert torch.equal(A[k], B2[k]), f"prefetch {k}: max diff {float((A[k] - B2[k]).abs().max())}"
 
 
 @pytest.mark.parametrize("precision,C,bg", [("fp32", 3, 1), ("bf16", 3, 1), ("fp32", 4, "tensor")])
