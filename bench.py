@@ -301,7 +301,6 @@ def render_bench(model, dev, world, rank, frames, barrier, max_over_ranks, min_n
     nerf/renderer.py:117-167), pixel rows sharded over the ranks.  Returns the `render` object of the JSON line."""
     import torch
     from stable_nerf_b200 import synthetic as syn
-    from stable_nerf_b200.trainer import shard_range
     ro, rd = syn.full_frame()
     # pixels interleaved over the ranks (rank r renders pixels r, r+W, ...): every shard is a uniform subsample of the
     # image, so the ranks carry equal work (contiguous row blocks leave the object to the middle ranks)

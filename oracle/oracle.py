@@ -7,7 +7,7 @@ pinning status of each function.
 import ctypes
 import os
 import subprocess
-from ctypes import POINTER, c_float, c_int, c_uint32, c_void_p
+from ctypes import c_float, c_int, c_uint32, c_void_p
 
 import numpy as np
 

@@ -6,7 +6,7 @@ code, a RuntimeError is raised.  The library is built in-tree by ``__graft_entry
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int32, c_size_t, c_uint32, c_uint64, c_void_p, POINTER
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint32, c_uint64, c_void_p, POINTER
 
 import torch
 

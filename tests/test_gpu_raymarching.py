@@ -5,13 +5,12 @@ prebuilt oracle/_ref/_raymarching.so travelled to the box -- vs the reference ke
 Bars: bit-exact for near/far, marching (per-ray counts and per-ray sample bytes), Morton, packbits, compaction;
 1e-4 relative for compositing (fp32 re-association + ex2.approx)."""
 import os
-import sys
 
 import numpy as np
 import pytest
 import torch
 
-from scenarios import SCENARIOS, Scenario
+from scenarios import SCENARIOS
 
 pytestmark = pytest.mark.gpu
 
