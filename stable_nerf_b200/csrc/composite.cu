@@ -10,7 +10,6 @@
 
 namespace snerf {
 
-constexpr int kCompThreads = 256;  // 8 rays per block
 constexpr float kNegLog2e = -1.4426950408889634f;
 
 // alpha = 1 - __expf(-sigma*delta): same formula and the same ex2.approx path as raymarching.cu:549
