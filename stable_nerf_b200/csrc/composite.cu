@@ -10,7 +10,7 @@
 
 namespace snerf {
 
-constexpr float kNegLog2e = -1.4426950408889634f;
+constexpr int kCompThreads = 256;  // 8 rays per block
 
 // alpha = 1 - __expf(-sigma*delta): same formula and the same ex2.approx path as raymarching.cu:549
 __device__ __forceinline__ float alpha_of(float sigma, float delta) { return 1.0f - __expf(-sigma * delta); }
