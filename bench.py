@@ -570,6 +570,15 @@ def run_gpu_arm(args):
                 a_ = w / (tm * 1e-3) / (1e9 if b_ == "hbm" else 1e12)
                 out["stage_rooflines"][k] = {"bound": b_, "achieved": round(a_, 2), "unit": "GB/s" if b_ == "hbm" else "TFLOP/s",
                                              "frac": round(a_ / (pk["hbm"] if b_ == "hbm" else pk["tf_sust"]), 4)}
+                if k in ("hashgrid_gather", "hashgrid_scatter"):
+                    # SURVEY 8d's per-sample figure counts the 1024 B of table gathers / reductions, which the L2-resident
+                    # table (46.5 MiB of the 126 MB L2) serves: against the HBM copy peak the fraction can exceed 1.  What
+                    # has to cross HBM per sample is the sample's own rows.
+                    own = (12 + 64) * M if k == "hashgrid_gather" else (12 + 128) * M
+                    out["stage_rooflines"][k].update({
+                        "served_by": "L2-resident table", "hbm_compulsory_GBs": round(own / (tm * 1e-3) / 1e9, 2),
+                        "hbm_compulsory_frac": round(own / (tm * 1e-3) / 1e9 / pk["hbm"], 4),
+                        "dram_bytes_ncu": ncu_traffic.get(k)})
     if rank == 0 and world == 1 and not args.no_large and not args.no_stages and ts.fused:
         out["large_batch"] = large_batch_profile(model, dev, peaks())
     if rank == 0 and world == 1 and not args.no_cpu:
