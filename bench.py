@@ -352,6 +352,31 @@ def render_bench(model, dev, world, rank, frames, barrier, max_over_ranks, min_n
             "samples_per_frame": float(tot[1]) / frames, "unit": "samples/s", "density_grid_update_ms": upd_ms}
 
 
+def first_epoch_profile(model, ts, iters=10):
+    """cfg2 on the reference's first-epoch path: before update_extra_state has produced
+    mean_count, march_rays_train sizes its outputs from the measured sample total -- one D2H read per step
+    (raymarching.py:196-229) -- so the step cannot be a graph; it runs through NeRFNetwork.render + autograd, eagerly.
+    This is the path TrainStep.warmup() itself takes for its first steps."""
+    import torch
+    mean_count, local_step = model.mean_count, model.local_step
+    model.mean_count = 0
+    try:
+        for _ in range(3):
+            ts._body()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            ts._body()
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        model.mean_count, model.local_step = mean_count, local_step
+    ms = e0.elapsed_time(e1) / iters
+    return {"workload": "cfg2 before mean_count exists: eager NeRFNetwork.render + autograd, sample total read back every step",
+            "ms_per_step": ms, "rays_per_s": RAYS_PER_GPU / (ms * 1e-3)}
+
+
 def large_batch_profile(model, dev, pk, n_rays=1 << 18):
     """cfg5's per-step ray count on ONE GPU (2^18 rays, ~22 M samples): at this size the byte-moving kernels are no
     longer launch-bound, so their HBM fractions mean something.  Eager fused step, CUDA events per stage / kernel."""
@@ -579,6 +604,10 @@ def run_gpu_arm(args):
                         "served_by": "L2-resident table", "hbm_compulsory_GBs": round(own / (tm * 1e-3) / 1e9, 2),
                         "hbm_compulsory_frac": round(own / (tm * 1e-3) / 1e9 / pk["hbm"], 4),
                         "dram_bytes_ncu": ncu_traffic.get(k)})
+        try:
+            out["first_epoch_path"] = first_epoch_profile(model, ts)
+        except Exception as e:  # an extra line of the report must not take the bench line down
+            out["first_epoch_path"] = {"error": repr(e)[:200]}
     if rank == 0 and world == 1 and not args.no_large and not args.no_stages and ts.fused:
         out["large_batch"] = large_batch_profile(model, dev, peaks())
     if rank == 0 and world == 1 and not args.no_cpu:
