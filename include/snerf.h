@@ -213,6 +213,10 @@ typedef struct snerf_field_desc {
   uint32_t geo_feat_dim;   /* 15 (nerf/network.py:14)                                                */
   uint32_t channel_dim;    /* colour channels, 1..4                                                  */
   float bound;             /* scene bound: x01 = (x + bound) / (2*bound)  (nerf/network.py:43)       */
+  float color_in_pad;      /* value fed into the colour net's padded 32nd input (nerf/network.py:34-37 builds
+                            * tcnn.Network(31, C): tiny-cuda-nn wraps it in an Identity encoding whose alignment
+                            * padding is 1.0, so first-layer column 31 is a learned bias; 0.0 = the reference's
+                            * commented-out manual zero pad, nerf/network.py:54).  DESIGN.md section 2.          */
 } snerf_field_desc;
 
 /* x01 [M,3] in [0,1] -> enc [M, n_levels*n_features] fp32, level-major. */

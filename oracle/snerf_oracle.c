@@ -593,7 +593,7 @@ static void field_one_forward(const orc_field_desc* f, const net_shape* ss, cons
   sh4((dir[0] + 1.0f) * 0.5f, (dir[1] + 1.0f) * 0.5f, (dir[2] + 1.0f) * 0.5f, sh); /* nerf/network.py:51 */
   for (int k = 0; k < 16; k++) a_c[0][k] = q(sh[k], bf);
   for (int k = 0; k < (int)f->geo_feat_dim; k++) a_c[0][16 + k] = q(out_s[1 + k], bf); /* :48,:55 */
-  for (int k = 16 + (int)f->geo_feat_dim; k < sc->in_dim[0]; k++) a_c[0][k] = 0.0f;      /* zero pad 31 -> 32 */
+  for (int k = 16 + (int)f->geo_feat_dim; k < sc->in_dim[0]; k++) a_c[0][k] = q(f->color_in_pad, bf); /* pad 31 -> 32 */
   net_forward(sc, w_color, bf, a_c, out_c);
 }
 

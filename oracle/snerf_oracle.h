@@ -40,6 +40,7 @@ typedef struct orc_field_desc { /* identical layout to snerf_field_desc */
   orc_grid_desc grid;
   uint32_t width, n_hidden_sigma, n_hidden_color, geo_feat_dim, channel_dim;
   float bound;
+  float color_in_pad; /* value of the colour net's padded 32nd input (tiny-cuda-nn Identity-encoding padding: 1.0) */
 } orc_field_desc;
 
 void orc_set_threads(int n); /* 0 = all cores */

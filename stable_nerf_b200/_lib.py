@@ -38,7 +38,7 @@ class FieldDesc(ctypes.Structure):
     _fields_ = [
         ("grid", GridDesc),
         ("width", c_uint32), ("n_hidden_sigma", c_uint32), ("n_hidden_color", c_uint32),
-        ("geo_feat_dim", c_uint32), ("channel_dim", c_uint32), ("bound", c_float),
+        ("geo_feat_dim", c_uint32), ("channel_dim", c_uint32), ("bound", c_float), ("color_in_pad", c_float),
     ]
 
 

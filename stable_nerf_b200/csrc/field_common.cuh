@@ -6,7 +6,7 @@ namespace snerf {
 
 constexpr int kMaxMats = 8;   // matrices per net (n_hidden + 1)
 constexpr int kOutPad = 16;   // both nets' output layers are padded to 16 rows (nerf/network.py:24,35)
-constexpr int kColorIn = 32;  // SH16 + geo15 + 1 zero pad (nerf/network.py:55)
+constexpr int kColorIn = 32;  // SH16 + geo15 + 1 pad column = snerf_field_desc::color_in_pad (nerf/network.py:55)
 
 struct NetShape {
   int n_mats;

@@ -118,9 +118,9 @@ static void linear_wgrad(const float* GY, int N, const float* X, int K, float* G
 
 __device__ __forceinline__ void sh4_eval_f(float x01, float y01, float z01, float* o);  // below (copy of k_sh4 math)
 
-// cin[m] = [ SH16((d+1)/2), out_s[m][1:16], 0 ]      (nerf/network.py:51-55)
+// cin[m] = [ SH16((d+1)/2), out_s[m][1:16], pad ]      (nerf/network.py:51-55)
 __global__ void __launch_bounds__(256) k_color_input(const float* __restrict__ dirs, const float* __restrict__ out_s,
-                                                     uint32_t m, float* __restrict__ cin) {
+                                                     uint32_t m, float pad, float* __restrict__ cin) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   float o[32];
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) k_color_input(const float* __restrict__ d
   o[19] = g1.x; o[20] = g1.y; o[21] = g1.z; o[22] = g1.w;
   o[23] = g2.x; o[24] = g2.y; o[25] = g2.z; o[26] = g2.w;
   o[27] = g3.x; o[28] = g3.y; o[29] = g3.z; o[30] = g3.w;
-  o[31] = 0.f;
+  o[31] = pad;
   float4* out = reinterpret_cast<float4*>(cin + (size_t)i * 32);
 #pragma unroll
   for (int k = 0; k < 8; k++) out[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
@@ -264,7 +264,7 @@ static int chunk_forward(const snerf_field_desc* f, const NetShape& ss, const Ne
     x = y;
   }
   if (sigma_only) return finish_launch(0);
-  k_color_input<<<div_up(m, 256), 256, 0, s>>>(dirs, b.out_s, m, b.cin);
+  k_color_input<<<div_up(m, 256), 256, 0, s>>>(dirs, b.out_s, m, f->color_in_pad, b.cin);
   g_launch_count++;
   x = b.cin;
   for (int i = 0; i < sc.n_mats; i++) {

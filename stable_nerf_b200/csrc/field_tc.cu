@@ -93,6 +93,7 @@ struct TcParams {
   PackedNet net;
   float bound;
   uint32_t M, C;
+  uint32_t pad_hi;       // colour net: bf16 bits of snerf_field_desc::color_in_pad in the upper half (input column 31)
   const float* xyzs;
   const float* dirs;
   const float2* table;
@@ -150,7 +151,7 @@ __device__ __forceinline__ void encode_levels(const snerf_grid_desc& g, const fl
 __device__ __forceinline__ float norm01(float v, float bound) { return __fdiv_rn(fadd(v, bound), fmul(2.0f, bound)); }
 
 // The 32-column input operand of sample m is 4 groups of 8 columns.  NET 0: group g = hash-grid levels 4g..4g+3;
-// NET 1: groups 0,1 = SH-4 of the direction, groups 2,3 = the 15 geometry features + a zero pad.
+// NET 1: groups 0,1 = SH-4 of the direction, groups 2,3 = the 15 geometry features + the pad value (color_in_pad).
 // fetch_input produces groups [G0, G0+NG) of sample m in registers (zeros for rows past M); store_input writes them
 // into row `row` of chunk 0 of tile a0.  Split so that the global loads can be issued long before the tile needs them.
 template <int NET, int G0, int NG, bool kFromSaved>
@@ -188,7 +189,7 @@ __device__ __forceinline__ void fetch_input(const TcParams& p, uint32_t m, uint4
         const uint4* gp = reinterpret_cast<const uint4*>(p.geo + (size_t)m * 16);
         out[NG - 2] = __ldg(gp);
         out[NG - 1] = __ldg(gp + 1);
-        out[NG - 1].w &= 0x0000ffffu;  // column 31 is the zero pad (the slot holds sigma_raw in the geo buffer)
+        out[NG - 1].w = (out[NG - 1].w & 0x0000ffffu) | p.pad_hi;  // column 31 = the pad value (the slot holds sigma_raw in the geo buffer)
       }
     }
   }
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_field_fwd(const TcParams p) 
       sh4_eval(fmul(fadd(pd[0], 1.0f), 0.5f), fmul(fadd(pd[1], 1.0f), 0.5f), fmul(fadd(pd[2], 1.0f), 0.5f), o);
       pre[0] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
       pre[1] = make_uint4(pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]), pack_bf16(o[12], o[13]), pack_bf16(o[14], o[15]));
-      pre[3].w &= 0x0000ffffu;  // column 31 is the zero pad (the slot holds sigma_raw in the geo buffer)
+      pre[3].w = (pre[3].w & 0x0000ffffu) | p.pad_hi;  // column 31 = the pad value (the slot holds sigma_raw in the geo buffer)
     }
     {  // 32 input columns = 16 packed words -> A operand columns 0..15
       const uint32_t in16[16] = {pre[0].x, pre[0].y, pre[0].z, pre[0].w, pre[1].x, pre[1].y, pre[1].z, pre[1].w,
@@ -482,6 +483,16 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
   const uint32_t tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31u, q = warp & 3u, hc = (warp >> 2) & 1u;
   const uint32_t row = q * 32u + lane;
   const uint32_t n_tiles = div_up(p.M, kTile);
+  // per-CTA wall-clock marks (debug buffer only): [64 + 4*cta + k] = globaltimer at entry / first tile / after the
+  // last tile / after the weight-gradient flush
+  auto cta_mark = [&](uint32_t k) {
+    if (p.dbg && tid == 0) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      p.dbg[64 + 4 * blockIdx.x + k] = (long long)ns;
+    }
+  };
+  cta_mark(0);
 
   if (tid == 0) {
     mbar_init(&mbarh[0], 1);
@@ -775,6 +786,7 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
       }
     };
     if (blockIdx.x < n_tiles) fetch_tile(blockIdx.x);
+    cta_mark(1);
 
     for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, iter++) {
       const uint32_t m = t * kTile + row;
@@ -882,6 +894,7 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
       // the next tile's hand_over (after its input tile is written) orders these TMEM reads before the next MMA
     }
     if (p.dbg && tid == 0 && blockIdx.x == 0) p.dbg[0] = n_marks;
+    cta_mark(2);
 
     // ---------------- hand this CTA's weight gradients to k_reduce_partials (plain coalesced stores: 148 CTAs adding
     // into the same 200 KB with atomics serialise at the L2 and cost as much as several tiles)
@@ -921,6 +934,7 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
   }
   tc_fence_before();
   __syncthreads();
+  cta_mark(3);
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
@@ -1033,6 +1047,10 @@ static void fill_common(TcParams& p, const snerf_field_desc* f, const PackedNet&
   p.bound = f->bound;
   p.M = M;
   p.C = f->channel_dim;
+  {
+    const __nv_bfloat16 pad = __float2bfloat16_rn(f->color_in_pad);
+    p.pad_hi = (uint32_t)(*reinterpret_cast<const unsigned short*>(&pad)) << 16;
+  }
   p.xyzs = xyzs;
   p.dirs = dirs;
   p.table = reinterpret_cast<const float2*>(table);

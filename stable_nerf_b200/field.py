@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import FieldDesc, GridDesc, check, ptr, stream, workspace
 
 OUT_PAD = 16   # both nets' outputs are padded to 16 (tiny-cuda-nn pads to a multiple of 16)
-COLOR_IN = 32  # 16 SH + 15 geo + 1 zero pad
+COLOR_IN = 32  # 16 SH + 15 geo + 1 pad column (value: snerf_field_desc.color_in_pad, tiny-cuda-nn pads with 1.0)
 
 
 def make_grid_desc(enc_cfg):
@@ -49,7 +49,7 @@ def make_grid_desc(enc_cfg):
     return g
 
 
-def make_field_desc(config, channel_dim, geo_feat_dim, bound):
+def make_field_desc(config, channel_dim, geo_feat_dim, bound, color_in_pad=1.0):
     """snerf_field_desc for the reference's config dict (``BaseNeRFConfig().as_dict()``)."""
     net_s, net_c = config["network_sigma"], config["network_color"]
     for net in (net_s, net_c):
@@ -67,6 +67,7 @@ def make_field_desc(config, channel_dim, geo_feat_dim, bound):
     f.geo_feat_dim = int(geo_feat_dim)
     f.channel_dim = int(channel_dim)
     f.bound = float(bound)
+    f.color_in_pad = float(color_in_pad)
     return f
 
 

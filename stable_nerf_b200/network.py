@@ -14,7 +14,8 @@ from .renderer import NeRFRenderer
 
 
 class NeRFNetwork(NeRFRenderer):
-    def __init__(self, config=None, channel_dim=3, geo_feat_dim=15, bound=1, precision="fp32", **kwargs):
+    def __init__(self, config=None, channel_dim=3, geo_feat_dim=15, bound=1, precision="fp32", color_in_pad=1.0,
+                 **kwargs):
         super().__init__(bound, channel_dim, **kwargs)
         if config is None:
             config = BaseNeRFConfig().as_dict()
@@ -22,7 +23,10 @@ class NeRFNetwork(NeRFRenderer):
         self.geo_feat_dim = geo_feat_dim
         self.precision = precision  # "fp32": CUDA-core reference-accuracy path; "bf16": tcgen05 path
         self.grads_in_place = False  # set by trainer.TrainStep: backward adds straight into .grad
-        self.fdesc = make_field_desc(config, channel_dim, geo_feat_dim, bound)
+        # value of the colour net's padded 32nd input: 1.0 = tiny-cuda-nn's Identity-encoding padding, which makes
+        # first-layer column 31 a learned bias in reference checkpoints; 0.0 = manual zero pad
+        self.color_in_pad = float(color_in_pad)
+        self.fdesc = make_field_desc(config, channel_dim, geo_feat_dim, bound, color_in_pad=self.color_in_pad)
         self.sigma_net = SigmaNet(self.fdesc)
         self.encoder_dir = DirEncoder()
         self.color_net = ColorNet(self.fdesc)

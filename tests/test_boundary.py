@@ -44,7 +44,7 @@ def test_struct_layouts_match_header():
     from oracle import oracle as orc
     from stable_nerf_b200 import _lib
     assert ctypes.sizeof(_lib.GridDesc) == 16 + 5 * 16 * 4
-    assert ctypes.sizeof(_lib.FieldDesc) == ctypes.sizeof(_lib.GridDesc) + 6 * 4
+    assert ctypes.sizeof(_lib.FieldDesc) == ctypes.sizeof(_lib.GridDesc) + 7 * 4  # ... bound, color_in_pad
     assert ctypes.sizeof(orc.GridDesc) == ctypes.sizeof(_lib.GridDesc)
     assert ctypes.sizeof(orc.FieldDesc) == ctypes.sizeof(_lib.FieldDesc)
 

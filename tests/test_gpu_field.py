@@ -185,6 +185,46 @@ def test_field_bf16_forward_backward(C, M, setup, built_lib, cuda):
             assert cos >= 0.99 or np.abs(o).max() == 0, f"grad {name}: cosine {cos} vs fp32 oracle"
 
 
+@pytest.mark.parametrize("pad", [0.0, 1.0])
+def test_color_in_pad_value(pad, setup, built_lib, cuda):
+    """snerf_field_desc.color_in_pad: the colour net's 32nd input.  1.0 (default) = tiny-cuda-nn's Identity-encoding
+    padding, under which first-layer column 31 is a learned bias of reference checkpoints; 0.0 = a manual zero pad
+    (nerf/network.py:54).  Both against the oracle, fp32 (1e-4) and bf16 (5e-3 / 1e-2 vs the emulating oracle), with a
+    colour net whose column 31 is far from zero so that a wrong pad value cannot hide."""
+    import copy
+    from oracle import oracle as orc
+    C, M = 3, 300
+    f0, _, ws, table, wc = setup[C]
+    f = copy.deepcopy(f0)
+    f.color_in_pad = pad
+    of = orc.copy_desc(f, orc.FieldDesc)
+    wc = wc.copy()
+    wc[:128 * 32].reshape(128, 32)[:, 31] = np.linspace(-0.5, 0.5, 128, dtype=np.float32)
+    x, dirs = sample_points(M, seed=11)
+    rng = np.random.default_rng(12)
+    g_sig = rng.standard_normal(M).astype(np.float32)
+    g_rgb = rng.standard_normal((M, C)).astype(np.float32)
+    sig_o, rgb_o = orc.field_forward(of, x, dirs, table, ws, wc)
+    gt_o, gws_o, gwc_o = orc.field_backward(of, x, dirs, table, ws, wc, g_sig, g_rgb)
+    sig, rgb, (gt, gws, gwc) = run_cuda_field(f, x, dirs, ws, table, wc, 0, g_sig, g_rgb, cuda)
+    assert rel_err(sig, sig_o) <= 1e-4 and rel_err(rgb, rgb_o) <= 1e-4
+    assert rel_err(gws, gws_o) <= 1e-4 and rel_err(gwc, gwc_o) <= 1e-4 and rel_err(gt, gt_o) <= 1e-4
+    col31 = gwc.reshape(-1)[:128 * 32].reshape(128, 32)[:, 31]
+    assert (np.abs(col31).max() > 0) == (pad != 0.0), "column 31 trains as a bias exactly when the pad is non-zero"
+    # the other pad value gives different colours (the test can tell them apart)
+    f_other = copy.deepcopy(f0)
+    f_other.color_in_pad = 1.0 - pad
+    _, rgb_other = orc.field_forward(orc.copy_desc(f_other, orc.FieldDesc), x, dirs, table, ws, wc)
+    assert rel_err(rgb_other, rgb_o) > 1e-2
+    # tcgen05 path, with and without the forward->backward hand-off
+    sig_e, rgb_e = orc.field_forward(of, x, dirs, table, ws, wc, emulate_bf16=True)
+    gt_e, gws_e, gwc_e = orc.field_backward(of, x, dirs, table, ws, wc, g_sig, g_rgb, emulate_bf16=True)
+    for use_saved in (False, True):
+        sig_b, rgb_b, (gt_b, gws_b, gwc_b) = run_cuda_field(f, x, dirs, ws, table, wc, 1, g_sig, g_rgb, cuda, use_saved=use_saved)
+        assert rel_err(sig_b, sig_e) <= 5e-3 and rel_err(rgb_b, rgb_e) <= 5e-3
+        assert rel_err(gws_b, gws_e) <= 1e-2 and rel_err(gwc_b, gwc_e) <= 1e-2 and rel_err(gt_b, gt_e) <= 1e-2
+
+
 def test_network_module_autograd(setup, built_lib, cuda):
     """NeRFNetwork.forward/density through torch autograd (nerf/network.py:39-76 surface)."""
     from oracle import oracle as orc

@@ -208,15 +208,19 @@ def test_composite_against_float64_numpy_and_finite_differences():
         assert abs(num - gr[i, 1]) <= 1e-3 * max(1.0, abs(num))
 
 
-def test_field_oracle_against_torch_float64():
-    """hash grid + SH + MLP restated independently with torch float64 ops; fp32 oracle must agree to 1e-5."""
+@pytest.mark.parametrize("color_in_pad", [1.0, 0.0])
+def test_field_oracle_against_torch_float64(color_in_pad):
+    """hash grid + SH + MLP restated independently with torch float64 ops; fp32 oracle must agree to 1e-5.
+    color_in_pad: the colour net's 32nd input -- 1.0 (tiny-cuda-nn's Identity-encoding padding, the default) and 0.0
+    (a manual zero pad, nerf/network.py:54); with 1.0 first-layer column 31 acts as a bias and receives a gradient."""
     import torch
     from oracle import oracle as orc
     from stable_nerf_b200 import synthetic as syn
     from stable_nerf_b200.config import BaseNeRFConfig
     from stable_nerf_b200.field import make_field_desc, mlp_layer_shapes
-    f = make_field_desc(BaseNeRFConfig().as_dict(), 3, 15, 1.0)
+    f = make_field_desc(BaseNeRFConfig().as_dict(), 3, 15, 1.0, color_in_pad=color_in_pad)
     of = orc.copy_desc(f, orc.FieldDesc)
+    assert of.color_in_pad == color_in_pad
     ss, sc_ = mlp_layer_shapes(32, 128, 3), mlp_layer_shapes(32, 128, 4)
     ws, table, wc = syn.field_params(38912, f.grid.n_entries * 2, 55296, shapes_sigma=ss, shapes_color=sc_, table_scale=1.0)
     rng = np.random.default_rng(0)
@@ -266,7 +270,7 @@ def test_field_oracle_against_torch_float64():
     hs = mlp(enc, Ws, ss)
     sigma_t = torch.relu(hs[:, 0])
     sh = torch.from_numpy(orc.sh4_forward(((d + 1) / 2).astype(np.float32))).double()
-    cin = torch.cat([sh, hs[:, 1:16], torch.zeros(M, 1).double()], -1)
+    cin = torch.cat([sh, hs[:, 1:16], torch.full((M, 1), color_in_pad).double()], -1)
     rgb_t = torch.sigmoid(mlp(cin, Wc, sc_)[:, :3])
     assert rel_err(sig, sigma_t.detach().numpy()) < 1e-5 and rel_err(rgb, rgb_t.detach().numpy()) < 1e-5
     assert rel_err(geo, hs[:, 1:16].detach().numpy()) < 1e-5
@@ -278,6 +282,8 @@ def test_field_oracle_against_torch_float64():
     gt, gws, gwc = orc.field_backward(of, x, d, table, ws, wc, g_sig, g_rgb)
     assert rel_err(gws, Ws.grad.numpy()) < 1e-4 and rel_err(gwc, Wc.grad.numpy()) < 1e-4
     assert rel_err(gt, tab.grad.view(-1).numpy()) < 1e-4
+    col31 = gwc[:128 * 32].reshape(128, 32)[:, 31]  # d loss / d (first-layer column 31): the bias when the pad is 1
+    assert (np.abs(col31).max() > 0) == (color_in_pad != 0.0)
     # bf16 emulation stays within the stated bf16 tolerance of the fp32 result
     sig_b, rgb_b = orc.field_forward(of, x, d, table, ws, wc, emulate_bf16=True)
     assert rel_err(sig_b, sig) < 2e-2 and rel_err(rgb_b, rgb) < 2e-2
