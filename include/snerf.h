@@ -308,6 +308,39 @@ int snerf_composite_l1_train(const float* sigmas, const float* rgbs, const float
  * int32 for the per-iteration read (NULL = a pageable local).  This entry point synchronises `stream` once per
  * iteration, as the reference's loop does; background blend and depth normalisation (:164-167) stay with the caller.
  * ---------------------------------------------------------------------------------------------- */
+/* ------------------------------------------------------------------------------------------------
+ * Occupancy-grid maintenance (reference: NeRFRenderer.mark_untrained_grid nerf/renderer.py:174-234 and
+ * NeRFRenderer.update_extra_state nerf/renderer.py:236-327; csrc/grid_update.cu).  The density grid is
+ * f32 [C, H^3] in Morton order inside a cascade, like the reference's.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* nerf/renderer.py:174-234.  poses f32 [B,4,4] cam2world, row-major; kx = cx/fx and ky = cy/fy as the reference's host
+ * code evaluates them (:187, :220-221); bound = the renderer's `bound`.  Every cell of every cascade that no camera
+ * sees gets density_grid = -1 (`self.density_grid[count == 0] = -1`, :230); other cells are left alone.
+ * n_untrained (device uint32, may be NULL) receives the number of cells marked. */
+int snerf_mark_untrained_grid(const float* poses, uint32_t B, float kx, float ky, double bound, uint32_t C, uint32_t H,
+                              float* density_grid, uint32_t* n_untrained, snerf_stream_t stream);
+
+/* nerf/renderer.py:259-266 (full sweep) / :293-300 (partial update): jittered sample positions of n grid cells of
+ * cascade `cas`:  xyz = (2*coord/(H-1) - 1) * (bound_c - half) + (u*2 - 1) * half,  bound_c = min(2^cas, bound),
+ * half = bound_c / H.  cells: int32 [n] Morton indices, or NULL for the cells first_cell .. first_cell+n-1.
+ * noise: f32 [n,3] uniforms in [0,1) (the reference's torch.rand_like), or NULL for counter-based uniforms derived
+ * from `seed` and the cell position in the call.  xyzs: f32 [n,3]. */
+int snerf_grid_cell_points(const int32_t* cells, uint32_t first_cell, uint32_t n, uint32_t cas, double bound, uint32_t H,
+                           const float* noise, uint64_t seed, float* xyzs, snerf_stream_t stream);
+
+size_t snerf_grid_ema_workspace_bytes(uint32_t n_cells);
+
+/* nerf/renderer.py:310-319 in two launches and no host round trip: for all n_cells = C*H^3 cells
+ *   t = tmp_grid * tmp_scale;  grid = max(grid * decay, t) where grid >= 0 and t >= 0   (:311-312; tmp_grid < 0 = not sampled)
+ *   mean = mean(max(grid, 0))  (:313; block sums in double, added in block order: deterministic)
+ *   bitfield = packbits(grid, min(mean, density_thresh))                                 (:318-319)
+ * mean_and_thresh: device f32 [2] = {mean, threshold used}.  workspace: snerf_grid_ema_workspace_bytes() bytes, 256-byte
+ * aligned, zero-filled by the caller before its FIRST use (the call leaves it ready for the next one). */
+int snerf_grid_ema_update(float* density_grid, const float* tmp_grid, uint32_t n_cells, float tmp_scale, float decay,
+                          float density_thresh, float* mean_and_thresh, uint8_t* bitfield, void* workspace,
+                          size_t workspace_bytes, snerf_stream_t stream);
+
 typedef struct {
   uint32_t iterations;
   uint32_t reserved;

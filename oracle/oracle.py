@@ -116,6 +116,43 @@ def packbits(grid, thresh):
     return out
 
 
+def mark_untrained_grid(poses, intrinsic, bound, C, H, density_grid):
+    """nerf/renderer.py:174-234 on density_grid f32 [C,H^3] (in place; Morton order).  Returns the number of cells marked."""
+    from ctypes import c_double
+    poses = _f32(poses).reshape(-1, 4, 4)
+    fx, fy, cx, cy = intrinsic
+    assert density_grid.dtype == np.float32 and density_grid.flags.c_contiguous
+    fn = lib().orc_mark_untrained_grid
+    fn.restype = c_uint32
+    return int(fn(_p(poses), c_uint32(poses.shape[0]), c_float(cx / fx), c_float(cy / fy), c_double(bound), c_uint32(C),
+                  c_uint32(H), _p(density_grid)))
+
+
+def grid_cell_points(cells, first, n, cas, bound, H, noise):
+    """nerf/renderer.py:259-266: jittered sample positions [n,3] of Morton cells (cells int32 [n] or None = first..)."""
+    from ctypes import c_double
+    noise = _f32(noise).reshape(-1, 3)
+    out = np.empty((n, 3), np.float32)
+    cells = None if cells is None else np.ascontiguousarray(cells, np.int32)
+    lib().orc_grid_cell_points(_p(cells) if cells is not None else None, c_uint32(first), c_uint32(n), c_uint32(cas),
+                               c_double(bound), c_uint32(H), _p(noise), _p(out))
+    return out
+
+
+def grid_ema_update(grid, tmp, decay, density_thresh, tmp_scale=1.0):
+    """nerf/renderer.py:310-319 on grid f32 [C*H^3] (in place).  Returns (mean_density, threshold used, bitfield)."""
+    assert grid.dtype == np.float32 and grid.flags.c_contiguous
+    tmp = _f32(tmp).reshape(-1)
+    n = grid.size
+    bits = np.empty(n // 8, np.uint8)
+    thresh = c_float(0)
+    fn = lib().orc_grid_ema_update
+    fn.restype = c_float
+    mean = fn(_p(grid), _p(tmp), c_uint32(n), c_float(tmp_scale), c_float(decay), c_float(density_thresh),
+              ctypes.byref(thresh), _p(bits))
+    return float(mean), float(thresh.value), bits
+
+
 def march_rays_train(rays_o, rays_d, bound, bitfield, C, H, nears, fars, noises=None, dt_gamma=0.0, max_steps=1024,
                      M=None):
     """Returns xyzs, dirs, deltas [M,...], rays [N,3], counter [2].  M=None sizes the outputs to the exact total."""

@@ -684,6 +684,85 @@ void orc_field_backward(const orc_field_desc* f, const float* xyzs, const float*
   free(x01); free(enc); free(genc);
 }
 
+/* ---------------------------------------------------------------- occupancy-grid maintenance
+ * nerf/renderer.py:174-234 (mark_untrained_grid) and :236-327 (update_extra_state), expression by expression: the
+ * reference evaluates them as separate torch fp32 element-wise ops (every intermediate rounded to fp32; -ffp-contract=off
+ * keeps gcc from fusing), python-double scalars are rounded to fp32 once when they meet a tensor, and the batched
+ * [S,N,3] @ [S,3,3] product (:215) is summed over k in order with fused multiply-adds (pinned against the reference's
+ * own CPU run in tests/golden/grid_update.npz, where cells whose decision hangs on the last bit are listed). */
+
+static inline float cell_centre(uint32_t c, float Hm1) { return (2.0f * (float)c) / Hm1 - 1.0f; } /* :198 / :259 */
+
+static void cascade_scale(double bound, uint32_t cas, uint32_t H, float* scale, float* half, float* two_half) {
+  const double b = fmin((double)(1u << cas), bound), h = b / (double)H; /* :203-204 */
+  *scale = (float)(b - h);
+  *half = (float)h;
+  *two_half = (float)(h * 2.0);
+}
+
+/* poses [B,4,4] cam2world; kx = cx/fx, ky = cy/fy; density_grid [C,H^3] Morton order: unseen cells <- -1 (:230).
+ * Returns the number of cells marked. */
+uint32_t orc_mark_untrained_grid(const float* poses, uint32_t B, float kx, float ky, double bound, uint32_t C, uint32_t H,
+                                 float* density_grid) {
+  const uint32_t H3 = H * H * H;
+  const float Hm1 = (float)(H - 1);
+  uint32_t marked = 0;
+  for (uint32_t cas = 0; cas < C; cas++) {
+    float scale, half, two_half;
+    cascade_scale(bound, cas, H, &scale, &half, &two_half);
+#pragma omp parallel for reduction(+ : marked) schedule(static)
+    for (uint32_t i = 0; i < H3; i++) {
+      const float wx = cell_centre(morton3D_invert_(i), Hm1) * scale, wy = cell_centre(morton3D_invert_(i >> 1), Hm1) * scale,
+                  wz = cell_centre(morton3D_invert_(i >> 2), Hm1) * scale; /* :206 */
+      int seen = 0;
+      for (uint32_t b = 0; b < B && !seen; b++) {
+        const float* P = poses + (size_t)b * 16;
+        const float dx = wx - P[3], dy = wy - P[7], dz = wz - P[11];                      /* :214 */
+        const float X = fmaf(dz, P[8], fmaf(dy, P[4], dx * P[0]));                       /* :215, column j of R */
+        const float Y = fmaf(dz, P[9], fmaf(dy, P[5], dx * P[1]));
+        const float Z = fmaf(dz, P[10], fmaf(dy, P[6], dx * P[2]));
+        seen = Z > 0.0f && fabsf(X) < kx * Z + two_half && fabsf(Y) < ky * Z + two_half; /* :218-221 */
+      }
+      if (!seen) {
+        density_grid[(size_t)cas * H3 + i] = -1.0f;
+        marked++;
+      }
+    }
+  }
+  return marked;
+}
+
+/* :259-266 / :293-300.  cells int32 [n] Morton indices or NULL (= first .. first+n-1); noise [n,3] uniforms. */
+void orc_grid_cell_points(const int32_t* cells, uint32_t first, uint32_t n, uint32_t cas, double bound, uint32_t H,
+                          const float* noise, float* xyzs) {
+  float scale, half, two_half;
+  cascade_scale(bound, cas, H, &scale, &half, &two_half);
+  const float Hm1 = (float)(H - 1);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t m = cells ? (uint32_t)cells[i] : first + i;
+    for (int k = 0; k < 3; k++) {
+      const float centre = cell_centre(morton3D_invert_(m >> k), Hm1) * scale;
+      const float jitter = (noise[(size_t)i * 3 + k] * 2.0f - 1.0f) * half;
+      xyzs[(size_t)i * 3 + k] = centre + jitter;
+    }
+  }
+}
+
+/* :310-319.  Returns mean (sum in double); *thresh = min(mean, density_thresh); bitfield = packbits(grid, thresh). */
+float orc_grid_ema_update(float* grid, const float* tmp, uint32_t n, float tmp_scale, float decay, float density_thresh,
+                          float* thresh, uint8_t* bitfield) {
+  double s = 0.0;
+  for (uint32_t i = 0; i < n; i++) {
+    const float t = tmp[i] * tmp_scale;
+    if (grid[i] >= 0.0f && t >= 0.0f) grid[i] = fmaxf(grid[i] * decay, t);
+    s += (double)fmaxf(grid[i], 0.0f);
+  }
+  const float mean = (float)(s / (double)n);
+  *thresh = fminf(mean, density_thresh);
+  orc_packbits(grid, n / 8, *thresh, bitfield);
+  return mean;
+}
+
 /* ---------------------------------------------------------------- trunc_exp (nerf/activation.py:6-18) */
 
 void orc_trunc_exp_forward(const float* x, uint32_t n, float* y) {

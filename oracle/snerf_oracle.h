@@ -98,6 +98,14 @@ void orc_field_backward(const orc_field_desc* f, const float* xyzs, const float*
                         const float* w_sigma, const float* w_color, const float* grad_sigmas, const float* grad_rgbs,
                         int emulate_bf16, float* grad_table, float* grad_w_sigma, float* grad_w_color);
 
+/* ---- occupancy-grid maintenance: nerf/renderer.py:174-234 and :236-327 ---- */
+uint32_t orc_mark_untrained_grid(const float* poses, uint32_t B, float kx, float ky, double bound, uint32_t C, uint32_t H,
+                                 float* density_grid);
+void orc_grid_cell_points(const int32_t* cells, uint32_t first, uint32_t n, uint32_t cas, double bound, uint32_t H,
+                          const float* noise, float* xyzs);
+float orc_grid_ema_update(float* grid, const float* tmp, uint32_t n, float tmp_scale, float decay, float density_thresh,
+                          float* thresh, uint8_t* bitfield);
+
 /* nerf/activation.py:6-18 */
 void orc_trunc_exp_forward(const float* x, uint32_t n, float* y);
 void orc_trunc_exp_backward(const float* g, const float* x, uint32_t n, float* dx);

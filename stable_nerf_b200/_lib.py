@@ -109,6 +109,10 @@ SIGNATURES = {
     "snerf_field_backward_ex": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_size_t,
                                         _P, c_size_t, _P, _U, _S]),
     "snerf_hashgrid_backward_levels": (c_int, [POINTER(GridDesc), _P, _F, _P, _U, _P, _U, _U, _S]),
+    "snerf_mark_untrained_grid": (c_int, [_P, _U, _F, _F, ctypes.c_double, _U, _U, _P, _P, _S]),
+    "snerf_grid_cell_points": (c_int, [_P, _U, _U, _U, ctypes.c_double, _U, _P, c_uint64, _P, _S]),
+    "snerf_grid_ema_workspace_bytes": (c_size_t, [_U]),
+    "snerf_grid_ema_update": (c_int, [_P, _P, _U, _F, _F, _F, _P, _P, _P, c_size_t, _S]),
     "snerf_tc_selftest": (c_int, [_P, _P, _P, _U, _U, c_int, c_int, _S]),
     "snerf_debug_set_march_warp_max_rays": (None, [_U]),
     "snerf_debug_set_field_stage_mask": (None, [_U]),

@@ -39,6 +39,12 @@ class NeRFNetwork(NeRFRenderer):
         sigma, geo_feat = field_density(x, self.sigma_net, self.fdesc, self.precision)
         return {'sigma': sigma, 'geo_feat': geo_feat}
 
+    def _query_sigma(self, cas_xyzs):
+        # occupancy-grid update (nerf/renderer.py:268): sigma only -- the 15 geometry features of 2 M cells are not written
+        if type(self).density is not NeRFNetwork.density:
+            return super()._query_sigma(cas_xyzs)
+        return field_density(cas_xyzs, self.sigma_net, self.fdesc, self.precision, want_geo=False)[0]
+
     def color(self, x, d, mask=None, geo_feat=None, **kwargs):
         """Colour query (nerf/network.py:82-112).  geo_feat is a function of x, so it is recomputed by the fused
         field call rather than consumed; with a mask only the selected rows are evaluated."""

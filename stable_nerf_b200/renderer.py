@@ -193,83 +193,103 @@ class NeRFRenderer(nn.Module):
         """int32 [n,3] grid coordinates of Morton indices."""
         return raymarching.morton3D_invert(indices.to(torch.int32))
 
-    def _cell_centres(self, coords):
-        """cell coordinates -> [-1,1] positions (nerf/renderer.py:259)."""
-        return 2 * coords.float() / (self.grid_size - 1) - 1
-
     @torch.no_grad()
     def mark_untrained_grid(self, poses, intrinsic, S=64):
         """Cells no camera sees get density -1 (nerf/renderer.py:174-234).  poses [B,4,4] cam2world; intrinsic
-        (fx, fy, cx, cy)."""
+        (fx, fy, cx, cy).  One launch per cascade (``snerf_mark_untrained_grid``, csrc/grid_update.cu): every cell runs
+        the reference's frustum test over all cameras and stops at the first that sees it; ``S`` (the reference's
+        chunking against OOM) has no effect on the result and is ignored."""
         if isinstance(poses, np.ndarray):
             poses = torch.from_numpy(poses)
         device = self.density_grid.device
-        poses = poses.to(device=device, dtype=torch.float32)
-        B = poses.shape[0]
+        _lib.require_cuda(self.density_grid)
+        poses = poses.to(device=device, dtype=torch.float32).contiguous().view(-1, 4, 4)
         fx, fy, cx, cy = intrinsic
-        H3 = self.grid_size ** 3
-        count = torch.zeros_like(self.density_grid)
-        chunk = 64 ** 3
-        for start in range(0, H3, chunk):
-            idx = torch.arange(start, min(start + chunk, H3), dtype=torch.int32, device=device)
-            world = self._cell_centres(self._cell_coords(idx)).unsqueeze(0)  # [1,n,3]
-            for cas in range(self.cascade):
-                bound = min(2 ** cas, self.bound)
-                half = bound / self.grid_size
-                cas_world = world * (bound - half)
-                seen = torch.zeros(idx.shape[0], dtype=torch.float32, device=device)
-                for head in range(0, B, S):
-                    R = poses[head:head + S, :3, :3]
-                    cam = (cas_world - poses[head:head + S, :3, 3].unsqueeze(1)) @ R  # world -> camera
-                    z = cam[:, :, 2]
-                    vis = (z > 0) & (cam[:, :, 0].abs() < cx / fx * z + half * 2) & (cam[:, :, 1].abs() < cy / fy * z + half * 2)
-                    seen += vis.sum(0)
-                count[cas, start:start + idx.shape[0]] += seen
-        self.density_grid[count == 0] = -1
-        print(f'[mark untrained grid] {(count == 0).sum()} from {H3 * self.cascade}')
+        n_marked = torch.zeros(1, dtype=torch.int32, device=device)
+        _lib.check(_lib.load().snerf_mark_untrained_grid(
+            _lib.ptr(poses), poses.shape[0], float(cx / fx), float(cy / fy), float(self.bound), int(self.cascade),
+            int(self.grid_size), _lib.ptr(self.density_grid), _lib.ptr(n_marked), _lib.stream()), "mark_untrained_grid")
+        print(f'[mark untrained grid] {int(n_marked.item())} from {self.grid_size ** 3 * self.cascade}')
 
     def _query_sigma(self, cas_xyzs):
-        return self.density(cas_xyzs)['sigma'].reshape(-1).detach().to(torch.float32) * self.density_scale
+        """density of the sample points, before ``density_scale`` (nerf/renderer.py:268 / :302)"""
+        return self.density(cas_xyzs)['sigma'].reshape(-1).detach().to(torch.float32)
+
+    # Source of the update's random numbers.  The reference draws them with torch.rand_like / torch.randint on the device
+    # (nerf/renderer.py:266, :280, :284, :300); a test replaces these two methods to feed the draws of a reference run.
+    def _jitter_noise(self, cells, first, n, device):
+        """uniforms [n,3] for the cells' jitter, or None = counter-based uniforms generated inside the kernel from a seed
+        drawn from torch's generator (no 25 MB noise tensor per cascade)."""
+        return None
+
+    def _randint(self, high, shape, device):
+        return torch.randint(0, high, shape, device=device)
+
+    def _cell_points(self, cells, first, n, cas, device):
+        """jittered sample positions [n,3] of Morton cells of cascade cas (nerf/renderer.py:259-266)"""
+        noise = self._jitter_noise(cells, first, n, device)
+        seed = 0 if noise is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        xyzs = torch.empty(n, 3, dtype=torch.float32, device=device)
+        if noise is not None:
+            noise = noise.to(device=device, dtype=torch.float32).contiguous()
+        if cells is not None:
+            cells = cells.to(torch.int32).contiguous()
+        _lib.check(_lib.load().snerf_grid_cell_points(_lib.ptr(cells), int(first), int(n), int(cas), float(self.bound),
+                                                      int(self.grid_size), _lib.ptr(noise), seed, _lib.ptr(xyzs),
+                                                      _lib.stream()), "grid_cell_points")
+        return xyzs
 
     @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128):
-        """EMA update of the occupancy grid + bitfield + running sample-count estimate (nerf/renderer.py:236-327)."""
+        """EMA update of the occupancy grid + bitfield + running sample-count estimate (nerf/renderer.py:236-327).
+
+        Full sweep (the first 16 calls): per cascade one launch turns the Morton cells into jittered sample points, the
+        density query runs on them (hash-grid gather + sigma net on the tensor cores), and ONE call
+        (``snerf_grid_ema_update``: two launches) does max(grid*decay, sigma), the mean of the clamped grid, the threshold
+        min(mean, density_thresh) and the bitfield without a host round trip; the only read-back is ``mean_density`` at
+        the end (a python attribute in the reference too).  ``S`` chunks the sweep (S**3 cells per density query)."""
         device = self.density_grid.device
+        _lib.require_cuda(self.density_grid)
+        lib = _lib.load()
         H3 = self.grid_size ** 3
-        tmp_grid = -torch.ones_like(self.density_grid)
+        tmp_grid = torch.empty_like(self.density_grid)
 
-        def jittered(coords, cas):
-            bound = min(2 ** cas, self.bound)
-            half = bound / self.grid_size
-            xyzs = self._cell_centres(coords) * (bound - half)
-            return xyzs + (torch.rand_like(xyzs) * 2 - 1) * half
-
-        if self.iter_density < 16:  # full sweep
-            chunk = max(int(S), 1) ** 3
+        if self.iter_density < 16:  # full sweep: every cell of every cascade, Morton order = the grid's own order
+            chunk = min(max(int(S), 1) ** 3, H3)
             for start in range(0, H3, chunk):
-                idx = torch.arange(start, min(start + chunk, H3), dtype=torch.int32, device=device)
-                coords = self._cell_coords(idx)
+                n = min(chunk, H3 - start)
                 for cas in range(self.cascade):
-                    tmp_grid[cas, start:start + idx.shape[0]] = self._query_sigma(jittered(coords, cas))
-        else:  # partial update: H^3/4 uniform cells + H^3/4 occupied cells per cascade
+                    tmp_grid[cas, start:start + n] = self._query_sigma(self._cell_points(None, start, n, cas, device))
+        else:  # partial update: H^3/4 uniform cells + H^3/4 occupied cells per cascade (nerf/renderer.py:277-303)
+            tmp_grid.fill_(-1)
             n = H3 // 4
             for cas in range(self.cascade):
-                coords = torch.randint(0, self.grid_size, (n, 3), device=device)
+                coords = self._randint(self.grid_size, (n, 3), device)
                 indices = raymarching.morton3D(coords).long()
                 occ = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
-                if occ.shape[0] > 0:
-                    occ = occ[torch.randint(0, occ.shape[0], [n], dtype=torch.long, device=device)]
+                if occ.shape[0] > 0:  # (the reference raises on an empty grid: randint(0, 0))
+                    occ = occ[self._randint(occ.shape[0], [n], device).long()]
                     indices = torch.cat([indices, occ], dim=0)
-                    coords = torch.cat([coords.int(), self._cell_coords(occ)], dim=0)
-                tmp_grid[cas, indices] = self._query_sigma(jittered(coords, cas))
+                sig = self._query_sigma(self._cell_points(indices, 0, indices.shape[0], cas, device))
+                # `tmp_grid[cas, indices] = sigmas` with duplicate indices: on the reference's device the winner of a
+                # duplicate is arbitrary; here the LAST occurrence wins (what a sequential assignment gives), always
+                order = torch.arange(indices.shape[0], device=device)
+                last = torch.full((H3,), -1, dtype=torch.long, device=device).scatter_reduce_(0, indices, order, "amax")
+                hit = last >= 0
+                tmp_grid[cas, hit] = sig[last[hit]]
 
-        valid = (self.density_grid >= 0) & (tmp_grid >= 0)
-        self.density_grid[valid] = torch.maximum(self.density_grid[valid] * decay, tmp_grid[valid])
-        self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()
+        # EMA, mean, threshold, bitfield (nerf/renderer.py:310-319)
+        nbytes = lib.snerf_grid_ema_workspace_bytes(tmp_grid.numel())
+        ws = getattr(self, "_ema_ws", None)
+        if ws is None or ws.numel() < nbytes or ws.device != device:
+            ws = self._ema_ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        out = torch.empty(2, dtype=torch.float32, device=device)
+        _lib.check(lib.snerf_grid_ema_update(_lib.ptr(self.density_grid), _lib.ptr(tmp_grid), tmp_grid.numel(),
+                                             float(self.density_scale), float(decay), float(self.density_thresh),
+                                             _lib.ptr(out), _lib.ptr(self.density_bitfield), _lib.ptr(ws), nbytes,
+                                             _lib.stream()), "grid_ema_update")
+        self.mean_density = out[0].item()
         self.iter_density += 1
-
-        density_thresh = min(self.mean_density, self.density_thresh)
-        self.density_bitfield = raymarching.packbits(self.density_grid, density_thresh, self.density_bitfield)
 
         total_step = min(16, self.local_step)
         if total_step > 0:
