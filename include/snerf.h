@@ -366,15 +366,27 @@ int snerf_render_rays(const snerf_field_desc* f, const float* rays_o, const floa
  * per rank and step: rank r reads slice r of every arena over NVLink, adds the copies in rank order (bit-identical
  * sums on all ranks) and stores the result into every arena.  The launch carries no per-step argument (the epoch
  * lives in the flag block), so it can be captured in the step's CUDA graph.  All ranks must launch it the same
- * number of times; a rank that never arrives is reported through snerf_p2p_status (timeouts != 0) after a bounded
- * wait instead of hanging the device.
+ * number of times.  A rank that does not arrive within the wait budget is fatal for the exchange, not a partial sum: the
+ * waiting rank moves no data, leaves a sticky error (snerf_p2p_status: timeouts != 0; every later call is a no-op) and
+ * sets the caller's host_error word.  With the arenas bound to an NVSwitch multicast object (snerf_mc_*) the same call
+ * reduces inside the switch (multimem.ld_reduce / multimem.st): 1/W instead of (W-1)/W of the arena per GPU and direction.
  * ---------------------------------------------------------------------------------------------- */
 #define SNERF_P2P_MAX_RANKS 16
 #define SNERF_P2P_HANDLE_BYTES 64
 #define SNERF_P2P_CHANNELS 4 /* independent flag sets: calls on different channels may overlap (different streams) */
+#define SNERF_P2P_EMULATE_RANKS 1u /* flags_word: ONE cooperative launch plays all `world` ranks on this device (rank
+                                    * argument ignored) -- for single-device tests of the protocol: kernels that wait
+                                    * for each other must not be separate launches on one GPU */
 typedef struct {
-  float* buf[SNERF_P2P_MAX_RANKS];      /* arena of rank r as mapped in THIS process (own entry: local memory)    */
+  float* buf[SNERF_P2P_MAX_RANKS];      /* arena of rank r as mapped in THIS process (own entry: local memory);
+                                         * unused (may be NULL) when mc_buf is set                                 */
   uint32_t* flags[SNERF_P2P_MAX_RANKS]; /* flag block of rank r, likewise                                          */
+  float* mc_buf;                        /* NVLS: multicast mapping of all ranks' arenas (snerf_mc_bind_and_map), or NULL
+                                         * = peer loads / stores in rank order                                     */
+  uint32_t* host_error;                 /* optional word of mapped (pinned) host memory: set to 1 + rank when a wait
+                                         * for another rank runs out -- the host can poll it without synchronising  */
+  uint32_t timeout_ms;                  /* budget of a wait for another rank; 0 = 30 000 ms                         */
+  uint32_t flags_word;                  /* SNERF_P2P_EMULATE_RANKS                                                  */
 } snerf_p2p_peers;
 
 size_t snerf_p2p_flag_bytes(void);
@@ -388,6 +400,20 @@ int snerf_p2p_close(void* ptr);
  * slice exchanged on a side stream while the next one is still being produced) use different channels. */
 int snerf_p2p_allreduce(const snerf_p2p_peers* peers, uint32_t rank, uint32_t world, size_t offset_floats, size_t n_floats,
                         uint32_t channel, uint32_t n_ctas, snerf_stream_t stream);
+/* NVLS set-up, one process per GPU (csrc/p2p_reduce.cu; the driver's virtual-memory and multicast entry points are
+ * looked up at run time, the library does not link libcuda).  Order on every rank:
+ *   g = snerf_mc_granularity(world, bytes); bytes = round_up(bytes, g); snerf_mc_arena_create(bytes, g, &arena, &mem);
+ *   rank 0: snerf_mc_create(world, bytes, &mc, &fd) and send fd to the other processes (SCM_RIGHTS);  others:
+ *   snerf_mc_import(fd, &mc);   all: snerf_mc_add_device(mc);  BARRIER;  snerf_mc_bind_and_map(mc, mem, bytes, g, &mc_ptr);
+ *   BARRIER;  peers.mc_buf = mc_ptr.  Return codes >= 100000 are CUresult + 100000. */
+int snerf_mc_supported(void);
+size_t snerf_mc_granularity(uint32_t world, size_t bytes);
+int snerf_mc_arena_create(size_t bytes, size_t gran, void** ptr, uint64_t* mem);
+int snerf_mc_create(uint32_t world, size_t bytes, uint64_t* mc, int* fd);
+int snerf_mc_import(int fd, uint64_t* mc);
+int snerf_mc_add_device(uint64_t mc);
+int snerf_mc_bind_and_map(uint64_t mc, uint64_t mem, size_t bytes, size_t gran, void** mc_ptr);
+int snerf_mc_release(void* mc_ptr, void* arena_ptr, uint64_t mc, uint64_t mem, size_t bytes);
 /* Synchronous read of this rank's flag block: completed calls and bounded waits that ran out, per channel. */
 int snerf_p2p_status(const uint32_t* local_flags, uint32_t channel, uint32_t* epoch, uint32_t* timeouts);
 

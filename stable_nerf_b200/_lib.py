@@ -45,11 +45,13 @@ class FieldDesc(ctypes.Structure):
 SNERF_P2P_MAX_RANKS = 16
 SNERF_P2P_HANDLE_BYTES = 64
 SNERF_P2P_CHANNELS = 4
+SNERF_P2P_EMULATE_RANKS = 1
 
 
 class P2PPeers(ctypes.Structure):
     """snerf_p2p_peers (include/snerf.h): arenas and flag blocks of all ranks as mapped in this process."""
-    _fields_ = [("buf", c_void_p * SNERF_P2P_MAX_RANKS), ("flags", c_void_p * SNERF_P2P_MAX_RANKS)]
+    _fields_ = [("buf", c_void_p * SNERF_P2P_MAX_RANKS), ("flags", c_void_p * SNERF_P2P_MAX_RANKS),
+                ("mc_buf", c_void_p), ("host_error", c_void_p), ("timeout_ms", c_uint32), ("flags_word", c_uint32)]
 
 
 class RenderStats(ctypes.Structure):
@@ -135,6 +137,14 @@ SIGNATURES = {
     "snerf_p2p_close": (c_int, [_P]),
     "snerf_p2p_allreduce": (c_int, [POINTER(P2PPeers), _U, _U, c_size_t, c_size_t, _U, _U, _S]),
     "snerf_p2p_status": (c_int, [_P, _U, POINTER(c_uint32), POINTER(c_uint32)]),
+    "snerf_mc_supported": (c_int, []),
+    "snerf_mc_granularity": (c_size_t, [_U, c_size_t]),
+    "snerf_mc_arena_create": (c_int, [c_size_t, c_size_t, POINTER(c_void_p), POINTER(c_uint64)]),
+    "snerf_mc_create": (c_int, [_U, c_size_t, POINTER(c_uint64), POINTER(c_int)]),
+    "snerf_mc_import": (c_int, [c_int, POINTER(c_uint64)]),
+    "snerf_mc_add_device": (c_int, [c_uint64]),
+    "snerf_mc_bind_and_map": (c_int, [c_uint64, c_uint64, c_size_t, c_size_t, POINTER(c_void_p)]),
+    "snerf_mc_release": (c_int, [_P, _P, c_uint64, c_uint64, c_size_t]),
     "snerf_trunc_exp_forward": (c_int, [_P, _U, _P, _S]),
     "snerf_trunc_exp_backward": (c_int, [_P, _P, _U, _P, _S]),
 }

@@ -69,7 +69,7 @@ class TrainStep:
 
     def __init__(self, model, n_rays, max_steps=1024, bg_color=1, T_thresh=1e-4, use_graph=True, world_size=1,
                  loss_scale=1.0, fused=True, perturb=False, dt_gamma=0, optimizer=None, overlap_allreduce=False,
-                 scatter_groups=2, group=None, exchange="auto"):
+                 scatter_groups=2, group=None, exchange="auto", exchange_timeout_ms=0):
         self.model, self.n_rays, self.max_steps = model, int(n_rays), int(max_steps)
         self.bg_color, self.T_thresh, self.world_size = bg_color, T_thresh, world_size
         self.loss_scale = loss_scale
@@ -107,23 +107,24 @@ class TrainStep:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
         model.grads_in_place = True  # the field backward accumulates straight into these .grad tensors
-        # Gradient exchange between ranks: "p2p" = one kernel over NVLink peer memory inside the step's graph
-        # (stable_nerf_b200.p2p / csrc/p2p_reduce.cu), "nccl" = NCCL all-reduce after the replay, "auto" = p2p when the
-        # ranks can map each other's memory (one node, CUDA IPC), else nccl.
+        # Gradient exchange between ranks, one kernel inside the step's graph (stable_nerf_b200.p2p / csrc/p2p_reduce.cu):
+        # "nvls" = reduced inside the NVSwitch (multicast), "p2p" = peer loads / stores in rank order (bit-reproducible);
+        # "nccl" = NCCL all-reduce after the replay; "auto" = nvls, else p2p, else nccl, whatever the node supports.
         self.exchange, self.exchange_kind, self.exchange_error = None, ("none" if world_size == 1 else "nccl"), None
-        if exchange not in ("auto", "p2p", "nccl"):
-            raise ValueError(f"exchange must be 'auto', 'p2p' or 'nccl', got {exchange!r}")
-        if exchange == "p2p" and world_size > 1 and dev.type != "cuda":
-            raise RuntimeError("exchange='p2p' needs CUDA devices (peer memory over NVLink); use 'auto' or 'nccl'")
-        if world_size > 1 and exchange in ("auto", "p2p") and dev.type == "cuda":
+        self.exchange_timeout_ms = int(exchange_timeout_ms)
+        if exchange not in ("auto", "nvls", "p2p", "nccl"):
+            raise ValueError(f"exchange must be 'auto', 'nvls', 'p2p' or 'nccl', got {exchange!r}")
+        if exchange in ("p2p", "nvls") and world_size > 1 and dev.type != "cuda":
+            raise RuntimeError(f"exchange={exchange!r} needs CUDA devices (NVLink); use 'auto' or 'nccl'")
+        if world_size > 1 and exchange in ("auto", "nvls", "p2p") and dev.type == "cuda":
             try:
-                self._setup_p2p(dev)
+                self._setup_p2p(dev, {"auto": "auto", "nvls": "nvls", "p2p": "peer"}[exchange])
             except RuntimeError as e:
-                if exchange == "p2p":
+                if exchange != "auto":
                     raise
                 self.exchange_error = str(e)
 
-    def _setup_p2p(self, dev):
+    def _setup_p2p(self, dev, algo="auto"):
         """Move the parameters' .grad into one peer-mapped arena: [colour MLP | sigma MLP | table], 16-byte aligned, so
         that "everything but the fine levels of the table" is one contiguous range at the front."""
         from .p2p import P2PExchange
@@ -135,11 +136,13 @@ class TrainStep:
         for p in order:
             offs[id(p)] = n
             n += (p.numel() + 3) // 4 * 4
-        ex = P2PExchange(n, dev, group=self.group)
+        ex = P2PExchange(n, dev, group=self.group, algo=algo, timeout_ms=self.exchange_timeout_ms)
         for p in order:
             o = offs[id(p)]
             p.grad = ex.tensor[o:o + p.numel()].view_as(p)
-        self.exchange, self.exchange_kind, self._ex_off = ex, "p2p", offs
+        self.exchange, self.exchange_kind, self._ex_off = ex, ("nvls" if ex.algo == "nvls" else "p2p"), offs
+        if ex.nvls_error and ex.algo != "nvls":
+            self.exchange_error = f"NVLS unavailable: {ex.nvls_error}"
         # The scatter-add stays inside the field backward and the exchange follows it as one launch over the whole arena.
         # Exchanging the fine levels' slice on a (high-priority) side stream while the coarse levels are scattered was
         # measured at 2 ranks and bought nothing (763 vs 768 us/step), like the NCCL variant of the same overlap
@@ -391,6 +394,16 @@ class TrainStep:
         torch.cuda.synchronize()
         if self.use_graph:
             self._capture()
+        self._zero_grads_after_dry_runs()
+
+    def _zero_grads_after_dry_runs(self):
+        """With an optimiser that zeroes the gradients inside its own step (``zero_grad_in_step``) the fused body zeroes
+        nothing, so the bodies run by warmup / capture / launch counting -- none followed by an optimiser step -- leave
+        their gradients accumulated (and, ray-sharded, all-reduced again and again).  Start the first real step from zero."""
+        if self._opt_zeroes:
+            for p in self.params:
+                p.grad.zero_()
+            torch.cuda.synchronize()
 
     def _capture(self):
         m = self.model
@@ -427,6 +440,7 @@ class TrainStep:
             self.target.copy_(target, non_blocking=True)
         if self.exchange is not None:
             self._check_arena()
+            self.exchange.raise_on_error()  # a rank gave up waiting in an earlier step: those gradients were never summed
         if self.graph is not None:
             self.graph.replay()
         else:
@@ -439,6 +453,37 @@ class TrainStep:
         if self.optimizer is not None:
             self.optimizer.step()
         return self.loss
+
+    def sample_overflow(self):
+        """(samples the last step's march produced, rows M the step's buffers hold).  The step is captured for one M =
+        pad128(mean_count); like in the reference (raymarching.cu:417) rays whose samples do not fit are dropped
+        silently, so a caller that changes the occupancy grid checks this (one 4-byte read, synchronises) or calls
+        ``refresh()``."""
+        if self._bufs is None:
+            return 0, 0
+        return int(self._bufs["n_samples"].item()), int(self._bufs["M"])
+
+    def refresh(self):
+        """Call after ``model.update_extra_state()``: the reference re-estimates ``mean_count`` there
+        (nerf/renderer.py:321-325) and sizes the next steps' buffers from it; a captured step keeps the M it was recorded
+        with, so when pad128(mean_count) has changed the buffers are re-allocated and the graph is captured again.
+        Returns True when it re-captured."""
+        m = self.model
+        if not (self.fused and m.mean_count > 0):
+            return False
+        M = _pad_up(int(m.mean_count), 128)
+        if self._bufs is not None and self._bufs["M"] == M:
+            return False
+        self.graph = self._graph_fwd = self._graph_bwd = None
+        local_step = m.local_step
+        for _ in range(2):
+            self._body()
+        torch.cuda.synchronize()
+        if self.use_graph:
+            self._capture()
+        m.local_step = local_step
+        self._zero_grads_after_dry_runs()
+        return True
 
     def _scatter_and_reduce(self):
         """Table scatter-add in groups of levels, each group's (contiguous) slice of the gradient all-reduced while the
@@ -492,6 +537,7 @@ class TrainStep:
         b = self._bufs
         if self.exchange is not None:
             self._check_arena()
+            self.exchange.raise_on_error()
         if grad_image is not None:
             g = grad_image.detach().to(torch.float32).reshape(self.n_rays, self.model.channel_dim)
             b["g_img"].add_(g)
@@ -527,6 +573,8 @@ class TrainStep:
             self._body_fused(phase)
         if phase == "forward":
             m.local_step = local_step  # replays keep writing the step_counter row recorded here
+        if phase == "backward":
+            self._zero_grads_after_dry_runs()  # the dry run above accumulated a second backward of the same forward
         return g
 
     def pinned_inputs(self):
@@ -549,4 +597,6 @@ class TrainStep:
             self.step(rays_o_pinned, rays_d_pinned, target_pinned)
         self.loss_host.copy_(self.loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        if self.exchange is not None:
+            self.exchange.raise_on_error()  # the step has completed: its own exchange is covered too
         return float(self.loss_host)

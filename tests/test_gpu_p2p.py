@@ -1,7 +1,9 @@
 """Peer-memory gradient exchange (csrc/p2p_reduce.cu) on ONE device: the W "ranks" are W arenas and
-flag blocks in the same memory, each rank's kernel launched on its own stream.  The kernels wait for each other through
-the flag protocol exactly as across GPUs; what this cannot cover is the IPC mapping (scripts/dp_check.py, 2 GPUs).
-The oracle is the sum in rank order, which the kernel promises bit for bit on every rank."""
+flag blocks in the same memory, played by ONE cooperative launch (SNERF_P2P_EMULATE_RANKS: rank = blockIdx.y) -- kernels
+that wait for each other must not be separate launches on one GPU, nothing guarantees that they run at the same time.
+The CTAs wait for each other through the flag protocol exactly as across GPUs; what this cannot cover is the IPC mapping
+and the NVLS path (tests/test_multi_gpu.py, 2 GPUs).  The oracle is the sum in rank order, which the kernel promises bit
+for bit on every rank."""
 import ctypes
 
 import pytest
@@ -18,14 +20,15 @@ def make_ranks(world, n, cuda, seed):
     peers = _lib.P2PPeers()
     for r in range(world):
         peers.buf[r], peers.flags[r] = arenas[r].data_ptr(), flags[r].data_ptr()
+    peers.flags_word = _lib.SNERF_P2P_EMULATE_RANKS
     return arenas, flags, peers
 
 
 def launch_all(lib, peers, world, n, streams, n_ctas=8, lo=0, channel=0):
+    """all `world` ranks in one cooperative launch on streams[0]"""
     from stable_nerf_b200._lib import check
-    for r in range(world):
-        check(lib.snerf_p2p_allreduce(ctypes.byref(peers), r, world, lo, n, channel, n_ctas, ctypes.c_void_p(streams[r].cuda_stream)),
-              f"p2p all-reduce rank {r}")
+    check(lib.snerf_p2p_allreduce(ctypes.byref(peers), 0, world, lo, n, channel, n_ctas, ctypes.c_void_p(streams[0].cuda_stream)),
+          "p2p all-reduce (all ranks)")
 
 
 def status(lib, flags, channel=0):
@@ -73,18 +76,26 @@ def test_two_ranges_on_two_channels_overlap(built_lib, cuda):
         assert status(built_lib, flags[r], 0) == (1, 0) and status(built_lib, flags[r], 1) == (1, 0)
 
 
-def test_absent_rank_is_reported_not_hung(built_lib, cuda):
-    """Rank 1 never launches: rank 0's bounded wait runs out (~2 s), the call returns and the status says so."""
+def test_absent_rank_is_fatal_and_visible_not_a_partial_sum(built_lib, cuda):
+    """Rank 1 never launches: rank 0's wait runs out (budget 300 ms here, 30 s by default), NO data moves, the error is
+    sticky (the next call is refused too) and lands in the registered pinned host word without a synchronising read."""
     arenas, flags, peers = make_ranks(2, 4 * 256, cuda, seed=3)
     launch_all(built_lib, peers, 1, 4 * 256, [torch.cuda.current_stream()])  # world == 1 is a no-op
     torch.cuda.synchronize()
     assert status(built_lib, flags[0]) == (0, 0)
     from stable_nerf_b200._lib import check
-    check(built_lib.snerf_p2p_allreduce(ctypes.byref(peers), 0, 2, 0, 4 * 256, 0, 2,
-                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "p2p")
-    torch.cuda.synchronize()
-    epoch, timeouts = status(built_lib, flags[0])
-    assert timeouts > 0
+    host_error = torch.zeros(1, dtype=torch.int32).pin_memory()
+    peers.flags_word = 0  # a real rank: rank 0 alone
+    peers.timeout_ms = 300
+    peers.host_error = host_error.data_ptr()
+    before = [a.clone() for a in arenas]
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for call in range(2):
+        check(built_lib.snerf_p2p_allreduce(ctypes.byref(peers), 0, 2, 0, 4 * 256, 0, 2, s), "p2p")
+        torch.cuda.synchronize()
+        epoch, timeouts = status(built_lib, flags[0])
+        assert timeouts > 0 and int(host_error[0]) == 1
+        assert torch.equal(arenas[0], before[0]) and torch.equal(arenas[1], before[1]), "no partial sums"
 
 
 def test_bad_arguments(built_lib, cuda):
