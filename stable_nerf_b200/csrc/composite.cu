@@ -467,7 +467,7 @@ using namespace snerf;
     default: return SNERF_E_CHANNELS;                \
   }
 
-static uint32_t g_tail_prefetch = 0;  // snerf_debug_set_tail_prefetch: the one-launch tail fetches its rows a round ahead
+static uint32_t g_tail_prefetch = 1;  // the one-launch tail fetches its rows a round ahead (round 2 A/B, cfg2 step: 0.6185 -> 0.6090 ms)
 
 extern "C" {
 

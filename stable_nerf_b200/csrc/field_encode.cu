@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_fwd(snerf_grid_desc g,
 //   * samples whose gradient is exactly zero (padding, terminated rays) issue nothing.
 static uint32_t g_dedupe_max_res = 300;  // tunable through snerf_debug_set_dedupe_max_res (measurement aid)
 
-static uint32_t g_scatter_adaptive = 0;   // snerf_debug_set_scatter_adaptive_scan: scan depth follows the longest run
+static uint32_t g_scatter_adaptive = 1;   // scan depth follows the warp's longest run (round 2 A/B, cfg2 step: 0.6185 -> 0.6110 ms; both: 0.6064)
 
 template <bool kNormalize, bool kAdaptive = false>
 __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g, const float* __restrict__ x,

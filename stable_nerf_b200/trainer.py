@@ -376,18 +376,26 @@ class TrainStep:
             lib.snerf_debug_set_field_stage_mask(0xffffffff)
         return out
 
-    def warmup(self, rays_o, rays_d, target, iters=3):
+    def warmup(self, rays_o, rays_d, target, iters=3, batches=None):
         """Reference-style first steps on the synchronising path, then ``mean_count`` from the measured sample
-        counts (nerf/renderer.py:321-325) so that later steps never read the device."""
+        counts (nerf/renderer.py:321-325) so that later steps never read the device.  ``batches``: optional list of
+        (rays_o, rays_d, target) triples, one per warm-up step in turn -- ``mean_count`` is then the mean over different
+        ray batches, as it is in training, instead of one batch's exact count."""
         self.rays_o.copy_(rays_o)
         self.rays_d.copy_(rays_d)
         self.target.copy_(target)
         m = self.model
         m.train()
-        for _ in range(iters):
+        for it in range(iters):
+            if batches:
+                o, d, t = batches[it % len(batches)]
+                self.rays_o.copy_(o)
+                self.rays_d.copy_(d)
+                self.target.copy_(t)
             self._body()
         total_step = min(16, m.local_step)
-        m.mean_count = int(m.step_counter[:total_step, 0].sum().item() / total_step)
+        self.warmup_counts = [int(c) for c in m.step_counter[:total_step, 0].tolist()]  # sample totals of the warm-up steps
+        m.mean_count = int(sum(self.warmup_counts) / total_step)
         m.local_step = 0
         for _ in range(2):  # steady-state path once eagerly: sizes every workspace before a capture
             self._body()
@@ -585,6 +593,26 @@ class TrainStep:
         n3 = self.n_rays * 3
         st = self._staging
         return (st[:n3].view(self.n_rays, 3), st[n3:2 * n3].view(self.n_rays, 3), st[2 * n3:].view(self.n_rays, -1))
+
+    def new_pinned_batch(self):
+        """A pinned host buffer laid out like the device inputs, and its (rays_o, rays_d, target) views: fill the views,
+        pass the buffer to ``step_from_packed`` -- a data loader keeps a few of these in rotation."""
+        st = torch.zeros(self._inputs.numel(), pin_memory=self._inputs.is_cuda)
+        n3 = self.n_rays * 3
+        return st, (st[:n3].view(self.n_rays, 3), st[n3:2 * n3].view(self.n_rays, 3), st[2 * n3:].view(self.n_rays, -1))
+
+    def step_from_packed(self, packed, read_loss=False):
+        """One step on a batch packed as [rays_o | rays_d | target] (device tensor, or pinned host tensor: ONE copy of
+        36+4C B/ray either way).  read_loss: also bring the loss back to the host (synchronises) -- the end-to-end form."""
+        self._inputs.copy_(packed, non_blocking=True)
+        self.step()
+        if not read_loss:
+            return self.loss
+        self.loss_host.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if self.exchange is not None:
+            self.exchange.raise_on_error()
+        return float(self.loss_host)
 
     def step_from_host(self, rays_o_pinned, rays_d_pinned, target_pinned):
         """End-to-end form: pinned host inputs -> device, one step, loss back to the host (synchronises)."""

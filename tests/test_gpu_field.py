@@ -360,7 +360,7 @@ def test_backward_ex_zero_table_grad_flag(setup, built_lib, cuda, precision, sid
 
 
 def test_scatter_adaptive_scan_depth_gives_the_same_sums(setup, built_lib, cuda):
-    """snerf_debug_set_scatter_adaptive_scan (round-2 candidate, off by default): the segmented scan that merges equal
+    """snerf_debug_set_scatter_adaptive_scan (on by default since its round-2 A/B): the segmented scan that merges equal
     cells stops at the depth the warp's longest run needs.  Samples along rays (long runs on coarse levels, short ones
     on fine levels, isolated and zero-gradient samples in between) must give the sums of the five-step scan; the two
     launches differ in the order of their fp32 reductions only."""
@@ -388,6 +388,6 @@ def test_scatter_adaptive_scan_depth_gives_the_same_sums(setup, built_lib, cuda)
             torch.cuda.synchronize()
             out[adaptive] = gt.cpu().numpy()
     finally:
-        lib.snerf_debug_set_scatter_adaptive_scan(0)
+        lib.snerf_debug_set_scatter_adaptive_scan(1)  # the default since its round-2 A/B
     assert np.abs(out[0]).max() > 0
     assert rel_err(out[1], out[0]) <= 1e-5

@@ -239,9 +239,10 @@ def test_one_launch_tail_equals_the_three_kernels(C, bg, M_cap, built_lib, cuda)
     assert int(cnt) == 0 and float(A["ws"].max()) > 0.5 and float(A["gs"].abs().max()) > 0
     for k in B:
         assert torch.equal(A[k], B[k]), f"{k}: max diff {float((A[k] - B[k]).abs().max())}"
-    # the round-2 candidate of the same kernel (rows fetched a round ahead, off by default): only the loads move
+    # the other instantiation of the same kernel (rows NOT fetched a round ahead; the prefetching one is the default
+    # since its round-2 A/B): only the loads move, the results are the same bits
     B2 = {k: torch.full_like(v, float("nan")) for k, v in B.items()}
-    lib.snerf_debug_set_tail_prefetch(1)
+    lib.snerf_debug_set_tail_prefetch(0)
     try:
         check(lib.snerf_composite_l1_train(ptr(sig), ptr(rgb), ptr(deltas), ptr(rays), M, N, 1e-4, C, ptr(tgt), ptr(bgt), bgs,
                                            scale, ptr(nears), ptr(fars), ptr(B2["ws"]), ptr(B2["depth"]), ptr(B2["image"]),
@@ -249,7 +250,7 @@ def test_one_launch_tail_equals_the_three_kernels(C, bg, M_cap, built_lib, cuda)
                                            ptr(n_samples), ptr(cnt), stream()), "fused tail, prefetch")
         torch.cuda.synchronize()
     finally:
-        lib.snerf_debug_set_tail_prefetch(0)
+        lib.snerf_debug_set_tail_prefetch(1)
     for k in B2:
         assert torch.equal(A[k], B2[k]), f"prefetch {k}: max diff {float((A[k] - B2[k]).abs().max())}"
 
