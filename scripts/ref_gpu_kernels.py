@@ -78,9 +78,8 @@ def main():
         # ---- march_rays_train, steady state: M = the exact sample total rounded up to 128 (raymarching.py:199-203)
         noises = torch.zeros(N, device=dev)
         counter = torch.zeros(2, dtype=torch.int32, device=dev)
-        ws_bytes = lib.snerf_march_rays_train_workspace_bytes_ex(N, max_steps)
-        if ws_bytes > (1 << 30):
-            ws_bytes = lib.snerf_march_rays_train_workspace_bytes(N)
+        from stable_nerf_b200.raymarching import march_train_workspace_bytes
+        ws_bytes = march_train_workspace_bytes(lib, N, max_steps)  # what the operator wrapper and TrainStep allocate
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         geom = (bound, 0.0, max_steps, N, C, H)
         chk(lib.snerf_march_rays_train_count(P(rays_o), P(rays_d), P(bitfield), *geom, P(nears), P(fars), P(counter), P(noises),

@@ -28,7 +28,7 @@ def _cuda_f32_rows(t, width):
     return t.to(torch.float32).contiguous().view(-1, width)
 
 
-def march_train_workspace_bytes(lib, N, max_steps, limit=1 << 30):
+def march_train_workspace_bytes(lib, N, max_steps, limit=4 << 30):
     """Workspace of the training march: with room for N*max_steps sample positions (<= `limit` bytes) the write pass
     expands them instead of marching a second time."""
     big = lib.snerf_march_rays_train_workspace_bytes_ex(N, max_steps)
