@@ -465,9 +465,15 @@ int snerf_p2p_allreduce(const snerf_p2p_peers* peers, uint32_t rank, uint32_t wo
   if (mc && (((uintptr_t)peers->mc_buf & 15u) || emulate)) return SNERF_E_BADARG;
   p.mc = mc ? reinterpret_cast<float4*>(peers->mc_buf + offset_floats) : nullptr;
   p.host_error = peers->host_error;
-  int dev = 0, khz = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess)
-    return (int)cudaGetLastError();
+  // SM clock of the device, looked up once (an immutable device property; the query itself takes ~1 ms of host time)
+  static int khz_of[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
+  int khz = (dev >= 0 && dev < 64) ? khz_of[dev] : 0;
+  if (khz == 0) {
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess) return (int)cudaGetLastError();
+    if (dev >= 0 && dev < 64) khz_of[dev] = khz;
+  }
   p.budget = (long long)(peers->timeout_ms ? peers->timeout_ms : 30000u) * (long long)khz;  // SM clocks
   p.rank = rank;
   p.world = world;
