@@ -424,6 +424,18 @@ int snerf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_
                     float beta2, float eps, float weight_decay, int decoupled_weight_decay, uint32_t step, int zero_grad,
                     snerf_stream_t stream);
 
+/* The same update with the step count on the device, so that the optimiser's launches carry no per-step argument and can
+ * be captured in the training step's CUDA graph.  state: 32 bytes of device memory, 16-byte aligned, zero-filled at
+ * creation = {int32 steps applied, int32 skip-next flag, f32 lr/(1-b1^t), f32 1/sqrt(1-b2^t), int32 enabled, pad}.
+ * snerf_adam_advance (one thread) starts an optimiser step: it increments the step count and refreshes the bias
+ * corrections -- or, when the skip flag is set, clears the flag and disables this step's parameter launches (how a
+ * pipelined training step skips the update that precedes its first gradients).  snerf_adam_step_dev then updates one
+ * flat parameter tensor like snerf_adam_step, reading the scalars from `state`. */
+int snerf_adam_advance(void* state, float lr, float beta1, float beta2, snerf_stream_t stream);
+int snerf_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, uint32_t n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, int decoupled_weight_decay, const void* state,
+                        int zero_grad, snerf_stream_t stream);
+
 /* Same, with two extras.
  * d_enc_out != NULL (f32 [M, 2*n_levels], 16-byte aligned; bf16 precision only): for callers that overlap the table's
  * gradient all-reduce with its scatter-add (ray-sharded training) the backward stops after writing d loss / d encoding

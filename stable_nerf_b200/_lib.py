@@ -108,6 +108,8 @@ SIGNATURES = {
     "snerf_pack_sd_condition": (c_int, [_P, _P, _U, _U, _U, _F, _F, _P, _S]),
     "snerf_pack_sd_condition_backward": (c_int, [_P, _U, _U, _U, _F, _P, _S]),
     "snerf_adam_step": (c_int, [_P, _P, _P, _P, _U, _F, _F, _F, _F, _F, c_int, _U, c_int, _S]),
+    "snerf_adam_advance": (c_int, [_P, _F, _F, _F, _S]),
+    "snerf_adam_step_dev": (c_int, [_P, _P, _P, _P, _U, _F, _F, _F, _F, _F, c_int, _P, c_int, _S]),
     "snerf_field_backward_ex": (c_int, [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_size_t,
                                         _P, c_size_t, _P, _U, _S]),
     "snerf_hashgrid_backward_levels": (c_int, [POINTER(GridDesc), _P, _F, _P, _U, _P, _U, _U, _S]),

@@ -59,6 +59,52 @@ __global__ void __launch_bounds__(256) k_adam_step(float4* __restrict__ p, float
   }
 }
 
+// Graph-capturable form: the step count and the bias corrections live on the device, so the launches carry no argument
+// that changes from step to step and the optimiser can sit inside the training step's CUDA graph.
+struct AdamState {
+  int32_t step;     // optimiser steps applied so far
+  int32_t skip;     // != 0: the next advance applies nothing (and clears the flag)
+  float step_size;  // lr / (1 - b1^step)
+  float rsqrt_bc2;  // 1 / sqrt(1 - b2^step)
+  int32_t enabled;  // what the parameter kernels of this step read
+  int32_t pad[3];
+};
+__global__ void k_adam_advance(AdamState* st, float lr, float b1, float b2) {
+  if (st->skip) {
+    st->skip = 0;
+    st->enabled = 0;
+    return;
+  }
+  const int32_t s = ++st->step;
+  const double bc1 = 1.0 - pow((double)b1, (double)s), bc2 = 1.0 - pow((double)b2, (double)s);  // torch: python doubles
+  st->step_size = (float)((double)lr / bc1);
+  st->rsqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  st->enabled = 1;
+}
+__global__ void __launch_bounds__(256) k_adam_step_dev(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
+                                                       float4* __restrict__ v, uint32_t n4, float lr, float b1, float b2,
+                                                       float eps, float wd, int decoupled, const AdamState* __restrict__ st,
+                                                       int zero_grad) {
+  if (!st->enabled) return;
+  const float step_size = st->step_size, rsqrt_bc2 = st->rsqrt_bc2;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    float* P = &pp.x; float* G = &gg.x; float* Mv = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float grad = G[k];
+      if (decoupled) P[k] *= 1.0f - lr * wd;
+      else grad += wd * P[k];
+      Mv[k] = Mv[k] + (grad - Mv[k]) * (1.0f - b1);
+      V[k] = V[k] * b2 + (1.0f - b2) * grad * grad;
+      const float denom = sqrtf(V[k]) * rsqrt_bc2 + eps;
+      P[k] -= step_size * (Mv[k] / denom);
+    }
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 // out[b, 0:C*N] = image[b, 0:N*C] * scale + shift (flat; 2, -1 at train.py:75);  out[b, (C+k)*N + i] = rays_d[b, i, k] (train.py:76)
 __global__ void __launch_bounds__(256) k_pack_sd_condition(const float* __restrict__ image, const float* __restrict__ rays_d,
                                                            uint32_t N, uint32_t C, float scale, float shift,
@@ -132,6 +178,28 @@ int snerf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_
   k_adam_step<<<blocks, 256, 0, (cudaStream_t)stream>>>((float4*)params, (float4*)grads, (float4*)exp_avg,
                                                        (float4*)exp_avg_sq, n4, lr, beta1, beta2, eps, weight_decay,
                                                        decoupled_weight_decay, step_size, rsqrt_bc2, zero_grad);
+  return finish_launch();
+}
+
+/* see include/snerf.h */
+int snerf_adam_advance(void* state, float lr, float beta1, float beta2, snerf_stream_t stream) {
+  if (!state || ((uintptr_t)state & 15u)) return SNERF_E_BADARG;
+  k_adam_advance<<<1, 1, 0, (cudaStream_t)stream>>>((AdamState*)state, lr, beta1, beta2);
+  return finish_launch();
+}
+
+int snerf_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, uint32_t n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, int decoupled_weight_decay, const void* state,
+                        int zero_grad, snerf_stream_t stream) {
+  if (n == 0) return SNERF_OK;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !state) return SNERF_E_BADARG;
+  if ((n & 3u) || (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq | (uintptr_t)state) & 15u))
+    return SNERF_E_BADARG;
+  const uint32_t n4 = n / 4;
+  const uint32_t blocks = min(div_up(n4, 256), 148u * 16u);
+  k_adam_step_dev<<<blocks, 256, 0, (cudaStream_t)stream>>>((float4*)params, (float4*)grads, (float4*)exp_avg,
+                                                           (float4*)exp_avg_sq, n4, lr, beta1, beta2, eps, weight_decay,
+                                                           decoupled_weight_decay, (const AdamState*)state, zero_grad);
   return finish_launch();
 }
 

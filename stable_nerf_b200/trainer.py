@@ -69,11 +69,22 @@ class TrainStep:
 
     def __init__(self, model, n_rays, max_steps=1024, bg_color=1, T_thresh=1e-4, use_graph=True, world_size=1,
                  loss_scale=1.0, fused=True, perturb=False, dt_gamma=0, optimizer=None, overlap_allreduce=False,
-                 scatter_groups=2, group=None, exchange="auto", exchange_timeout_ms=0):
+                 scatter_groups=2, group=None, exchange="auto", exchange_timeout_ms=0, pipeline=False):
         self.model, self.n_rays, self.max_steps = model, int(n_rays), int(max_steps)
         self.bg_color, self.T_thresh, self.world_size = bg_color, T_thresh, world_size
         self.loss_scale = loss_scale
         self.fused, self.perturb, self.dt_gamma = bool(fused), bool(perturb), dt_gamma
+        # pipeline=True: what a step leaves to do once its gradients exist -- the gradient exchange between the ranks and
+        # the optimiser update -- is deferred to the START of the next step, on a second stream beside that step's ray
+        # march (near/far + march need the rays and the occupancy grid, not the parameters), and joined before the
+        # hash-grid gather.  A step is still march -> field -> composite -> loss -> backward -> exchange -> update, one
+        # exchange and one update per step; they just run under the next march (~80 us of the step at 4096 rays).
+        # ``finish()`` applies what the last step left pending.  Parameters / summed gradients read between steps are one
+        # update behind until ``finish()``.
+        self.pipeline = bool(pipeline)
+        self._pipe_stream = None
+        self._dry = True  # warm-up / dry-run bodies: never step the optimiser
+        self._capturing = False
         self.fuse_tail = True  # whole steps: composite forward + L1 + composite backward in one launch
         self.zero_in_backward = True  # the gradients' zero fills belong to the field backward call
         self._bufs = None
@@ -123,6 +134,22 @@ class TrainStep:
                 if exchange != "auto":
                     raise
                 self.exchange_error = str(e)
+
+    def _apply_pending(self):
+        """gradient exchange + optimiser update of the gradients the previous step produced (current stream)"""
+        if self.exchange is not None:
+            self.exchange.all_reduce()
+        if self.optimizer is not None and (self._capturing or not self._dry):
+            self.optimizer.step()
+
+    def _pipelined(self):
+        return self.pipeline and not (self.world_size > 1 and self.exchange is None)  # (NCCL after the replay: not deferred)
+
+    def finish(self):
+        """pipeline=True: apply the exchange / update the last ``step()`` left pending.  No-op otherwise."""
+        if self._pipelined() and self.fused and self.model.mean_count > 0:
+            self._dry = False
+            self._apply_pending()
 
     def _setup_p2p(self, dev, algo="auto"):
         """Move the parameters' .grad into one peer-mapped arena: [colour MLP | sigma MLP | table], 16-byte aligned, so
@@ -221,7 +248,15 @@ class TrainStep:
         if phase == "backward":
             return self._fused_backward(b, M, mark)
         mark("start")
-        if not self._opt_zeroes:
+        pipelined = self._pipelined() and phase == "both"
+        if pipelined:  # the previous step's exchange + update on a second stream, beside this step's march
+            if self._pipe_stream is None:
+                self._pipe_stream = torch.cuda.Stream(device=self.rays_o.device)
+            cur = torch.cuda.current_stream()
+            self._pipe_stream.wait_stream(cur)
+            with torch.cuda.stream(self._pipe_stream):
+                self._apply_pending()
+        if not self._opt_zeroes and not pipelined:
             # The field's gradients (table 46.5 MiB, MLP weights 0.4 MB) are zero-filled by the field backward itself
             # (SNERF_BWD_ZERO_*), on the library's side stream under the colour kernel; anything else is zeroed here.
             # (Zeroing everything on a side stream under the march was measured: +5 us/step -- the fills slow the
@@ -245,6 +280,12 @@ class TrainStep:
                                              P(b["rays"]), P(b["noises"]), 1, P(b["n_samples"]), P(b["march_ws"]),
                                              b["march_ws_bytes"], S), "march write")
         mark("march")
+        if pipelined:  # join: the parameters are updated, the gradients consumed
+            torch.cuda.current_stream().wait_stream(self._pipe_stream)
+            if not self._opt_zeroes:
+                for p in self.params:
+                    if not (self.zero_in_backward and (p is sp or p is cp)):
+                        p.grad.zero_()
         spd = sp.detach()
         chk(lib.snerf_field_forward(m.fdesc, P(b["xyzs"]), P(b["dirs"]), M, P(spd[nm:]), P(spd[:nm]), P(cp.detach()), prec,
                                     P(b["sigmas"]), P(b["rgbs"]), P(b["saved"]), b["saved_bytes"], P(b["field_ws"]),
@@ -263,7 +304,7 @@ class TrainStep:
                 "composite + L1 + composite backward")
             mark("composite_l1_fused")
             self.outputs = {"image": b["pred"], "depth": b["depth_norm"], "weights_sum": b["ws"]}
-            return self._fused_backward(b, M, mark, composite=False)
+            return self._fused_backward(b, M, mark, composite=False, exchange=not pipelined)
         chk(lib.snerf_composite_rays_train_forward(P(b["sigmas"]), P(b["rgbs"]), P(b["deltas"]), P(b["rays"]), M, N,
                                                    float(self.T_thresh), C, P(b["ws"]), P(b["depth"]), P(b["image"]), S),
             "composite forward")
@@ -278,7 +319,7 @@ class TrainStep:
             return
         self._fused_backward(b, M, mark)
 
-    def _fused_backward(self, b, M, mark, composite=True):
+    def _fused_backward(self, b, M, mark, composite=True, exchange=True):
         m, N, C = self.model, self.n_rays, self.model.channel_dim
         lib = _lib.load()
         P, S, chk = _lib.ptr, _lib.stream(), _lib.check
@@ -301,7 +342,7 @@ class TrainStep:
                                         P(b["saved"]), b["saved_bytes"], P(b["field_ws"]), b["field_ws_bytes"],
                                         P(b.get("d_enc")), flags, S), "field backward")
         mark("field_bwd")
-        if self.exchange is not None:  # all ranks' gradients summed in place, same stream: part of the captured step
+        if self.exchange is not None and exchange:  # all ranks' gradients summed in place, same stream: part of the captured step
             self.exchange.all_reduce()
 
     def profile_stages(self, iters=10):
@@ -386,6 +427,9 @@ class TrainStep:
         self.target.copy_(target)
         m = self.model
         m.train()
+        self._dry = True
+        if self.optimizer is not None and hasattr(self.optimizer, "init_state"):
+            self.optimizer.init_state()  # moments allocated before any capture
         for it in range(iters):
             if batches:
                 o, d, t = batches[it % len(batches)]
@@ -404,6 +448,19 @@ class TrainStep:
             self._capture()
         self._zero_grads_after_dry_runs()
 
+    def _reset_pipeline(self):
+        """The first pipelined step applies 'the previous step's' exchange and update before any real gradient exists:
+        make that a no-op (zero gradients sum to zero; the optimiser skips one application and does not count it)."""
+        if not self._pipelined():
+            return
+        for p in self.params:
+            p.grad.zero_()
+        if self.optimizer is not None:
+            if not hasattr(self.optimizer, "skip_next") or not getattr(self.optimizer, "capturable", False):
+                raise RuntimeError("pipeline=True needs an optimiser whose step can be captured: FusedAdam(..., capturable=True)")
+            self.optimizer.skip_next()
+        torch.cuda.synchronize()
+
     def _zero_grads_after_dry_runs(self):
         """With an optimiser that zeroes the gradients inside its own step (``zero_grad_in_step``) the fused body zeroes
         nothing, so the bodies run by warmup / capture / launch counting -- none followed by an optimiser step -- leave
@@ -412,6 +469,7 @@ class TrainStep:
             for p in self.params:
                 p.grad.zero_()
             torch.cuda.synchronize()
+        self._reset_pipeline()
 
     def _capture(self):
         m = self.model
@@ -427,8 +485,12 @@ class TrainStep:
         # measured no gain at N=2 (0.931 vs 0.941 ms/step) and made process teardown hang on this torch/NCCL pair.
         self.allreduce_in_graph = False
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._body()
+        self._capturing = True
+        try:
+            with torch.cuda.graph(self.graph):
+                self._body()
+        finally:
+            self._capturing = False
         before = _lib.launch_count()
         m.local_step = local_step
         self._mark = None
@@ -449,6 +511,7 @@ class TrainStep:
         if self.exchange is not None:
             self._check_arena()
             self.exchange.raise_on_error()  # a rank gave up waiting in an earlier step: those gradients were never summed
+        self._dry = False
         if self.graph is not None:
             self.graph.replay()
         else:
@@ -458,7 +521,7 @@ class TrainStep:
                 self._scatter_and_reduce()
             else:
                 allreduce_gradients(self.params, self.world_size, group=self.group)
-        if self.optimizer is not None:
+        if self.optimizer is not None and not (self._pipelined() and self.fused and self.model.mean_count > 0):
             self.optimizer.step()
         return self.loss
 
@@ -482,6 +545,8 @@ class TrainStep:
         M = _pad_up(int(m.mean_count), 128)
         if self._bufs is not None and self._bufs["M"] == M:
             return False
+        self.finish()  # (pipeline: the last step's exchange / update must not be lost in the dry runs below)
+        self._dry = True
         self.graph = self._graph_fwd = self._graph_bwd = None
         local_step = m.local_step
         for _ in range(2):

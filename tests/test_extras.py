@@ -87,6 +87,30 @@ def test_fused_adam_vs_torch_and_golden(name, built_lib, cuda):
         assert float(a.grad.abs().max()) == 0.0
     assert rel(a.detach().cpu().numpy(), b.detach().cpu().numpy()) <= 2e-6
     assert ours.state_dict()["state"][0]["step"] == 3
+    # capturable form (step count and bias corrections on the device): same trajectory; a skipped application does not
+    # count; the whole step replays as a CUDA graph
+    p = torch.nn.Parameter(torch.from_numpy(g["adam_p0"]).to(cuda))
+    opt = (FusedAdamW if decoupled else FusedAdam)([p], capturable=True, **kw)
+    p.grad = torch.zeros_like(p)
+    opt.skip_next()
+    opt.step()  # skipped: nothing moves, nothing counts
+    assert np.array_equal(p.detach().cpu().numpy(), g["adam_p0"]) and opt.steps_applied() == [0]
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        p.grad.copy_(torch.from_numpy(g["adam_grads"][0]).to(cuda))
+        opt.step()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    assert rel(p.detach().cpu().numpy(), g[name + "_traj"][0]) <= 2e-6
+    with torch.cuda.graph(graph):
+        opt.step()
+    for k, grad in list(enumerate(g["adam_grads"]))[1:]:
+        p.grad.copy_(torch.from_numpy(grad).to(cuda))
+        graph.replay()
+        assert rel(p.detach().cpu().numpy(), g[name + "_traj"][k]) <= 2e-6, f"captured step {k + 1}"
+    assert opt.steps_applied() == [len(g["adam_grads"])]
 
 
 @pytest.mark.gpu
