@@ -500,6 +500,7 @@ def cfg5_profile(args, dev, world, rank, bitfield, barrier, max_over_ranks, n_to
         e0.record()
         for k in range(steps):
             ts.step_from_packed(packed[k % len(packed)])
+        ts.finish()
         e1.record()
         barrier()
         return max_over_ranks(e0.elapsed_time(e1)) / steps
@@ -511,7 +512,7 @@ def cfg5_profile(args, dev, world, rank, bitfield, barrier, max_over_ranks, n_to
     # ---- sharded
     model = make_model()
     ts = TrainStep(model, hi - lo, max_steps=MAX_STEPS, use_graph=not args.no_graph, world_size=world, loss_scale=1.0 / world,
-                   exchange=args.exchange)
+                   exchange=args.exchange, pipeline=not args.no_pipeline)
     shards = [tuple(torch.from_numpy(np.ascontiguousarray(a[lo:hi])).to(dev) for a in b[1:]) for b in full]
     packed = [torch.cat([t.reshape(-1) for t in s]) for s in shards]
     ts.warmup(*shards[0], iters=2, batches=shards)
@@ -586,8 +587,10 @@ def run_gpu_arm(args):
     broadcast_occupancy(model)
     model.train()
 
+    # several ranks: the gradient exchange of step k runs beside step k+1's ray march (TrainStep pipeline=True), still one
+    # exchange per step; finish() applies the last one inside the timed region
     ts = TrainStep(model, RAYS_PER_GPU, max_steps=MAX_STEPS, use_graph=not args.no_graph, world_size=world,
-                   loss_scale=1.0 / world, exchange=args.exchange)
+                   loss_scale=1.0 / world, exchange=args.exchange, pipeline=world > 1 and not args.no_pipeline)
     d_batches = [tuple(torch.from_numpy(a).to(dev) for a in b[1:]) for b in batches]
     d_packed = [torch.cat([t.reshape(-1) for t in b]) for b in d_batches]   # [rays_o | rays_d | target], resident in HBM
     h_packed = []                                                           # the same in pinned host memory (one H2D copy)
@@ -629,6 +632,7 @@ def run_gpu_arm(args):
             e0.record()
             for k in range(args.steps):
                 ts.step_from_packed(d_packed[k % N_BATCHES])  # one 147 KB device copy + the step (a graph replay)
+            ts.finish()  # (pipelined exchange of the last step)
             e1.record()
             barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
@@ -643,20 +647,34 @@ def run_gpu_arm(args):
         f0.record()
         for _ in range(args.steps):
             ts.step()
+        ts.finish()
         f1.record()
         barrier()
         frozen_ms = max_over_ranks(f0.elapsed_time(f1))
 
-        # ---- end to end: pinned host inputs -> H2D -> step -> loss D2H, wall clock between device-complete points
+        # ---- end to end, the data-loader form: every step copies ITS inputs from pinned host memory (147 KB, started on a
+        # copy stream while the previous step computes) and brings ITS loss back to the host (4 B, into a pinned slot); the
+        # host reads the loss of step k-1 while step k runs, so the device never waits for the host.  Wall clock between
+        # device-complete points, all copies and the last loss inside.
         for k in range(args.warmup):
             ts.step_from_packed(h_packed[k % N_BATCHES], read_loss=True)
         barrier()
         with clocks.mark():
             t0 = time.perf_counter()
             for k in range(args.steps):
-                loss = ts.step_from_packed(h_packed[k % N_BATCHES], read_loss=True)
+                ts.step_from_packed(h_packed[k % N_BATCHES], read_loss="lagged", next_packed=h_packed[(k + 1) % N_BATCHES])
+            loss = ts.drain()
+            ts.finish()
             barrier()
             e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        # ---- the synchronous form of the same (H2D, step, loss D2H, host waits for the loss before the next step)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            loss_sync = ts.step_from_packed(h_packed[k % N_BATCHES], read_loss=True)
+        ts.finish()
+        barrier()
+        e2e_sync_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
 
     total_rays = RAYS_PER_GPU * world
     out = {
@@ -673,6 +691,9 @@ def run_gpu_arm(args):
                               f"{sum(c > M_step for c in batch_counts)} of them overflow M and lose their last rays as in "
                               "the reference (raymarching.cu:417)",
                    "cuda_graph": ts.graph is not None, "parallelism": f"ray-sharded dp{world}",
+                   "exchange_schedule": ("the exchange of step k runs beside the ray march of step k+1 (second stream inside the "
+                                         "graph, joined before the hash-grid gather); K exchanges for K steps, the last one by "
+                                         "finish() inside the timed region") if ts._pipelined() else "after the backward, same stream",
                    "gradient_exchange": {"none": "none (one rank)",
                                          "nvls": "one kernel per rank, reduced inside the NVSwitch (multimem.ld_reduce / "
                                                  "multimem.st on a multicast mapping of the gradient arenas), inside the "
@@ -684,7 +705,11 @@ def run_gpu_arm(args):
                    "l2": "not flushed between steps: the step streams params 49 MB + grads 49 MB + samples and "
                          "activations (> 126 MB L2 together); the hash table is meant to stay L2-resident across steps"},
         "e2e": {"value": total_rays * args.steps / (e2e_ms * 1e-3), "unit": "rays/s",
-                "h2d_bytes_per_step": int(h_packed[0].numel() * 4), "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": int(h_packed[0].numel() * 4), "d2h_bytes_per_step": 4,
+                "form": "TrainStep.step_from_packed(read_loss='lagged', next_packed=...): per step one H2D copy of that step's "
+                        "inputs (copy stream, under the previous step) and one D2H of that step's loss, read by the host one "
+                        "step later; synchronous form (host waits for every loss): "
+                        f"{total_rays * args.steps / (e2e_sync_ms * 1e-3):.0f} rays/s"},
         "frozen_batch": {"ms_per_step": frozen_ms / args.steps, "rays_per_s": total_rays * args.steps / (frozen_ms * 1e-3),
                          "note": "one batch replayed every step with no input copy (round 1's `value`): optimistic"},
         "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
@@ -693,23 +718,49 @@ def run_gpu_arm(args):
     }
 
     if rank == 0 and world == 1 and not args.no_stages and ts.fused:
-        # the same step followed by the fused Adam update (test_nerf.py:52 hyper-parameters): fwd + bwd + optimiser
+        # the same step with the fused Adam update (test_nerf.py:52 hyper-parameters): fwd + bwd + optimiser.
+        # (a) the update inside the step's graph, beside the next step's ray march (pipeline=True); (b) stepped eagerly
+        # after the replay (round 1's form)
         from stable_nerf_b200.optim import FusedAdam
-        ts.optimizer = FusedAdam(model.get_params(1e-4), betas=(0.9, 0.99), eps=1e-15)
-        for _ in range(3):
-            ts.step()
+        saved_params = [p.detach().clone() for p in ts.params]
+        opt = FusedAdam(model.get_params(1e-4), betas=(0.9, 0.99), eps=1e-15, capturable=True, zero_grad_in_step=True)
+        ts_opt = TrainStep(model, RAYS_PER_GPU, max_steps=MAX_STEPS, use_graph=not args.no_graph, optimizer=opt, pipeline=True)
+        local_step, mean_count = model.local_step, model.mean_count
+        model.mean_count = 0
+        ts_opt.warmup(d_o, d_d, d_t, iters=N_BATCHES, batches=d_batches)
+        for k in range(3):
+            ts_opt.step_from_packed(d_packed[k % N_BATCHES])
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
-        for _ in range(args.steps):
-            ts.step()
+        for k in range(args.steps):
+            ts_opt.step_from_packed(d_packed[k % N_BATCHES])
+        ts_opt.finish()
         a1.record()
         torch.cuda.synchronize()
         ms_opt = a0.elapsed_time(a1) / args.steps
+        del ts_opt
+        ts.optimizer = FusedAdam(model.get_params(1e-4), betas=(0.9, 0.99), eps=1e-15)
+        for k in range(3):
+            ts.step_from_packed(d_packed[k % N_BATCHES])
+        torch.cuda.synchronize()
+        a0.record()
+        for k in range(args.steps):
+            ts.step_from_packed(d_packed[k % N_BATCHES])
+        a1.record()
+        torch.cuda.synchronize()
+        ms_opt_eager = a0.elapsed_time(a1) / args.steps
         ts.optimizer = None
+        with torch.no_grad():  # the measurements that follow run on the parameters the step was timed with
+            for p, q in zip(ts.params, saved_params):
+                p.copy_(q)
+        model.local_step, model.mean_count = local_step, mean_count
         out["with_optimizer"] = {"ms_per_step": ms_opt, "rays_per_s": RAYS_PER_GPU / (ms_opt * 1e-3),
-                                 "optimizer": "FusedAdam betas=(0.9,0.99) eps=1e-15 over 12.29 M fp32 params "
-                                              "(344 MB/step), stepped eagerly after the graph replay"}
+                                 "extra_us_over_value": round((ms_opt - ms / args.steps) * 1e3, 1),
+                                 "optimizer": "FusedAdam betas=(0.9,0.99) eps=1e-15 over 12.29 M fp32 params (344 MB/step), "
+                                              "capturable: its launches are part of the step's CUDA graph, run beside the "
+                                              "next step's ray march, and leave the gradients zeroed (no memset)",
+                                 "stepped_eagerly_after_the_replay_ms": ms_opt_eager}
     if world > 1:
         # what a reader needs to trust a multi-GPU number: which exchange ran, that no wait ran out, and that every rank
         # holds the same gradients after it
@@ -846,6 +897,7 @@ def main():
     ap.add_argument("--no-large", action="store_true")
     ap.add_argument("--no-ref-kernels", action="store_true")
     ap.add_argument("--no-cfg5", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nvls", "p2p", "nccl"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -666,9 +666,17 @@ class TrainStep:
         n3 = self.n_rays * 3
         return st, (st[:n3].view(self.n_rays, 3), st[n3:2 * n3].view(self.n_rays, 3), st[2 * n3:].view(self.n_rays, -1))
 
-    def step_from_packed(self, packed, read_loss=False):
+    def step_from_packed(self, packed, read_loss=False, next_packed=None):
         """One step on a batch packed as [rays_o | rays_d | target] (device tensor, or pinned host tensor: ONE copy of
-        36+4C B/ray either way).  read_loss: also bring the loss back to the host (synchronises) -- the end-to-end form."""
+        36+4C B/ray either way).
+        read_loss=True: also bring the loss back to the host and wait for it -- the end-to-end form (synchronises).
+        read_loss="lagged": the data-loader form of the same.  Every step still copies its inputs from the host and reads
+        its loss back, but nothing waits on the step just launched: the loss of THIS step is copied to a pinned slot
+        asynchronously and the call returns the loss of the PREVIOUS step (None for the first), so the device never idles
+        between steps; ``next_packed`` (pinned host tensor) starts the next step's input copy on a copy stream while this
+        step computes.  ``drain()`` returns the last step's loss."""
+        if read_loss == "lagged":
+            return self._step_lagged(packed, next_packed)
         self._inputs.copy_(packed, non_blocking=True)
         self.step()
         if not read_loss:
@@ -678,6 +686,49 @@ class TrainStep:
         if self.exchange is not None:
             self.exchange.raise_on_error()
         return float(self.loss_host)
+
+    def _step_lagged(self, packed, next_packed):
+        dev = self._inputs.device
+        if getattr(self, "_lag", None) is None:
+            self._lag = dict(copy_stream=torch.cuda.Stream(device=dev), staged=torch.empty_like(self._inputs), staged_src=None,
+                             staged_ev=torch.cuda.Event(), slots=[torch.zeros((), pin_memory=True) for _ in range(2)],
+                             evs=[torch.cuda.Event(), torch.cuda.Event()], k=0, pending=None, consumed=torch.cuda.Event())
+        L = self._lag
+        cur = torch.cuda.current_stream()
+        if L["staged_src"] is packed:  # its H2D copy was started while the previous step ran
+            cur.wait_event(L["staged_ev"])
+            self._inputs.copy_(L["staged"], non_blocking=True)
+        else:
+            self._inputs.copy_(packed, non_blocking=True)
+        L["consumed"].record(cur)
+        self.step()
+        slot = L["k"] % 2
+        L["slots"][slot].copy_(self.loss, non_blocking=True)
+        L["evs"][slot].record(cur)
+        L["staged_src"] = None
+        if next_packed is not None:
+            with torch.cuda.stream(L["copy_stream"]):
+                L["copy_stream"].wait_event(L["consumed"])  # the staging buffer's previous content has been consumed
+                L["staged"].copy_(next_packed, non_blocking=True)
+                L["staged_ev"].record(L["copy_stream"])
+            L["staged_src"] = next_packed
+        prev, L["pending"] = L["pending"], slot
+        L["k"] += 1
+        if prev is None:
+            return None
+        L["evs"][prev].synchronize()  # the previous step's loss has landed; the step just launched keeps running
+        if self.exchange is not None:
+            self.exchange.raise_on_error()
+        return float(L["slots"][prev])
+
+    def drain(self):
+        """Loss of the last ``read_loss="lagged"`` step (waits for it)."""
+        L = getattr(self, "_lag", None)
+        if L is None or L["pending"] is None:
+            return None
+        L["evs"][L["pending"]].synchronize()
+        v, L["pending"] = float(L["slots"][L["pending"]]), None
+        return v
 
     def step_from_host(self, rays_o_pinned, rays_d_pinned, target_pinned):
         """End-to-end form: pinned host inputs -> device, one step, loss back to the host (synchronises)."""
