@@ -788,6 +788,26 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
     if (blockIdx.x < n_tiles) fetch_tile(blockIdx.x);
     cta_mark(1);
 
+    // Weight gradient of hidden matrix i (accumulated in TMEM over the CTA's tiles) -> this CTA's row of the partials.
+    // (Flushing a matrix during the CTA's last tile, as soon as its last wgrad has completed, was measured: the stores
+    // take the same time inside the tile as after it -- 148 CTAs write 33 MB at once, which is bandwidth.)
+    // A thread holds one ROW of an accumulator, so storing it row-major makes every store instruction of a warp touch 32
+    // lines (one 16-byte piece each): the 221 KB of a CTA took 9 us, bound by the LSU.  The partials are private scratch,
+    // so matrices with 128 rows are written COLUMN-BLOCK major instead -- float4 c4 of row r at [c4 * 128 + r]: a warp's
+    // store is 512 contiguous bytes -- and k_reduce_partials, which reads them in that order, undoes the permutation.
+    float* const part = p.dw_part + (size_t)blockIdx.x * p.n_params;
+    auto flush_hidden = [&](int i) {
+      float4* gw = reinterpret_cast<float4*>(part + p.net.src_off[i]) + row;
+#pragma unroll
+      for (uint32_t cc = 0; cc < 2; cc++) {
+        float v[32];
+        tmem_ld32(tlane + 128u * (uint32_t)i + hc * 64u + cc * 32u, v);
+        const uint32_t c4 = hc * 16u + cc * 8u;
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) gw[(size_t)(c4 + k / 4) * kTile] = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+      }
+    };
+
     for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, iter++) {
       const uint32_t m = t * kTile + row;
       mark(0);
@@ -841,6 +861,7 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
       // ---------------- hidden matrices W_{L-1} .. W_1 [128 x 128]
       uint8_t* gcur = ebuf;
       uint8_t* gnext = a_hid(L);
+      const bool last_tile = t + gridDim.x >= n_tiles;
       for (int i = L - 1; i >= 1; i--) {
         mask_prefetch(a_hid(i), row, hc, mk);
         wait_mma();  // dgrad (the wgrad runs under the epilogue)
@@ -852,7 +873,10 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
       }
 
       // ---------------- first matrix W_0 [128 x 32]: wgrad in columns [0,32), input gradient in [32,64)
-      if (t + gridDim.x < n_tiles) fetch_tile(t + gridDim.x);  // lands while the last phase runs
+      // (round 2, measured and dropped: requesting these rows earlier moves their latency onto the TMEM load of whichever
+      // phase follows; requesting them into the L2 here and loading them at the end of the tile exposes ~400 clk at the start
+      // of every tile -- the kernels got 2-10 us slower either way)
+      if (!last_tile) fetch_tile(t + gridDim.x);  // lands while the last phase runs
       wait_mma();
       mark(12);
       if (NET != 0 && hc == 0) {
@@ -900,7 +924,6 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
     // into the same 200 KB with atomics serialise at the L2 and cost as much as several tiles)
     if (iter > 0) {
       tc_fence_after();
-      float* part = p.dw_part + (size_t)blockIdx.x * p.n_params;
       if (hc == 0) {
         float first[32], last[16];
         if (NET == 0) {
@@ -912,24 +935,14 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
 #pragma unroll
           for (int k = 0; k < 16; k++) last[k] = acc_last[NET == 0 ? 0 : k];
         }
-        float4* g0 = reinterpret_cast<float4*>(part + p.net.src_off[0] + (size_t)row * 32);
+        float4* g0 = reinterpret_cast<float4*>(part + p.net.src_off[0]) + row;  // column-block major, like the hidden ones
 #pragma unroll
-        for (int k = 0; k < 8; k++) g0[k] = make_float4(first[4 * k], first[4 * k + 1], first[4 * k + 2], first[4 * k + 3]);
+        for (int k = 0; k < 8; k++) g0[(size_t)k * kTile] = make_float4(first[4 * k], first[4 * k + 1], first[4 * k + 2], first[4 * k + 3]);
         float* gl = part + p.net.src_off[L];
 #pragma unroll
         for (int n = 0; n < 16; n++) gl[(size_t)n * kTile + row] = last[n];
       }
-      for (int i = 1; i < L; i++) {
-        float* gw = part + p.net.src_off[i] + (size_t)row * kTile + hc * 64u;
-#pragma unroll
-        for (uint32_t cc = 0; cc < 2; cc++) {
-          float v[32];
-          tmem_ld32(tlane + 128u * (uint32_t)i + hc * 64u + cc * 32u, v);
-#pragma unroll
-          for (int k = 0; k < 32; k += 4)
-            *reinterpret_cast<float4*>(gw + cc * 32u + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-        }
-      }
+      for (int i = 1; i < L; i++) flush_hidden(i);
     }
   }
   tc_fence_before();
@@ -940,9 +953,11 @@ __global__ void __launch_bounds__(bwd_threads(NET), 1) k_field_bwd(const TcParam
 
 // grad_w[i] += sum over CTAs of part[c][i]: fixed summation order inside a group of CTAs, one atomic per group
 constexpr uint32_t kReduceGroups = 16;
+// The partials of the matrices with 128 rows (all but the last) are column-block major (k_field_bwd: float4 c4 of row r
+// at [c4 * 128 + r]); they are read in that order and the sum goes to its row-major place in grad_w.
 __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict__ part, uint32_t n_ctas, uint32_t n_params,
-                                                         float* __restrict__ grad_w) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
+                                                         float* __restrict__ grad_w, const PackedNet net) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index in the partials' layout
   if (i * 4u >= n_params) return;
   const uint32_t per = div_up(n_ctas, kReduceGroups), c0 = blockIdx.y * per, c1 = min(n_ctas, c0 + per);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -950,7 +965,14 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
     const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)c * n_params) + i);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  if (c1 > c0) atomicAdd(reinterpret_cast<float4*>(grad_w) + i, acc);
+  int m = 0;
+  while (m + 1 < net.n_mats && i * 4u >= net.src_off[m + 1]) m++;
+  uint32_t dest = i;
+  if (m + 1 < net.n_mats) {  // [128 x in] matrix: column-block major -> row-major
+    const uint32_t off4 = net.src_off[m] / 4u, local = i - off4, in4 = (uint32_t)net.in_dim[m] / 4u;
+    dest = off4 + (local % kTile) * in4 + local / kTile;
+  }
+  if (c1 > c0) atomicAdd(reinterpret_cast<float4*>(grad_w) + dest, acc);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1111,7 +1133,7 @@ static int launch_bwd(const TcParams& p, const PackedNet& n, uint32_t M, cudaStr
         return (int)cudaGetLastError();
       sr = side->stream;
     }
-    k_reduce_partials<<<dim3(div_up(p.n_params / 4, 256), kReduceGroups), 256, 0, sr>>>(p.dw_part, grid_for(M), p.n_params, p.grad_w);
+    k_reduce_partials<<<dim3(div_up(p.n_params / 4, 256), kReduceGroups), 256, 0, sr>>>(p.dw_part, grid_for(M), p.n_params, p.grad_w, n);
     return SNERF_OK;
   }
   const uint32_t slots = bwd_slots(n, NET);
