@@ -411,23 +411,30 @@ def first_epoch_profile(model, ts, iters=10):
     (raymarching.py:196-229) -- so the step cannot be a graph; it runs through NeRFNetwork.render + autograd, eagerly.
     This is the path TrainStep.warmup() itself takes for its first steps."""
     import torch
-    mean_count, local_step = model.mean_count, model.local_step
+    mean_count, local_step, bufs = model.mean_count, model.local_step, ts._bufs
     model.mean_count = 0
+    res = {}
     try:
-        for _ in range(3):
-            ts._body()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            ts._body()
-        e1.record()
-        torch.cuda.synchronize()
+        for fused in (True, False):
+            ts.first_epoch_fused = fused
+            for _ in range(3):
+                ts._body()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                ts._body()
+            e1.record()
+            torch.cuda.synchronize()
+            res[fused] = e0.elapsed_time(e1) / iters
     finally:
-        model.mean_count, model.local_step = mean_count, local_step
-    ms = e0.elapsed_time(e1) / iters
-    return {"workload": "cfg2 before mean_count exists: eager NeRFNetwork.render + autograd, sample total read back every step",
-            "ms_per_step": ms, "rays_per_s": RAYS_PER_GPU / (ms * 1e-3)}
+        ts.first_epoch_fused = True
+        model.mean_count, model.local_step, ts._bufs = mean_count, local_step, bufs
+    ms = res[True]
+    return {"workload": "cfg2 before mean_count exists (SURVEY Q8): the fused step issued eagerly, rows sized from the sample total "
+                        "read back after the count pass (one 4-byte D2H per step, no graph)",
+            "ms_per_step": ms, "rays_per_s": RAYS_PER_GPU / (ms * 1e-3),
+            "through_render_and_autograd_ms": res[False]}
 
 
 def large_batch_profile(model, dev, pk, n_rays=1 << 18):

@@ -85,6 +85,7 @@ class TrainStep:
         self._pipe_stream = None
         self._dry = True  # warm-up / dry-run bodies: never step the optimiser
         self._capturing = False
+        self.first_epoch_fused = True  # the mean_count <= 0 steps take the fused body too (one 4-byte read per step)
         self.fuse_tail = True  # whole steps: composite forward + L1 + composite backward in one launch
         self.zero_in_backward = True  # the gradients' zero fills belong to the field backward call
         self._bufs = None
@@ -187,8 +188,15 @@ class TrainStep:
 
     def _body(self):
         m = self.model
-        if self.fused and m.training and m.mean_count > 0 and m.bg_radius <= 0 and hasattr(m, "fdesc"):
-            return self._body_fused()
+        if self.fused and m.training and m.bg_radius <= 0 and hasattr(m, "fdesc"):
+            if m.mean_count > 0:
+                return self._body_fused()
+            if self.first_epoch_fused:
+                # before update_extra_state has produced mean_count the reference sizes the step from the
+                # measured sample total (raymarching.py:196-229: N*max_steps rows zero-filled, .item(), empty_cache).
+                # Same step here as the same straight sequence of C-ABI calls, with that ONE 4-byte read after the
+                # count pass -- no N*max_steps buffers, no autograd graph.
+                return self._body_fused(first_epoch=True)
         for p in self.params:
             p.grad.zero_()
         out = m.render(self.rays_o[None], self.rays_d[None], bg_color=self.bg_color, max_steps=self.max_steps,
@@ -228,7 +236,7 @@ class TrainStep:
         self._bufs = b
         return b
 
-    def _body_fused(self, phase="both"):
+    def _body_fused(self, phase="both", first_epoch=False):
         """The same step as a straight sequence of C-ABI calls: no autograd graph, no torch glue kernels.
         phase: "both" (a whole step), or "forward" / "backward" for callers that put their own differentiable stage
         between the rendered image and the NeRF's backward (``forward()`` / ``backward(grad_image)``).
@@ -240,8 +248,13 @@ class TrainStep:
         lib = _lib.load()
         P, S, chk = _lib.ptr, _lib.stream(), _lib.check
         prec = _precision_code(m.precision)
-        M = _pad_up(int(m.mean_count), 128)
-        b = self._fused_buffers(M)
+        if first_epoch:
+            # rows are known after the count pass; buffers for the largest total seen so far (in 64 Ki-row steps)
+            M = 0
+            b = self._bufs if self._bufs is not None else self._fused_buffers(1 << 16)
+        else:
+            M = _pad_up(int(m.mean_count), 128)
+            b = self._fused_buffers(M)
         sp, cp = m.sigma_net.params, m.color_net.params
         nm = m.sigma_net.n_mlp
         mark = self._mark or (lambda name: None)
@@ -275,6 +288,17 @@ class TrainStep:
                                                   float(m.min_near), *geom, P(b["nears"]), P(b["fars"]), P(counter),
                                                   P(b["noises"]), P(b["march_ws"]), b["march_ws_bytes"], S),
             "near/far + march count")
+        if first_epoch:
+            total = int(counter[0].item())  # the step's one read-back (raymarching.py:223)
+            M = _pad_up(max(total, 1), 128)
+            if b["M"] < M:
+                b = self._fused_buffers(_pad_up(M, 1 << 16))
+                # (the count pass wrote nears/fars and its workspace into the old buffers: run it again into the new ones)
+                counter.zero_()
+                chk(lib.snerf_march_rays_train_count_aabb(P(self.rays_o), P(self.rays_d), P(m.density_bitfield), P(m.aabb_train),
+                                                          float(m.min_near), *geom, P(b["nears"]), P(b["fars"]), P(counter),
+                                                          P(b["noises"]), P(b["march_ws"]), b["march_ws_bytes"], S),
+                    "near/far + march count")
         chk(lib.snerf_march_rays_train_write(P(self.rays_o), P(self.rays_d), P(m.density_bitfield), *geom, M,
                                              P(b["nears"]), P(b["fars"]), P(b["xyzs"]), P(b["dirs"]), P(b["deltas"]),
                                              P(b["rays"]), P(b["noises"]), 1, P(b["n_samples"]), P(b["march_ws"]),

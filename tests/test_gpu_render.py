@@ -520,3 +520,39 @@ def test_pipelined_step_with_captured_optimizer_matches_the_plain_loop(built_lib
         # fp32 atomics are ordered differently from run to run: compare the trajectories in the L2 sense
         moved = float((a - a0).double().norm())
         assert moved > 0 and float((a - b).double().norm()) <= 2e-2 * moved, "same trajectory"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_first_epoch_fused_body_matches_render_plus_autograd(precision, built_lib, cuda):
+    """Before mean_count exists the step is sized from the sample total read back after the count pass
+    (raymarching.py:196-229).  TrainStep runs it as the fused sequence of C-ABI calls with that one 4-byte read; the
+    reference-shaped path (NeRFNetwork.render + autograd) gives the same loss and gradients, for batches of different
+    sample totals in a row (the buffers grow, the rows passed to the kernels follow each batch)."""
+    from stable_nerf_b200 import synthetic as syn
+    from stable_nerf_b200.trainer import TrainStep
+    N, C = 640, 3
+    batches = []
+    for k, (n_views, seed) in enumerate([(2, 9), (1, 4), (3, 7)]):
+        ro, rd = syn.train_batch(N, 100, 100, 138.0, n_views=n_views, seed=seed)
+        tg = np.random.default_rng(k).random((N, C), dtype=np.float32)
+        batches.append([torch.from_numpy(a).to(cuda) for a in (ro, rd, tg)])
+    res = {}
+    for fused_first in (True, False):
+        model = _fresh_model(C, precision, cuda)
+        ts = TrainStep(model, N, max_steps=128, use_graph=False)
+        ts.first_epoch_fused = fused_first
+        assert model.mean_count == 0
+        out = []
+        for b in batches:
+            loss = ts.step(*b)  # mean_count <= 0: the first-epoch path
+            torch.cuda.synchronize()
+            out.append((float(loss), int(model.step_counter[(model.local_step - 1) % 16, 0]),
+                        model.sigma_net.params.grad.cpu().numpy().copy(), model.color_net.params.grad.cpu().numpy().copy()))
+        res[fused_first] = out
+        assert model.mean_count == 0
+    tol = 1e-4 if precision == "fp32" else 2e-3
+    totals = [o[1] for o in res[True]]
+    assert len(set(totals)) == 3, "three different sample totals"
+    for a, b in zip(res[True], res[False]):
+        assert a[1] == b[1] and abs(a[0] - b[0]) <= 1e-6 * abs(b[0])
+        assert rel_err(a[2], b[2]) <= tol and rel_err(a[3], b[3]) <= tol
