@@ -460,6 +460,14 @@ int snerf_hashgrid_backward_levels(const snerf_grid_desc* g, const float* xyzs, 
                                    uint32_t M, float* grad_table, uint32_t level_begin, uint32_t level_end,
                                    snerf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Measurement and test hooks.  NOT part of the product library: libsnerf_b200.so is compiled without
+ * SNERF_DEBUG_HOOKS -- its tunables are compile-time constants, it keeps no settable process state and exports
+ * none of the symbols below.  libsnerf_b200_dbg.so is the same sources compiled with -DSNERF_DEBUG_HOOKS (plus
+ * csrc/tc_selftest.cu); tests that exercise both instantiations of a kernel, scripts/ and bench.py's per-kernel
+ * timings load that one.
+ * ---------------------------------------------------------------------------------------------- */
+#ifdef SNERF_DEBUG_HOOKS
 /* Hardware self-test of the tcgen05 building blocks: D[128,N] = A[128,K] * B[N,K]^T (bf16 operands, fp32
  * accumulate) for one tile, with either operand staged K-major or MN-major (a_mn / b_mn).  Not on the hot path. */
 int snerf_tc_selftest(const float* A, const float* B, float* D, uint32_t N, uint32_t K, int a_mn, int b_mn,
@@ -482,12 +490,12 @@ void snerf_debug_set_side_reduce(uint32_t on);
 /* Measurement aid: levels with resolution <= res merge equal cells inside a warp before the scatter-add (default 300). */
 void snerf_debug_set_dedupe_max_res(uint32_t res);
 
-/* Round-2 candidate, off by default (unmeasured): 1 = the scatter-add's segmented scan stops at the depth the warp's
- * longest run of equal cells needs instead of always five steps; the sums are the same bits. */
+/* 1 (default since its round-2 A/B) = the scatter-add's segmented scan stops at the depth the warp's longest run of
+ * equal cells needs instead of always five steps; the sums are the same bits. */
 void snerf_debug_set_scatter_adaptive_scan(uint32_t on);
 
-/* Round-2 candidate, off by default (unmeasured): 1 = snerf_composite_l1_train requests a ray's next 32 sample rows
- * before the scans of the current 32 (the loads move, the arithmetic and its bits do not). */
+/* 1 (default since its round-2 A/B) = snerf_composite_l1_train requests a ray's next 32 sample rows before the scans
+ * of the current 32 (the loads move, the arithmetic and its bits do not). */
 void snerf_debug_set_tail_prefetch(uint32_t on);
 
 /* Timing probe of the tcgen05 building blocks (one CTA, clock64): out = 32 int64 on the device.  Not on the hot path. */
@@ -497,6 +505,7 @@ int snerf_tc_probe(long long* out, int variant, snerf_stream_t stream);
  * the bf16 path (net 0: sigma, 1: colour) store clock64() marks of CTA 0's second tile at every phase boundary
  * ([0] = number of marks).  NULL switches it off. */
 void snerf_debug_phase_buffer(void* dev_buffer, int net);
+#endif /* SNERF_DEBUG_HOOKS */
 
 /* nerf/activation.py:6-18.  y = exp(x); dx = g * exp(clamp(x,-15,15)). */
 int snerf_trunc_exp_forward(const float* x, uint32_t n, float* y, snerf_stream_t stream);

@@ -6,6 +6,7 @@ import numpy as np, torch
 import bench
 from stable_nerf_b200 import NeRFNetwork, _lib, raymarching as rm
 dev = torch.device("cuda:0")
+_lib.use_debug_library()  # hooks live in libsnerf_b200_dbg.so
 lib = _lib.load()
 P, S, chk = _lib.ptr, _lib.stream, _lib.check
 bitfield, rays_o, rays_d, target = bench.workload(4096, 0)

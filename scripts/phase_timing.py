@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from stable_nerf_b200 import NeRFNetwork, _lib
 dev = torch.device("cuda:0")
+_lib.use_debug_library()  # hooks live in libsnerf_b200_dbg.so
 lib = _lib.load()
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 128 * 4
 model = NeRFNetwork(channel_dim=3, precision="bf16").to(dev)

@@ -29,6 +29,7 @@ CONFIGS = [  # name, adaptive scan, tail prefetch, dedupe_max_res
 
 def main():
     dev = torch.device("cuda", 0)
+    _lib.use_debug_library()  # hooks live in libsnerf_b200_dbg.so
     lib = _lib.load()
     bitfield, rays_o, rays_d, target = bench.workload(bench.RAYS_PER_GPU, seed=0)
     d_o, d_d, d_t = (torch.from_numpy(a).to(dev) for a in (rays_o, rays_d, target))

@@ -2,6 +2,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from stable_nerf_b200 import _lib
+_lib.use_debug_library()  # hooks live in libsnerf_b200_dbg.so
 lib = _lib.load()
 for variant in (0, 1, 2, 3):
     out = torch.zeros(32, dtype=torch.int64, device="cuda")

@@ -12,6 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsnerf_b200.so")
+DBG_LIB_PATH = os.path.join(_HERE, "libsnerf_b200_dbg.so")
 
 SNERF_MAX_LEVELS = 16
 SNERF_MAX_CHANNELS = 4
@@ -117,15 +118,6 @@ SIGNATURES = {
     "snerf_grid_cell_points": (c_int, [_P, _U, _U, _U, ctypes.c_double, _U, _P, c_uint64, _P, _S]),
     "snerf_grid_ema_workspace_bytes": (c_size_t, [_U]),
     "snerf_grid_ema_update": (c_int, [_P, _P, _U, _F, _F, _F, _P, _P, _P, c_size_t, _S]),
-    "snerf_tc_selftest": (c_int, [_P, _P, _P, _U, _U, c_int, c_int, _S]),
-    "snerf_debug_set_march_warp_max_rays": (None, [_U]),
-    "snerf_debug_set_field_stage_mask": (None, [_U]),
-    "snerf_debug_set_side_reduce": (None, [_U]),
-    "snerf_debug_set_dedupe_max_res": (None, [_U]),
-    "snerf_debug_set_scatter_adaptive_scan": (None, [_U]),
-    "snerf_debug_set_tail_prefetch": (None, [_U]),
-    "snerf_tc_probe": (c_int, [_P, c_int, _S]),
-    "snerf_debug_phase_buffer": (None, [_P, c_int]),
     "snerf_composite_l1_train": (c_int, [_P, _P, _P, _P, _U, _U, _F, _U, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                          _P, _P, _S]),
     "snerf_render_rays_workspace_bytes": (c_size_t, [POINTER(FieldDesc), _U, _U, c_int]),
@@ -151,24 +143,77 @@ SIGNATURES = {
     "snerf_trunc_exp_backward": (c_int, [_P, _P, _U, _P, _S]),
 }
 
+# measurement / test hooks: exported by libsnerf_b200_dbg.so only (include/snerf.h, #ifdef SNERF_DEBUG_HOOKS)
+DEBUG_SIGNATURES = {
+    "snerf_tc_selftest": (c_int, [_P, _P, _P, _U, _U, c_int, c_int, _S]),
+    "snerf_debug_set_march_warp_max_rays": (None, [_U]),
+    "snerf_debug_set_field_stage_mask": (None, [_U]),
+    "snerf_debug_set_side_reduce": (None, [_U]),
+    "snerf_debug_set_dedupe_max_res": (None, [_U]),
+    "snerf_debug_set_scatter_adaptive_scan": (None, [_U]),
+    "snerf_debug_set_tail_prefetch": (None, [_U]),
+    "snerf_tc_probe": (c_int, [_P, c_int, _S]),
+    "snerf_debug_phase_buffer": (None, [_P, c_int]),
+}
+
 _lib = None
+_dbg_lib = None
+_use_debug = False
+
+
+def _open(path, signatures):
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
+            f"g.build()'` or `make -C stable_nerf_b200/csrc`. There is no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in signatures.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
 
 
 def load():
-    """Load libsnerf_b200.so once; raise loudly if it is not there (no fallback exists)."""
+    """Load libsnerf_b200.so once; raise loudly if it is not there (no fallback exists).  Inside ``debug_library()`` the
+    debug build is returned instead."""
     global _lib
+    if _use_debug:
+        return load_debug()
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(
-                f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
-                f"g.build()'` or `make -C stable_nerf_b200/csrc`. There is no CPU or PyTorch fallback.")
-        lib = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
-            fn.restype = res
-            fn.argtypes = args
-        _lib = lib
+        _lib = _open(LIB_PATH, SIGNATURES)
     return _lib
+
+
+def load_debug():
+    """libsnerf_b200_dbg.so: the same sources compiled with -DSNERF_DEBUG_HOOKS (settable tunables, stage masks, phase
+    marks, the tcgen05 self-test).  Tests, scripts and bench.py's per-kernel timings use it; the product path never does."""
+    global _dbg_lib
+    if _dbg_lib is None:
+        _dbg_lib = _open(DBG_LIB_PATH, {**SIGNATURES, **DEBUG_SIGNATURES})
+    return _dbg_lib
+
+
+def use_debug_library(on=True):
+    """Process-wide switch for measurement scripts: every later ``load()`` returns the debug build."""
+    global _use_debug
+    _use_debug = bool(on)
+
+
+class debug_library:
+    """``with debug_library() as lib:`` -- every call made through this package inside the block goes to the debug build
+    (so that a tunable set through ``lib.snerf_debug_*`` is the one the kernels launched in the block see)."""
+
+    def __enter__(self):
+        global _use_debug
+        self._prev = _use_debug
+        _use_debug = True
+        return load_debug()
+
+    def __exit__(self, *exc):
+        global _use_debug
+        _use_debug = self._prev
+        return False
 
 
 def check(code, what):

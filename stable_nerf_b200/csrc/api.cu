@@ -12,9 +12,11 @@ int snerf_version(void) { return 100; }  // round 1
 
 uint64_t snerf_launch_count(void) { return g_launch_count; }
 
+#ifdef SNERF_DEBUG_HOOKS
 void snerf_debug_set_field_stage_mask(uint32_t mask) { field_tc_set_stage_mask(mask); }
 void snerf_debug_set_side_reduce(uint32_t on) { field_tc_set_side_reduce(on); }
 void snerf_debug_phase_buffer(void* dev_buffer, int net) { field_tc_set_phase_buffer(dev_buffer, net); }
+#endif
 
 const char* snerf_error_string(int code) {
   switch (code) {

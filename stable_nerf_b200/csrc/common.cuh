@@ -9,6 +9,14 @@
 #error "libsnerf_b200 is written for sm_100a (B200) only"
 #endif
 
+// Tunables that tests and measurement scripts flip at run time exist as variables only in the debug build
+// (libsnerf_b200_dbg.so, -DSNERF_DEBUG_HOOKS); the product library compiles them as constants and has no setter.
+#ifdef SNERF_DEBUG_HOOKS
+#define SNERF_TUNABLE static uint32_t
+#else
+#define SNERF_TUNABLE static constexpr uint32_t
+#endif
+
 namespace snerf {
 
 extern unsigned long long g_launch_count;  // defined in api.cu

@@ -467,11 +467,13 @@ using namespace snerf;
     default: return SNERF_E_CHANNELS;                \
   }
 
-static uint32_t g_tail_prefetch = 1;  // the one-launch tail fetches its rows a round ahead (round 2 A/B, cfg2 step: 0.6185 -> 0.6090 ms)
+SNERF_TUNABLE g_tail_prefetch = 1;  // the one-launch tail fetches its rows a round ahead (round 2 A/B, cfg2 step: 0.6185 -> 0.6090 ms)
 
 extern "C" {
 
+#ifdef SNERF_DEBUG_HOOKS
 void snerf_debug_set_tail_prefetch(uint32_t on) { g_tail_prefetch = on; }
+#endif
 
 int snerf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays,
                                        uint32_t M, uint32_t N, float T_thresh, uint32_t channel_dim, float* weights_sum,

@@ -73,9 +73,11 @@ int field_fp32_backward(const snerf_field_desc* f, const float* xyzs, const floa
 // field_tc.cu (tcgen05 bf16 path)
 size_t field_tc_workspace_bytes(const snerf_field_desc* f, uint32_t M, int backward);
 size_t field_tc_saved_bytes(const snerf_field_desc* f, uint32_t M);
+#ifdef SNERF_DEBUG_HOOKS
 void field_tc_set_phase_buffer(void* dev_buffer, int net);
 void field_tc_set_stage_mask(uint32_t mask);
 void field_tc_set_side_reduce(uint32_t on);
+#endif
 int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                      const float* w_sigma, const float* w_color, float* sigmas, float* rgbs, float* geo_feat,
                      bool sigma_only, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, cudaStream_t s);

@@ -85,9 +85,9 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_fwd(snerf_grid_desc g,
 //   * the two corners that differ in x are adjacent entries whenever index0 is even (always for a hashed level with
 //     even x: x ^ h and (x+1) ^ h differ in bit 0 only): one 16-byte red.global.add.v4.f32 instead of two v2's;
 //   * samples whose gradient is exactly zero (padding, terminated rays) issue nothing.
-static uint32_t g_dedupe_max_res = 300;  // tunable through snerf_debug_set_dedupe_max_res (measurement aid)
+SNERF_TUNABLE g_dedupe_max_res = 300;  // levels with resolution <= this merge equal cells inside a warp (measured optimum)
 
-static uint32_t g_scatter_adaptive = 1;   // scan depth follows the warp's longest run (round 2 A/B, cfg2 step: 0.6185 -> 0.6110 ms; both: 0.6064)
+SNERF_TUNABLE g_scatter_adaptive = 1;   // scan depth follows the warp's longest run (round 2 A/B, cfg2 step: 0.6185 -> 0.6110 ms; both: 0.6064)
 
 template <bool kNormalize, bool kAdaptive = false>
 __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g, const float* __restrict__ x,
@@ -197,8 +197,10 @@ using namespace snerf;
 
 extern "C" {
 
+#ifdef SNERF_DEBUG_HOOKS
 void snerf_debug_set_dedupe_max_res(uint32_t res) { g_dedupe_max_res = res; }
 void snerf_debug_set_scatter_adaptive_scan(uint32_t on) { g_scatter_adaptive = on; }
+#endif
 
 int snerf_hashgrid_forward(const snerf_grid_desc* g, const float* x01, const float* table, uint32_t M, float* enc,
                            snerf_stream_t stream) {

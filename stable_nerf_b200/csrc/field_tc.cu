@@ -21,6 +21,7 @@
 // Numerics: weights, layer inputs and back-propagated gradients are rounded to bf16 (RNE) at exactly the points
 // the oracle's emulate_bf16 mode rounds them; accumulation is fp32.
 #include <algorithm>
+#include <mutex>
 
 #include "encode.cuh"
 #include "field_common.cuh"
@@ -1036,23 +1037,32 @@ size_t field_tc_workspace_bytes(const snerf_field_desc* f, uint32_t M, int backw
   return carve_tc(f, M, backward, nullptr, nullptr);
 }
 
-static uint32_t g_stage_mask = 0xffffffffu;  // measurement aid: which kernels of a field call are launched
+SNERF_TUNABLE g_stage_mask = 0xffffffffu;  // (debug build) which kernels of a field call are launched
+#ifdef SNERF_DEBUG_HOOKS
 void field_tc_set_stage_mask(uint32_t mask) { g_stage_mask = mask; }
+#endif
 enum : uint32_t { kStFwdPack = 1, kStFwdEncode = 2, kStFwdSigma = 4, kStFwdColor = 8, kStBwdPack = 16, kStBwdColor = 32,
                   kStBwdSigma = 64, kStBwdScatter = 128 };
+#ifdef SNERF_DEBUG_HOOKS
 static long long* g_phase_dbg = nullptr;
 static int g_phase_net = 0;
 void field_tc_set_phase_buffer(void* p, int net) { g_phase_dbg = (long long*)p; g_phase_net = net; }
+#else
+static constexpr long long* g_phase_dbg = nullptr;
+static constexpr int g_phase_net = 0;
+#endif
 
-static int g_sm_count = 0;
-static int sm_count() {
-  if (!g_sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
+static int sm_count() {  // of the current device (a cache of an immutable device property)
+  static int count_of[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!count_of[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    count_of[dev] = n > 0 ? n : 148;
   }
-  return g_sm_count;
+  return count_of[dev];
 }
 
 template <typename K>
@@ -1101,27 +1111,42 @@ static size_t bwd_smem(const PackedNet& n, int net) {
 // nothing but the end of the call depends on them: they run on a side stream forked after that kernel (events, so the
 // fork/join is captured with the step's graph like any other dependency) under the next tensor-core kernel / the table
 // scatter-add, and the caller's stream joins them before the call returns.
+// One side stream (and its events) per (device, caller stream): two callers on different streams -- or on different
+// devices -- never share events, so concurrent calls do not interfere.  The table only caches CUDA objects (created on
+// first use, never destroyed); it holds no state that changes what a call computes.  NULL: stay on the caller's stream.
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork[2] = {nullptr, nullptr}, join = nullptr, start = nullptr, zeroed = nullptr;
+  int dev = -1;
+  cudaStream_t owner = nullptr;
   bool ok = false;
 };
-static SideStream g_side[16];
-static SideStream* side_stream() {
+constexpr int kMaxSideStreams = 64;
+static SideStream g_side[kMaxSideStreams];
+static std::mutex g_side_mutex;
+static SideStream* side_stream(cudaStream_t caller) {
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-  SideStream& ss = g_side[dev];
-  if (!ss.ok) {
-    if (ss.stream) return nullptr;  // creation failed before: stay on the caller's stream
-    if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    for (cudaEvent_t* e : {&ss.fork[0], &ss.fork[1], &ss.join, &ss.start, &ss.zeroed})
-      if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    ss.ok = true;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(g_side_mutex);
+  SideStream* free_slot = nullptr;
+  for (SideStream& ss : g_side) {
+    if (ss.ok && ss.dev == dev && ss.owner == caller) return &ss;
+    if (!ss.ok && !ss.stream && !free_slot) free_slot = &ss;
   }
+  if (!free_slot) return nullptr;
+  SideStream& ss = *free_slot;
+  if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  for (cudaEvent_t* e : {&ss.fork[0], &ss.fork[1], &ss.join, &ss.start, &ss.zeroed})
+    if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  ss.dev = dev;
+  ss.owner = caller;
+  ss.ok = true;
   return &ss;
 }
-static uint32_t g_side_reduce = 1;  // measurement aid: 0 = the sums stay on the caller's stream
+SNERF_TUNABLE g_side_reduce = 1;  // (debug build) 0 = the sums stay on the caller's stream
+#ifdef SNERF_DEBUG_HOOKS
 void field_tc_set_side_reduce(uint32_t on) { g_side_reduce = on; }
+#endif
 
 // reduce_part == false: the net's kernel on s; true: the sum of its partials (on the side stream when there is one)
 template <int NET>
@@ -1170,7 +1195,7 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
   // Training forward (hand-off given; the step is replayed as a graph, so the extra stream calls cost nothing per step):
   // the weight packing depends on the parameters only and runs on the side stream under the gather.  The inference
   // loop's calls stay on one stream: they are launch-bound and three more API calls per call would show.
-  SideStream* side = (saved && g_side_reduce) ? side_stream() : nullptr;
+  SideStream* side = (saved && g_side_reduce) ? side_stream(s) : nullptr;
   bool pack_forked = false;
   if (st & kStFwdPack) {
     cudaStream_t sp = s;
@@ -1266,7 +1291,7 @@ int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float*
   p.dw_part = w.dw_part_color;
   p.n_params = sc.n_params;
   p.dbg = g_phase_net == 1 ? g_phase_dbg : nullptr;
-  SideStream* side = g_side_reduce ? side_stream() : nullptr;
+  SideStream* side = g_side_reduce ? side_stream(s) : nullptr;
   bool forked = false, zero_pending = false;
   const size_t table_bytes = (size_t)f->grid.n_entries * f->grid.n_features * sizeof(float);
   const bool zero_table = (flags & SNERF_BWD_ZERO_TABLE_GRAD) != 0, zero_w = (flags & SNERF_BWD_ZERO_W_GRADS) != 0;

@@ -694,11 +694,13 @@ using namespace snerf;
 
 // ------------------------------------------------------------------------------------------------ C ABI
 
-static uint32_t g_march_warp_max_rays = 49152;  // above: thread per ray (enough rays to fill the machine)
+SNERF_TUNABLE g_march_warp_max_rays = 49152;  // above: thread per ray (enough rays to fill the machine)
 
 extern "C" {
 
+#ifdef SNERF_DEBUG_HOOKS
 void snerf_debug_set_march_warp_max_rays(uint32_t n) { g_march_warp_max_rays = n; }
+#endif
 
 int snerf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
                              float* nears, float* fars, snerf_stream_t stream) {

@@ -400,9 +400,10 @@ class TrainStep:
 
     def profile_field_kernels(self, iters=10):
         """Device time (us) of each kernel of the bf16 field calls on the last step's samples, one kernel per launch
-        through the library's stage mask (CUDA events on the launch stream).  Leaves the gradients meaningless."""
+        through the stage mask of the debug build -- libsnerf_b200_dbg.so, the same sources compiled with
+        -DSNERF_DEBUG_HOOKS -- (CUDA events on the launch stream).  Leaves the gradients meaningless."""
         m, b = self.model, self._bufs
-        lib = _lib.load()
+        lib = _lib.load_debug()  # the stage mask is a hook of the debug build (same sources, same kernels)
         P, S, chk = _lib.ptr, _lib.stream(), _lib.check
         prec = _precision_code(m.precision)
         if prec != _lib.PRECISION_BF16 or b is None:

@@ -8,14 +8,19 @@ import re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_symbols():
+def header_symbols(debug=False):
+    """symbols include/snerf.h declares: the product surface, or (debug=True) the block under #ifdef SNERF_DEBUG_HOOKS"""
     text = open(os.path.join(ROOT, "include", "snerf.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    m = re.search(r"#ifdef SNERF_DEBUG_HOOKS(.*?)#endif", text, flags=re.S)
+    assert m, "include/snerf.h keeps the measurement hooks under #ifdef SNERF_DEBUG_HOOKS"
+    text = m.group(1) if debug else text[:m.start()] + text[m.end():]
     return sorted(set(re.findall(r"\b(snerf_[a-zA-Z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol(built_lib):
     import ctypes
+    import subprocess
     from stable_nerf_b200 import _lib
     syms = header_symbols()
     assert len(syms) >= 30
@@ -25,13 +30,23 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert sorted(_lib.SIGNATURES) == syms, "ctypes signature table and include/snerf.h disagree"
     assert built_lib.snerf_version() >= 100
     assert b"channel_dim" in built_lib.snerf_error_string(-2)
+    # the product library carries no measurement hooks, no probe code and no settable tunables: nothing but the surface
+    exported = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted({l.split()[-1] for l in exported.splitlines() if " T " in l and l.split()[-1].startswith("snerf_")})
+    assert exported == syms, set(exported) ^ set(syms)
+    # the debug build is the same surface plus exactly the hooks the header declares under SNERF_DEBUG_HOOKS
+    dbg_syms = header_symbols(debug=True)
+    assert sorted(_lib.DEBUG_SIGNATURES) == dbg_syms and all(s.startswith(("snerf_debug_", "snerf_tc_")) for s in dbg_syms)
+    dbg = ctypes.CDLL(_lib.DBG_LIB_PATH)
+    for s in syms + dbg_syms:
+        assert hasattr(dbg, s), f"libsnerf_b200_dbg.so does not export {s}"
 
 
 def test_ctypes_arity_matches_header():
     from stable_nerf_b200 import _lib
     text = open(os.path.join(ROOT, "include", "snerf.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    for name, (_, args) in _lib.SIGNATURES.items():
+    for name, (_, args) in {**_lib.SIGNATURES, **_lib.DEBUG_SIGNATURES}.items():
         m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", text, flags=re.S)
         assert m, name
         params = m.group(1).strip()

@@ -299,7 +299,10 @@ def test_backward_ex_zero_table_grad_flag(setup, built_lib, cuda, precision, sid
     colour/sigma kernels) -- a table gradient full of garbage on entry gives what a caller-zeroed one gives; the weight
     gradients are accumulated into unless SNERF_BWD_ZERO_W_GRADS is set too.  Also inside a CUDA graph (the fork and join
     are captured), replayed twice."""
+    from stable_nerf_b200 import _lib as libmod
     from stable_nerf_b200._lib import BWD_ZERO_TABLE_GRAD, BWD_ZERO_W_GRADS, check, ptr, stream
+    if side_reduce == 0:  # the in-line variant exists in the debug build only (the product library always forks)
+        built_lib = libmod.load_debug()
     assert (BWD_ZERO_TABLE_GRAD, BWD_ZERO_W_GRADS) == (1, 2)
     zero_w = bool(flags & BWD_ZERO_W_GRADS)
     lib = built_lib
@@ -328,7 +331,8 @@ def test_backward_ex_zero_table_grad_flag(setup, built_lib, cuda, precision, sid
                                      ptr(t["gr"]), precision, ptr(gt2), ptr(gws2), ptr(gwc2), None, 0, ptr(wsb), nb, None,
                                      4, stream())
     assert rc != 0
-    lib.snerf_debug_set_side_reduce(side_reduce)
+    if side_reduce == 0:
+        lib.snerf_debug_set_side_reduce(0)
     try:
         bwd()
         torch.cuda.synchronize()
@@ -356,16 +360,19 @@ def test_backward_ex_zero_table_grad_flag(setup, built_lib, cuda, precision, sid
         k = 1 if zero_w else 2
         assert rel_err(gws2.cpu().numpy() / k, gws) <= tol and rel_err(gwc2.cpu().numpy() / k, gwc) <= tol
     finally:
-        lib.snerf_debug_set_side_reduce(1)
+        if side_reduce == 0:
+            lib.snerf_debug_set_side_reduce(1)
 
 
 def test_scatter_adaptive_scan_depth_gives_the_same_sums(setup, built_lib, cuda):
     """snerf_debug_set_scatter_adaptive_scan (on by default since its round-2 A/B): the segmented scan that merges equal
     cells stops at the depth the warp's longest run needs.  Samples along rays (long runs on coarse levels, short ones
     on fine levels, isolated and zero-gradient samples in between) must give the sums of the five-step scan; the two
-    launches differ in the order of their fp32 reductions only."""
+    launches differ in the order of their fp32 reductions only.  (Both instantiations through the debug build; the
+    product library compiles the adaptive one in.)"""
+    from stable_nerf_b200 import _lib as libmod
     from stable_nerf_b200._lib import check, ptr, stream
-    lib = built_lib
+    lib = libmod.load_debug()
     f = setup[3][0]
     rng = np.random.default_rng(21)
     n_rays, per = 96, 40

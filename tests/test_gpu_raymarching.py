@@ -89,14 +89,18 @@ def test_near_far_and_march_train_vs_oracle(sc, built_lib, cuda):
     again = cuda_march_with_noises(sc, cuda, inp, nears, fars, keep_positions=False)  # second-march write pass
     for a, b, name in zip((counter, xyzs, dirs, deltas, rays), again, ("counter", "xyzs", "dirs", "deltas", "rays")):
         assert_bits_equal(a, b, name + " (expand vs re-march write pass)")
-    built_lib.snerf_debug_set_march_warp_max_rays(0)  # thread-per-ray grain (what large batches use)
-    try:
-        for keep in (True, False):
-            again = cuda_march_with_noises(sc, cuda, inp, nears, fars, keep_positions=keep)
-            for a, b, name in zip((counter, xyzs, dirs, deltas, rays), again, ("counter", "xyzs", "dirs", "deltas", "rays")):
-                assert_bits_equal(a, b, name + f" (thread-per-ray grain, keep_positions={keep})")
-    finally:
-        built_lib.snerf_debug_set_march_warp_max_rays(49152)
+    # thread-per-ray grain (what large batches use): the threshold is a compile-time constant of the product library, so the
+    # other grain runs through the debug build (same sources, settable tunables) and is compared with the product's bits
+    from stable_nerf_b200 import _lib
+    with _lib.debug_library() as dbg:
+        dbg.snerf_debug_set_march_warp_max_rays(0)
+        try:
+            for keep in (True, False):
+                again = cuda_march_with_noises(sc, cuda, inp, nears, fars, keep_positions=keep)
+                for a, b, name in zip((counter, xyzs, dirs, deltas, rays), again, ("counter", "xyzs", "dirs", "deltas", "rays")):
+                    assert_bits_equal(a, b, name + f" (thread-per-ray grain, keep_positions={keep})")
+        finally:
+            dbg.snerf_debug_set_march_warp_max_rays(49152)
     ox, od, odl, orays, ocounter = orc.march_rays_train(inp["rays_o"], inp["rays_d"], sc.bound, inp["bitfield"],
                                                         sc.cascades, sc.H, on, of, inp["noises"], sc.dt_gamma,
                                                         sc.max_steps)
@@ -377,8 +381,14 @@ def test_cfg5_size_thread_grain_and_fused_near_far(built_lib, cuda):
     nb = lib.snerf_march_rays_train_workspace_bytes_ex(N, max_steps)
     geom = (1.0, 0.0, max_steps, N, 1, 128)
     out = {}
-    for name, thr in (("warp", 1 << 30), ("thread", 0)):
-        lib.snerf_debug_set_march_warp_max_rays(thr)
+    from stable_nerf_b200 import _lib as libmod
+    # "thread": the product library as it stands (2^18 rays are above its compile-time crossover of 49 152);
+    # "warp": the debug build of the same sources with the crossover raised
+    for name, thr in (("warp", 1 << 30), ("thread", None)):
+        ctx = libmod.debug_library() if thr is not None else None
+        lib = ctx.__enter__() if ctx is not None else built_lib
+        if thr is not None:
+            lib.snerf_debug_set_march_warp_max_rays(thr)
         try:
             ws = torch.empty(nb, dtype=torch.uint8, device=cuda)
             counter = torch.zeros(2, dtype=torch.int32, device=cuda)
@@ -394,7 +404,9 @@ def test_cfg5_size_thread_grain_and_fused_near_far(built_lib, cuda):
             torch.cuda.synchronize()
             out[name] = (total, rays.cpu().numpy(), xyzs.cpu().numpy(), deltas.cpu().numpy(), n2.cpu().numpy(), f2.cpu().numpy())
         finally:
-            lib.snerf_debug_set_march_warp_max_rays(49152)
+            if ctx is not None:
+                lib.snerf_debug_set_march_warp_max_rays(49152)
+                ctx.__exit__(None, None, None)
     tw, tt = out["warp"], out["thread"]
     assert tw[0] == tt[0] and tw[0] > 10_000_000
     for a, b, what in zip(tw[1:], tt[1:], ("rays", "xyzs", "deltas", "nears", "fars")):

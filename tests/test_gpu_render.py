@@ -242,6 +242,7 @@ def test_one_launch_tail_equals_the_three_kernels(C, bg, M_cap, built_lib, cuda)
     # the other instantiation of the same kernel (rows NOT fetched a round ahead; the prefetching one is the default
     # since its round-2 A/B): only the loads move, the results are the same bits
     B2 = {k: torch.full_like(v, float("nan")) for k, v in B.items()}
+    lib = _lib.load_debug()  # (the product library compiles the prefetching instantiation in; the debug build has both)
     lib.snerf_debug_set_tail_prefetch(0)
     try:
         check(lib.snerf_composite_l1_train(ptr(sig), ptr(rgb), ptr(deltas), ptr(rays), M, N, 1e-4, C, ptr(tgt), ptr(bgt), bgs,

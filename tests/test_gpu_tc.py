@@ -14,7 +14,9 @@ CASES = [(N, K, a, b) for (N, K), (a, b) in itertools.product(
 
 @pytest.mark.parametrize("N,K,a_mn,b_mn", CASES)
 def test_single_tile_gemm(N, K, a_mn, b_mn, built_lib, cuda):
+    from stable_nerf_b200 import _lib
     from stable_nerf_b200._lib import check, ptr, stream
+    built_lib = _lib.load_debug()  # the self-test of the tcgen05 building blocks lives in the debug build only
     g = torch.Generator(device="cpu").manual_seed(N * 1000 + K * 10 + a_mn * 2 + b_mn)
     A = torch.randn(128, K, generator=g).to(cuda)
     B = torch.randn(N, K, generator=g).to(cuda)
