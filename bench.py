@@ -519,7 +519,7 @@ def cfg5_profile(args, dev, world, rank, bitfield, barrier, max_over_ranks, n_to
     # ---- sharded
     model = make_model()
     ts = TrainStep(model, hi - lo, max_steps=MAX_STEPS, use_graph=not args.no_graph, world_size=world, loss_scale=1.0 / world,
-                   exchange=args.exchange, pipeline=not args.no_pipeline)
+                   exchange=args.exchange, pipeline=args.pipeline)
     shards = [tuple(torch.from_numpy(np.ascontiguousarray(a[lo:hi])).to(dev) for a in b[1:]) for b in full]
     packed = [torch.cat([t.reshape(-1) for t in s]) for s in shards]
     ts.warmup(*shards[0], iters=2, batches=shards)
@@ -594,10 +594,11 @@ def run_gpu_arm(args):
     broadcast_occupancy(model)
     model.train()
 
-    # several ranks: the gradient exchange of step k runs beside step k+1's ray march (TrainStep pipeline=True), still one
-    # exchange per step; finish() applies the last one inside the timed region
+    # (--pipeline: the gradient exchange of step k beside step k+1's ray march, TrainStep(pipeline=True).  Measured on 2 and 8
+    # B200 it does not pay for the exchange -- 0.731 vs 0.718 and 0.812 vs 0.808 ms/step -- so it is off by default; the
+    # optimiser update does profit from it, see with_optimizer)
     ts = TrainStep(model, RAYS_PER_GPU, max_steps=MAX_STEPS, use_graph=not args.no_graph, world_size=world,
-                   loss_scale=1.0 / world, exchange=args.exchange, pipeline=world > 1 and not args.no_pipeline)
+                   loss_scale=1.0 / world, exchange=args.exchange, pipeline=world > 1 and args.pipeline)
     d_batches = [tuple(torch.from_numpy(a).to(dev) for a in b[1:]) for b in batches]
     d_packed = [torch.cat([t.reshape(-1) for t in b]) for b in d_batches]   # [rays_o | rays_d | target], resident in HBM
     h_packed = []                                                           # the same in pinned host memory (one H2D copy)
@@ -904,7 +905,7 @@ def main():
     ap.add_argument("--no-large", action="store_true")
     ap.add_argument("--no-ref-kernels", action="store_true")
     ap.add_argument("--no-cfg5", action="store_true")
-    ap.add_argument("--no-pipeline", action="store_true")
+    ap.add_argument("--pipeline", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nvls", "p2p", "nccl"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -8,7 +8,10 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stable_nerf_b200 import _lib  # noqa: E402
 from stable_nerf_b200.p2p import P2PExchange  # noqa: E402
+
+_lib.use_debug_library()  # the exchange kernels of the debug build leave globaltimer stamps in their flag block
 
 
 def main():
@@ -51,9 +54,16 @@ def main():
             fill = lambda: ex.tensor.copy_(src)  # fresh "gradients" written by this GPU, as the scatter-add leaves them
             us_fresh = timed(ex.all_reduce, fill=fill)
             us_b2b = timed(ex.all_reduce)        # the arena as the previous exchange left it (written through the switch)
+            class _Mem:
+                __cuda_array_interface__ = {"shape": (64,), "typestr": "<i4", "data": (int(ex._flags.value), False),
+                                            "version": 3, "strides": None}
+            torch.cuda.synchronize()
+            flags = torch.as_tensor(_Mem(), device=dev).cpu().tolist()
+            st = [int(flags[40 + k]) & 0xffffffff for k in range(4)]
+            d = [((st[k + 1] - st[k]) & 0xffffffff) / 1e3 for k in range(3)]
             if rank == 0:
-                print(f"{algo:5s} ctas {n_ctas:4d}: after a local rewrite of the arena {us_fresh:8.1f} us   back to back {us_b2b:8.1f} us",
-                      flush=True)
+                print(f"{algo:5s} ctas {n_ctas:4d}: after a local rewrite of the arena {us_fresh:8.1f} us   back to back {us_b2b:8.1f} us"
+                      f"   last call on rank 0: arrive round {d[0]:6.1f} us, data {d[1]:6.1f} us, done round {d[2]:6.1f} us", flush=True)
             ex.tensor = None
             del src
             ex.close()

@@ -105,6 +105,16 @@ __device__ __forceinline__ void exchange(const P2PParams& p, uint32_t world, Bod
   if (tid == 0) ok_s = ld_acquire_sys(mine + kError) == 0u ? 1u : 0u;  // a failed exchange stays failed
   __syncthreads();
   const bool healthy = ok_s != 0u;
+#ifdef SNERF_DEBUG_HOOKS
+  // debug build: globaltimer (ns, low 32 bits) of CTA 0 at entry / after the arrive round / after its share of the data,
+  // and of the last CTA after the done round, in spare words 40..43 of the flag block
+  auto stamp = [&](uint32_t k) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    mine[40 + k] = (uint32_t)ns;
+  };
+  if (blockIdx.x == 0 && tid == 0) stamp(0);
+#endif
 
   // ---- arrive: this rank's gradients are complete (stream order); wait for everybody's
   if (blockIdx.x == 0 && tid < world) {
@@ -115,6 +125,9 @@ __device__ __forceinline__ void exchange(const P2PParams& p, uint32_t world, Bod
   if (healthy && tid < world && !wait_flag(mine + kArrive + tid, epoch, mine, p, rank)) ok_s = 0u;
   __syncthreads();
   const bool ok = ok_s != 0u;
+#ifdef SNERF_DEBUG_HOOKS
+  if (blockIdx.x == 0 && tid == 0) stamp(1);
+#endif
 
   // ---- this rank's slice: reduce over all ranks, store the sum everywhere (nothing moves after a failed wait)
   if (ok) {
@@ -126,6 +139,9 @@ __device__ __forceinline__ void exchange(const P2PParams& p, uint32_t world, Bod
   // ---- done: the last CTA of this rank tells everybody and waits for everybody
   __threadfence_system();
   __syncthreads();
+#ifdef SNERF_DEBUG_HOOKS
+  if (blockIdx.x == 0 && tid == 0) stamp(2);
+#endif
   if (tid == 0) last = atomicAdd(mine + kCounter, 1u) == gridDim.x - 1 ? 1u : 0u;
   __syncthreads();
   if (last) {
@@ -136,6 +152,11 @@ __device__ __forceinline__ void exchange(const P2PParams& p, uint32_t world, Bod
     }
     __syncthreads();
     if (tid == 0) {
+#ifdef SNERF_DEBUG_HOOKS
+      stamp(3);
+      stamp(4);
+      mine[44] = (uint32_t)0;
+#endif
       mine[kCounter] = 0u;
       st_release_sys(mine + kEpoch, epoch);
     }

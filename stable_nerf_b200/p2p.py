@@ -67,6 +67,10 @@ class P2PExchange:
                 self.nvls_error = self._setup_nvls()
                 if self.nvls_error is None:
                     self.algo = "nvls"
+                    if self.n_ctas == 0:
+                        # 32 CTAs saturate the switch's reduction path; more only add contention (8 B200, 49.2 MB:
+                        # 150 us at 32 CTAs, 157 / 173 / 179 us at 64 / 128 / 256 -- scripts/exchange_probe.py)
+                        self.n_ctas = 32
                 elif algo == "nvls":
                     self._release()
                     raise RuntimeError(f"NVLS exchange unavailable on rank {self.rank}: {self.nvls_error}")
