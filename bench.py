@@ -664,8 +664,9 @@ def run_gpu_arm(args):
         # copy stream while the previous step computes) and brings ITS loss back to the host (4 B, into a pinned slot); the
         # host reads the loss of step k-1 while step k runs, so the device never waits for the host.  Wall clock between
         # device-complete points, all copies and the last loss inside.
-        for k in range(args.warmup):
-            ts.step_from_packed(h_packed[k % N_BATCHES], read_loss=True)
+        for k in range(args.warmup):  # (also creates the copy stream, the staging buffer and the pinned loss slots)
+            ts.step_from_packed(h_packed[k % N_BATCHES], read_loss="lagged", next_packed=h_packed[(k + 1) % N_BATCHES])
+        ts.drain()
         barrier()
         with clocks.mark():
             t0 = time.perf_counter()

@@ -9,7 +9,11 @@ What the reference stores.  ``train.py:307`` pickles the whole unwrapped module 
                                                         to 16 on the last), followed by the hash table, level-major,
                                                         n_features_per_level floats per entry
     encoder_dir.params   fp32 [0]                       tcnn.Encoding, SphericalHarmonics (:29-32): no parameters
-    color_net.params     fp32 [n_mlp_color]             tcnn.Network (:34-37): input padded 31 -> 32
+    color_net.params     fp32 [n_mlp_color]             tcnn.Network (:34-37): input padded 31 -> 32.  tiny-cuda-nn feeds 1.0
+                                                        into the pad (Identity-encoding padding), so column 31 of the first
+                                                        matrix is a learned BIAS: it is copied as it is and this model
+                                                        evaluates it as the bias by default (NeRFNetwork(color_in_pad=1.0),
+                                                        DESIGN.md section 2; recalled from upstream, not verifiable here)
     aabb_train, aabb_infer, density_grid, density_bitfield, step_counter      buffers of nerf/renderer.py:32-45
 
 ``NeRFNetwork`` here registers the same names with the same shapes and the same flat order (field.py), so the
@@ -35,7 +39,26 @@ import torch
 
 _PREFIXES = ("module.", "_orig_mod.", "nerf.")
 _PLAIN_STATE = ("mean_density", "iter_density", "mean_count", "local_step")
-_SAFE_ROOTS = ("torch", "numpy", "collections", "builtins", "_codecs", "copyreg")
+# What a pickled module / state_dict legitimately references: tensor rebuilders, storages, dtypes, the containers.  An
+# explicit (module, name) allowlist -- NOT whole packages: `builtins`, `torch` or `numpy` as prefixes would let a crafted
+# file resolve builtins.eval / getattr / __import__ or torch.hub and REDUCE them.  Everything else becomes an inert stub.
+_SAFE_GLOBALS = {
+    ("collections", "OrderedDict"), ("collections", "defaultdict"),
+    ("builtins", "set"), ("builtins", "frozenset"), ("builtins", "slice"), ("builtins", "list"), ("builtins", "dict"),
+    ("builtins", "tuple"), ("builtins", "int"), ("builtins", "float"), ("builtins", "bool"), ("builtins", "complex"),
+    ("builtins", "str"), ("builtins", "bytes"), ("builtins", "bytearray"),
+    ("_codecs", "encode"), ("copyreg", "_reconstructor"), ("builtins", "object"),
+    ("torch._utils", "_rebuild_tensor"), ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_parameter"),
+    ("torch._utils", "_rebuild_parameter_with_state"), ("torch._utils", "_rebuild_qtensor"),
+    ("torch._tensor", "_rebuild_from_type_v2"), ("torch", "Size"), ("torch", "device"), ("torch", "dtype"),
+    ("torch.serialization", "_get_layout"), ("torch.nn.parameter", "Parameter"), ("torch", "Tensor"),
+    ("torch.storage", "_load_from_bytes"), ("torch.storage", "UntypedStorage"), ("torch.storage", "TypedStorage"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"), ("numpy", "ndarray"), ("numpy", "dtype"),
+}
+_SAFE_TORCH_NAMES = {n for n in dir(torch) if n.endswith("Storage")} | {
+    "float32", "float16", "bfloat16", "float64", "int32", "int64", "int16", "int8", "uint8", "bool", "float", "half",
+    "double", "long", "int", "short"}
 
 
 class CheckpointError(RuntimeError):
@@ -63,7 +86,7 @@ def _stub_class(module, name):
 
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
-        if module.split(".")[0] in _SAFE_ROOTS:
+        if (module, name) in _SAFE_GLOBALS or (module == "torch" and name in _SAFE_TORCH_NAMES):
             return super().find_class(module, name)
         return _stub_class(module, name)
 

@@ -190,3 +190,34 @@ def test_sd_image_embeds_vs_reference_expression(B, E, C, built_lib, cuda):
     assert torch.equal(pred.grad, pred2.grad)
     # what SDNetwork.forward does next (stable_diffusion/network.py:194-197): each block flattens to (C+3)*E*E
     assert out.view(-1, (C + 3) * E * E).shape == (2 * B, (C + 3) * E * E)
+
+
+def test_crafted_pickle_cannot_reach_code(tmp_path):
+    """The loader resolves an explicit allowlist of (module, name) pairs only: a file that REDUCEs builtins.eval /
+    os.system / torch.hub.load gets inert stubs back (nothing runs) and is refused for holding no tensors."""
+    import pickle
+
+    from stable_nerf_b200 import NeRFNetwork
+    from stable_nerf_b200.checkpoint import CheckpointError, _Unpickler, load_reference_checkpoint
+    import io
+
+    class Evil:
+        def __init__(self, mod, name, *args):
+            self.fn, self.args = (mod, name), args
+
+        def __reduce__(self):
+            import importlib
+            return getattr(importlib.import_module(self.fn[0]), self.fn[1]), self.args
+    marker = tmp_path / "pwned"
+    for mod, name, args in (("builtins", "eval", (f"open({str(marker)!r}, 'w').write('x')",)),
+                            ("os", "system", (f"touch {marker}",)),
+                            ("builtins", "getattr", (object, "__subclasses__"))):
+        blob = pickle.dumps(Evil(mod, name, *args))
+        obj = _Unpickler(io.BytesIO(blob)).load()
+        assert not marker.exists(), f"{mod}.{name} ran"
+        assert type(obj).__mro__[1].__name__ == "_Stub"
+    path = tmp_path / "evil.pth"
+    path.write_bytes(pickle.dumps(Evil("builtins", "eval", (f"open({str(marker)!r}, 'w').write('x')",))))
+    with pytest.raises((CheckpointError, Exception)):
+        load_reference_checkpoint(NeRFNetwork(), str(path))
+    assert not marker.exists()
