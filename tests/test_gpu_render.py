@@ -557,3 +557,53 @@ def test_first_epoch_fused_body_matches_render_plus_autograd(precision, built_li
     for a, b in zip(res[True], res[False]):
         assert a[1] == b[1] and abs(a[0] - b[0]) <= 1e-6 * abs(b[0])
         assert rel_err(a[2], b[2]) <= tol and rel_err(a[3], b[3]) <= tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cfg2_full_size_step_against_the_oracle(precision, built_lib, cuda):
+    """The whole cfg2 step at BASELINE's size -- 4096 rays of an 800x800 view, max_steps 1024, ~345 k samples -- on the
+    CUDA path (TrainStep's fused body: near/far, march, field, composite, L1, backward of all of it) against the CPU
+    oracle's restatement of the same chain (oracle/snerf_oracle.c, all host cores, ~15 s): sample total, loss, image and
+    the gradients of both MLPs and of the hash table.  fp32 path: 1e-4 relative (max-norm); bf16 tensor-core path against
+    the oracle with bf16 rounding emulation: loss 2e-3, gradients 2e-2 (the stated bf16 tolerance at this depth)."""
+    from oracle import oracle as orc
+    from stable_nerf_b200 import synthetic as syn
+    from stable_nerf_b200.trainer import TrainStep
+    N, C, max_steps = 4096, 3, 1024
+    grid = syn.occupancy_grid(lego_like=True, seed=0)
+    bitfield = syn.pack_bitfield(grid)
+    ro, rd = syn.train_batch(N, seed=0)
+    target = np.random.default_rng(1).random((N, C), dtype=np.float32)
+    model = _fresh_model(C, precision, cuda)
+    ts = TrainStep(model, N, max_steps=max_steps, use_graph=False)
+    t = [torch.from_numpy(a).to(cuda) for a in (ro, rd, target)]
+    loss = float(ts.step(*t))  # mean_count == 0: rows sized from the measured total, like the reference's first epoch
+    torch.cuda.synchronize()
+    total = int(model.step_counter[0, 0])
+    image = ts.outputs["image"].cpu().numpy()
+    nm = model.sigma_net.n_mlp
+    g_sp = model.sigma_net.params.grad.cpu().numpy()
+    g_cp = model.color_net.params.grad.cpu().numpy()
+
+    # ---- the same step on the oracle (nerf/renderer.py:75-114 + utils/loss_utils.py:9-10 + backward)
+    orc.set_threads(0)
+    emulate = precision == "bf16"
+    fd = orc.copy_desc(model.fdesc, orc.FieldDesc)
+    sp = model.sigma_net.params.detach().cpu().numpy()
+    cp = model.color_net.params.detach().cpu().numpy()
+    aabb = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    nears, fars = orc.near_far_from_aabb(ro, rd, aabb, 0.2)
+    xyzs, dirs, deltas, rays, counter = orc.march_rays_train(ro, rd, 1.0, bitfield, 1, 128, nears, fars, max_steps=max_steps)
+    assert int(counter[0]) == total and total > 300_000
+    sig, rgb = orc.field_forward(fd, xyzs, dirs, sp[nm:], sp[:nm], cp, emulate_bf16=emulate)
+    ws, depth, img = orc.composite_rays_train_forward(sig, rgb, deltas, rays, 1e-4)
+    pred = img + (1 - ws)[:, None]
+    loss_o = float(np.abs(pred - target).mean())
+    g_img = (np.sign(pred - target) / pred.size).astype(np.float32)
+    gs, gr = orc.composite_rays_train_backward(-g_img.sum(-1), g_img, sig, rgb, deltas, rays, ws, img, 1e-4)
+    gt_o, gws_o, gwc_o = orc.field_backward(fd, xyzs, dirs, sp[nm:], sp[:nm], cp, gs, gr, emulate_bf16=emulate)
+
+    tol_loss, tol_img, tol_g = (1e-5, 1e-4, 1e-4) if precision == "fp32" else (2e-3, 2e-2, 2e-2)
+    assert abs(loss - loss_o) <= tol_loss * abs(loss_o), (loss, loss_o)
+    assert rel_err(image, pred) <= tol_img
+    assert rel_err(g_sp[:nm], gws_o) <= tol_g and rel_err(g_cp, gwc_o) <= tol_g and rel_err(g_sp[nm:], gt_o) <= tol_g
