@@ -612,8 +612,22 @@ __global__ void __launch_bounds__(kMarchThreads) k_march_rays(MarchParams p, uin
                                                               const uint8_t* __restrict__ grid,
                                                               const float* __restrict__ fars, float* __restrict__ xyzs,
                                                               float* __restrict__ dirs, float* __restrict__ deltas,
-                                                              const float* __restrict__ noises, uint32_t n_rows) {
+                                                              const float* __restrict__ noises, uint32_t n_rows,
+                                                              const int32_t* __restrict__ n_alive_dev, uint32_t n_total,
+                                                              uint32_t min_n_step) {
   const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_alive_dev) {
+    // Sizes from the device (the inference loop launches the NEXT iteration's march before the host has read the alive
+    // count back, csrc/render_loop.cu): n_alive as the compaction left it, n_step and the padded row count as the host
+    // will derive them from it (nerf/renderer.py:146; rows rounded up to 128).  The grid was sized for an upper bound.
+    const int32_t c = *n_alive_dev;
+    n_alive = c > 0 ? (uint32_t)c : 0u;
+    if (n_alive == 0u) return;
+    n_step = n_total / n_alive < 8u ? n_total / n_alive : 8u;
+    if (n_step < min_n_step) n_step = min_n_step;
+    if (n_step < 1u) n_step = 1u;
+    n_rows = (n_alive * n_step + 127u) / 128u * 128u;
+  }
   // n_rows != 0: the caller's buffers are uninitialised; zero the padding rows [n_alive*n_step, n_rows)
   for (uint32_t i = n_alive * n_step + n; i < n_rows; i += gridDim.x * blockDim.x) zero_rows(xyzs, dirs, deltas, i);
   if (n >= n_alive) return;
@@ -851,9 +865,26 @@ int snerf_march_rays_ex(uint32_t n_alive, uint32_t n_step, const int32_t* rays_a
   MarchParams p;
   if (int e = make_march_params(&p, bound, dt_gamma, max_steps, C, H)) return e;
   k_march_rays<<<div_up(n_alive, kMarchThreads), kMarchThreads, 0, (cudaStream_t)stream>>>(
-      p, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, grid, fars, xyzs, dirs, deltas, noises, n_rows);
+      p, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, grid, fars, xyzs, dirs, deltas, noises, n_rows, nullptr, 0u, 0u);
   return finish_launch();
 }
+
+namespace snerf {
+// The same launch with n_alive / n_step / the padded row count taken from device memory (render_loop.cu): the grid covers
+// n_alive_upper rays, *n_alive_dev (<= n_alive_upper) of them are marched.
+int march_rays_device_sized(uint32_t n_alive_upper, const int32_t* n_alive_dev, uint32_t n_total, uint32_t min_n_step,
+                            const int32_t* rays_alive, const float* rays_t, const float* rays_o, const float* rays_d,
+                            float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid,
+                            const float* fars, float* xyzs, float* dirs, float* deltas, cudaStream_t stream) {
+  if (n_alive_upper == 0) return SNERF_OK;
+  MarchParams p;
+  if (int e = make_march_params(&p, bound, dt_gamma, max_steps, C, H)) return e;
+  k_march_rays<<<div_up(n_alive_upper, kMarchThreads), kMarchThreads, 0, stream>>>(
+      p, 0u, 0u, rays_alive, rays_t, rays_o, rays_d, grid, fars, xyzs, dirs, deltas, nullptr, 0u, n_alive_dev, n_total,
+      min_n_step);
+  return finish_launch();
+}
+}  // namespace snerf
 
 int snerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
                      const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,

@@ -66,6 +66,12 @@ static size_t carve_render(const snerf_field_desc* f, uint32_t N, uint32_t min_n
   return off;
 }
 
+// raymarch.cu: march_rays with its sizes read from device memory
+int march_rays_device_sized(uint32_t n_alive_upper, const int32_t* n_alive_dev, uint32_t n_total, uint32_t min_n_step,
+                            const int32_t* rays_alive, const float* rays_t, const float* rays_o, const float* rays_d,
+                            float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid,
+                            const float* fars, float* xyzs, float* dirs, float* deltas, cudaStream_t stream);
+
 }  // namespace snerf
 
 using namespace snerf;
@@ -103,15 +109,24 @@ int snerf_render_rays(const snerf_field_desc* f, const float* rays_o, const floa
   k_render_init<<<div_up(N, 256), 256, 0, s>>>(N, nears, c.alive[0], c.rays_t);
   if (int e = finish_launch()) return e;
 
+  // The per-iteration count read stays (the schedule depends on it), but the device does not wait for the host's wake-up:
+  // right after the compaction the NEXT iteration's march is launched with its sizes taken from device memory (the alive
+  // count the compaction just wrote; n_step and the row count derived from it in the kernel exactly as below), so it runs
+  // while the host waits for the 4-byte copy, wakes up and issues the field kernels.  Same kernels, same schedule, same bits.
+  cudaEvent_t count_read = nullptr;
+  if (cudaEventCreateWithFlags(&count_read, cudaEventDisableTiming) != cudaSuccess) return (int)cudaGetLastError();
+  struct EventGuard { cudaEvent_t e; ~EventGuard() { cudaEventDestroy(e); } } guard{count_read};
   uint32_t n_alive = N, step = 0, cur = 0;
+  bool marched = false;  // the march of the current iteration is already in the stream
   while (step < max_steps && n_alive > 0) {
     uint32_t n_step = N / n_alive < 8u ? N / n_alive : 8u;  // max(min(N // n_alive, 8), 1), nerf/renderer.py:130
     if (n_step < min_n_step) n_step = min_n_step;
     if (n_step < 1u) n_step = 1u;
     const uint32_t M = pad128((uint64_t)n_alive * n_step);
-    if (int e = snerf_march_rays_ex(n_alive, n_step, c.alive[cur], c.rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
-                                    grid, nears, fars, c.xyzs, c.dirs, c.deltas, step == 0 ? noises : nullptr, M, stream))
-      return e;
+    if (!marched)
+      if (int e = snerf_march_rays_ex(n_alive, n_step, c.alive[cur], c.rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
+                                      grid, nears, fars, c.xyzs, c.dirs, c.deltas, step == 0 ? noises : nullptr, M, stream))
+        return e;
     if (int e = snerf_field_forward(f, c.xyzs, c.dirs, M, table, w_sigma, w_color, precision, c.sigmas, c.rgbs, nullptr, 0,
                                     c.field_ws, c.field_bytes, stream))
       return e;
@@ -126,7 +141,15 @@ int snerf_render_rays(const snerf_field_desc* f, const float* rays_o, const floa
       return e;
     cur ^= 1u;
     cudaMemcpyAsync(hc, c.count, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-    cudaError_t err = cudaStreamSynchronize(s);  // the reference's per-iteration read (masked_select, :158)
+    if (cudaEventRecord(count_read, s) != cudaSuccess) return (int)cudaGetLastError();
+    marched = false;
+    if (step + n_step < max_steps) {  // the next iteration's march, sized on the device (a no-op when nothing is alive)
+      if (int e = march_rays_device_sized(n_alive, c.count, N, min_n_step, c.alive[cur], c.rays_t, rays_o, rays_d, bound,
+                                          dt_gamma, max_steps, C, H, grid, fars, c.xyzs, c.dirs, c.deltas, s))
+        return e;
+      marched = true;
+    }
+    cudaError_t err = cudaEventSynchronize(count_read);  // the reference's per-iteration read (masked_select, :158)
     if (err != cudaSuccess) return (int)err;
     if (stats) {
       stats->iterations += 1;
@@ -136,6 +159,7 @@ int snerf_render_rays(const snerf_field_desc* f, const float* rays_o, const floa
     n_alive = *hc > 0 ? (uint32_t)*hc : 0u;
     step += n_step;
   }
+  if (cudaStreamSynchronize(s) != cudaSuccess) return (int)cudaGetLastError();  // (a speculative march may still be running)
   return SNERF_OK;
 }
 
