@@ -869,6 +869,7 @@ int snerf_march_rays_ex(uint32_t n_alive, uint32_t n_step, const int32_t* rays_a
   return finish_launch();
 }
 
+extern "C++" {
 namespace snerf {
 // The same launch with n_alive / n_step / the padded row count taken from device memory (render_loop.cu): the grid covers
 // n_alive_upper rays, *n_alive_dev (<= n_alive_upper) of them are marched.
@@ -885,6 +886,7 @@ int march_rays_device_sized(uint32_t n_alive_upper, const int32_t* n_alive_dev, 
   return finish_launch();
 }
 }  // namespace snerf
+}  // extern "C++"
 
 int snerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
                      const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
