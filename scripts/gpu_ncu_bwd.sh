@@ -1,0 +1,9 @@
+#!/usr/bin/env bash
+# ncu --set full of the two backward MLP kernels (one launch each) of an eager cfg2 step -> gpurun_out/r2b_prof_bwd.ncu-rep
+set -u
+mkdir -p gpurun_out
+CMD="python bench.py --steps 2 --warmup 3 --precision bf16 --no-graph --no-cpu --no-stages --no-render --no-large --no-ref-kernels"
+timeout 300 $CMD > gpurun_out/r2b_plain.log 2>&1 && \
+timeout 800 ncu --set full --clock-control none --import-source on -k 'regex:k_field_bwd' -s 4 -c 2 -f -o gpurun_out/r2b_prof_bwd $CMD > gpurun_out/r2b_ncu.log 2>&1
+echo "ncu full rc=$?"; tail -3 gpurun_out/r2b_ncu.log
+ls -la gpurun_out/r2b_prof_bwd.ncu-rep 2>/dev/null
