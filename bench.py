@@ -850,6 +850,27 @@ def run_gpu_arm(args):
             out["roofline"]["issued_frac"] = issued[dom] / (t_ms * 1e-3) / 1e12 / pk["tf_sust"]
         if bound.startswith("l2"):
             out["roofline"]["bound_detail"] = f"L2-resident table: {bound} peak of this run"
+        # What actually binds the backward MLP kernels is the SM's shared-memory data pipe (128 B/clk/SM: tensor-core
+        # operand fetches + the epilogues' LDS/STS + the bulk copies of the weight ring all go through it), not the tensor
+        # pipe.  Bytes per 128-sample tile from the kernel's static schedule (checked against the ncu
+        # wavefront counters of profiles/r2b_ncu_full_bwd_smem_pipe.csv: tc 910 / 653 KB, TMA 228 / 164 KB per tile as
+        # modelled, LSU 524 / 459 KB incl. ~100 KB of bank-conflict replays), times the tiles of the busiest CTA, against
+        # 128 B/clk at the SM clock sampled in this run.
+        smem_tile = {"color_net_bwd": {"mma_operands": 908, "epilogue_lsu": 414, "weight_ring": 232},
+                     "sigma_net_bwd": {"mma_operands": 652, "epilogue_lsu": 332, "weight_ring": 164}}
+        smem_ncu = {"color_net_bwd": 0.850, "sigma_net_bwd": 0.838}  # tc + lsu + tma wavefronts, % of peak, under ncu
+        def smem_pipe(k, tm_ms):
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            tiles = -(-(-(-M // 128)) // n_sm)  # ceil(ceil(M/128) / SMs): the busiest CTA's tiles
+            kb = sum(smem_tile[k].values())
+            mhz = (out.get("clocks") or {}).get("sm_mhz") or 1965.0
+            peak = 128.0 * mhz * 1e6 / 1e9  # GB/s per SM
+            ach = tiles * kb * 1024.0 / (tm_ms * 1e-3) / 1e9
+            return {"bound": "shared-memory data pipe (128 B/clk/SM)", "KB_per_tile": smem_tile[k], "tiles_per_cta": tiles,
+                    "achieved_GBs_per_sm": round(ach, 1), "peak_GBs_per_sm": round(peak, 1), "frac_model": round(ach / peak, 4),
+                    "frac_ncu_wavefronts": smem_ncu[k], "source": "profiles/r2b_ncu_full_bwd_smem_pipe.csv"}
+        if dom in smem_tile:
+            out["roofline"]["smem_pipe"] = smem_pipe(dom, t_ms)
         out["stage_rooflines"] = {}
         for k, (tm, (b_, w)) in cands.items():
             if tm > 0:
@@ -858,6 +879,7 @@ def run_gpu_arm(args):
                                              "frac": round(a_ / p_, 4) if p_ else None}
                 if k in issued:
                     out["stage_rooflines"][k]["issued_frac_incl_recompute"] = round(issued[k] / (tm * 1e-3) / 1e12 / pk["tf_sust"], 4)
+                    out["stage_rooflines"][k]["smem_pipe"] = smem_pipe(k, tm)
                 if k in ("hashgrid_gather", "hashgrid_scatter"):
                     own = (12 + 64) * M if k == "hashgrid_gather" else (12 + 128) * M  # what must cross HBM: the sample's rows
                     out["stage_rooflines"][k].update({
