@@ -80,7 +80,8 @@ void field_tc_set_side_reduce(uint32_t on);
 #endif
 int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                      const float* w_sigma, const float* w_color, float* sigmas, float* rgbs, float* geo_feat,
-                     bool sigma_only, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, cudaStream_t s);
+                     bool sigma_only, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, cudaStream_t s,
+                     bool weights_packed = false);
 int field_tc_backward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                       const float* w_sigma, const float* w_color, const float* grad_sigmas, const float* grad_rgbs,
                       float* grad_table, float* grad_w_sigma, float* grad_w_color, const void* saved, size_t saved_bytes,

@@ -1182,7 +1182,10 @@ static int launch_bwd(const TcParams& p, const PackedNet& n, uint32_t M, cudaStr
 
 int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* dirs, uint32_t M, const float* table,
                      const float* w_sigma, const float* w_color, float* sigmas, float* rgbs, float* geo_feat,
-                     bool sigma_only, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, cudaStream_t s) {
+                     bool sigma_only, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, cudaStream_t s,
+                     bool weights_packed) {
+  // weights_packed: an earlier call with the same parameters and the same `ws` / `saved` base left the packed operand
+  // images there (they sit at the head of the buffer, independent of M): the inference loop packs once per frame
   if (ws_bytes < field_tc_workspace_bytes(f, M, 0)) return SNERF_E_WORKSPACE;
   if (((uintptr_t)ws & 15u) || ((uintptr_t)saved & 15u)) return SNERF_E_BADARG;
   if (saved && saved_bytes < field_tc_saved_bytes(f, M)) return SNERF_E_WORKSPACE;
@@ -1197,7 +1200,7 @@ int field_tc_forward(const snerf_field_desc* f, const float* xyzs, const float* 
   // loop's calls stay on one stream: they are launch-bound and three more API calls per call would show.
   SideStream* side = (saved && g_side_reduce) ? side_stream(s) : nullptr;
   bool pack_forked = false;
-  if (st & kStFwdPack) {
+  if ((st & kStFwdPack) && !weights_packed) {
     cudaStream_t sp = s;
     if (side) {
       if (cudaEventRecord(side->start, s) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->start, 0) != cudaSuccess)

@@ -11,6 +11,7 @@
 //
 // Unlike every other entry point this one synchronises the stream (once per iteration, like the reference).
 #include "common.cuh"
+#include "field_common.cuh"
 
 namespace snerf {
 
@@ -127,9 +128,14 @@ int snerf_render_rays(const snerf_field_desc* f, const float* rays_o, const floa
       if (int e = snerf_march_rays_ex(n_alive, n_step, c.alive[cur], c.rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H,
                                       grid, nears, fars, c.xyzs, c.dirs, c.deltas, step == 0 ? noises : nullptr, M, stream))
         return e;
-    if (int e = snerf_field_forward(f, c.xyzs, c.dirs, M, table, w_sigma, w_color, precision, c.sigmas, c.rgbs, nullptr, 0,
-                                    c.field_ws, c.field_bytes, stream))
+    if (precision == SNERF_PRECISION_BF16) {  // (the weights' operand images are packed by the first iteration only)
+      if (int e = field_tc_forward(f, c.xyzs, c.dirs, M, table, w_sigma, w_color, c.sigmas, c.rgbs, nullptr, false, nullptr, 0,
+                                   c.field_ws, c.field_bytes, s, step > 0))
+        return e;
+    } else if (int e = snerf_field_forward(f, c.xyzs, c.dirs, M, table, w_sigma, w_color, precision, c.sigmas, c.rgbs, nullptr,
+                                           0, c.field_ws, c.field_bytes, stream)) {
       return e;
+    }
     if (density_scale != 1.0f) {
       k_scale<<<div_up(M, 256), 256, 0, s>>>(c.sigmas, M, density_scale);
       if (int e = finish_launch()) return e;
