@@ -519,7 +519,9 @@ def cfg5_profile(args, dev, world, rank, bitfield, barrier, max_over_ranks, n_to
     # ---- sharded
     model = make_model()
     ts = TrainStep(model, hi - lo, max_steps=MAX_STEPS, use_graph=not args.no_graph, world_size=world, loss_scale=1.0 / world,
-                   exchange=args.exchange, pipeline=args.pipeline)
+                   exchange=args.exchange, pipeline=args.pipeline,
+                   overlap_exchange={"auto": "auto", "on": True, "off": False}[args.overlap_exchange],
+                   overlap_split_level=args.overlap_split_level)
     shards = [tuple(torch.from_numpy(np.ascontiguousarray(a[lo:hi])).to(dev) for a in b[1:]) for b in full]
     packed = [torch.cat([t.reshape(-1) for t in s]) for s in shards]
     ts.warmup(*shards[0], iters=2, batches=shards)
@@ -598,7 +600,9 @@ def run_gpu_arm(args):
     # B200 it does not pay for the exchange -- 0.731 vs 0.718 and 0.812 vs 0.808 ms/step -- so it is off by default; the
     # optimiser update does profit from it, see with_optimizer)
     ts = TrainStep(model, RAYS_PER_GPU, max_steps=MAX_STEPS, use_graph=not args.no_graph, world_size=world,
-                   loss_scale=1.0 / world, exchange=args.exchange, pipeline=world > 1 and args.pipeline)
+                   loss_scale=1.0 / world, exchange=args.exchange, pipeline=world > 1 and args.pipeline,
+                   overlap_exchange={"auto": "auto", "on": True, "off": False}[args.overlap_exchange],
+                   overlap_split_level=args.overlap_split_level)
     d_batches = [tuple(torch.from_numpy(a).to(dev) for a in b[1:]) for b in batches]
     d_packed = [torch.cat([t.reshape(-1) for t in b]) for b in d_batches]   # [rays_o | rays_d | target], resident in HBM
     h_packed = []                                                           # the same in pinned host memory (one H2D copy)
@@ -702,7 +706,11 @@ def run_gpu_arm(args):
                    "cuda_graph": ts.graph is not None, "parallelism": f"ray-sharded dp{world}",
                    "exchange_schedule": ("the exchange of step k runs beside the ray march of step k+1 (second stream inside the "
                                          "graph, joined before the hash-grid gather); K exchanges for K steps, the last one by "
-                                         "finish() inside the timed region") if ts._pipelined() else "after the backward, same stream",
+                                         "finish() inside the timed region") if ts._pipelined() else (
+                                         f"split against the table scatter-add: levels [{ts.overlap_split_level}, L) are scattered first "
+                                         "and their slice of the arena is exchanged on a second stream (flag channel 1) beside the "
+                                         "coarse levels' scatter-add; MLP gradients + coarse levels follow on the step's stream"
+                                         if ts._overlap_exchange_on() else "after the backward, same stream"),
                    "gradient_exchange": {"none": "none (one rank)",
                                          "nvls": "one kernel per rank, reduced inside the NVSwitch (multimem.ld_reduce / "
                                                  "multimem.st on a multicast mapping of the gradient arenas), inside the "
@@ -929,6 +937,8 @@ def main():
     ap.add_argument("--no-ref-kernels", action="store_true")
     ap.add_argument("--no-cfg5", action="store_true")
     ap.add_argument("--pipeline", action="store_true")
+    ap.add_argument("--overlap-exchange", default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--overlap-split-level", type=int, default=8)
     ap.add_argument("--exchange", default="auto", choices=["auto", "nvls", "p2p", "nccl"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

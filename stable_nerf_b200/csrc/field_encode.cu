@@ -107,7 +107,15 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_bwd(snerf_grid_desc g,
     xs[i] = v;
   }
   const float2* gin = reinterpret_cast<const float2*>(grad_enc) + (size_t)m0 * L;
-  for (uint32_t i = threadIdx.x; i < ns * L; i += kEncThreads) tile[tile_slot(i / L, i % L)] = __ldg(gin + i);
+  if (level_begin == 0 && level_end >= L) {
+    for (uint32_t i = threadIdx.x; i < ns * L; i += kEncThreads) tile[tile_slot(i / L, i % L)] = __ldg(gin + i);
+  } else {  // a call for some of the levels reads only their columns of the gradient rows
+    const uint32_t nl = min(level_end, L) - level_begin;
+    for (uint32_t i = threadIdx.x; i < ns * nl; i += kEncThreads) {
+      const uint32_t s = i / nl, l = level_begin + i % nl;
+      tile[tile_slot(s, l)] = __ldg(gin + (size_t)s * L + l);
+    }
+  }
   __syncthreads();
   // A warp works on 32 consecutive samples of ONE level.  The level is derived from a warp index the compiler knows to
   // be uniform (a shuffle's result), so the level table sits in uniform registers, `dedupe` is a uniform branch and the

@@ -69,7 +69,8 @@ class TrainStep:
 
     def __init__(self, model, n_rays, max_steps=1024, bg_color=1, T_thresh=1e-4, use_graph=True, world_size=1,
                  loss_scale=1.0, fused=True, perturb=False, dt_gamma=0, optimizer=None, overlap_allreduce=False,
-                 scatter_groups=2, group=None, exchange="auto", exchange_timeout_ms=0, pipeline=False):
+                 scatter_groups=2, group=None, exchange="auto", exchange_timeout_ms=0, pipeline=False,
+                 overlap_exchange="auto", overlap_split_level=8):
         self.model, self.n_rays, self.max_steps = model, int(n_rays), int(max_steps)
         self.bg_color, self.T_thresh, self.world_size = bg_color, T_thresh, world_size
         self.loss_scale = loss_scale
@@ -101,6 +102,14 @@ class TrainStep:
         self.overlap_allreduce = bool(overlap_allreduce) and world_size > 1
         self.scatter_groups = int(scatter_groups)
         self.group = group  # process group of the gradient exchange (None = the default group)
+        # In-graph exchange (NVLS / peer kernel) split in two against the table scatter-add: the FINE levels
+        # [overlap_split_level, L) -- the bulk of the bytes, the tail of the gradient arena -- are scattered first and their
+        # slice is exchanged on a high-priority second stream (its own flag channel) while the coarse levels are still being
+        # scattered; the rest (MLP gradients + coarse levels) follows on the step's stream.  "auto": on for the NVLS kernel
+        # (32 CTAs: it runs beside the scatter-add), off for the peer kernel (2-3 ranks: measured 763 vs 768 us/step).
+        self.overlap_exchange = overlap_exchange
+        self.overlap_split_level = int(overlap_split_level)
+        self._ex_stream = None
         dev = next(model.parameters()).device
         C = model.channel_dim
         # one allocation [rays_o | rays_d | target] (and a pinned host mirror of it): a step's inputs arrive in ONE H2D copy
@@ -228,7 +237,7 @@ class TrainStep:
         b["field_ws"] = torch.empty(max(b["field_ws_bytes"], 256), dtype=torch.uint8, device=dev)
         b["saved_bytes"] = lib.snerf_field_saved_bytes(m.fdesc, M, prec)
         b["saved"] = torch.empty(b["saved_bytes"], dtype=torch.uint8, device=dev) if b["saved_bytes"] else None
-        if self.overlap_allreduce and prec == _lib.PRECISION_BF16:
+        if (self.overlap_allreduce or self._overlap_exchange_on(M)) and prec == _lib.PRECISION_BF16:
             b["d_enc"] = e(M, m.fdesc.grid.n_levels * m.fdesc.grid.n_features)
         bg = self.bg_color
         b["bg"] = bg.to(**f32).contiguous().view(-1) if torch.is_tensor(bg) else None
@@ -343,6 +352,47 @@ class TrainStep:
             return
         self._fused_backward(b, M, mark)
 
+    def _overlap_exchange_on(self, M=None):
+        if self.exchange is None or _precision_code(self.model.precision) != _lib.PRECISION_BF16:
+            return False
+        L = int(self.model.fdesc.grid.n_levels)
+        if not (0 < self.overlap_split_level < L):
+            return False
+        if self.overlap_exchange == "auto":
+            # measured on 8 B200 (NVLS): 4096 rays per rank 0.7765 -> 0.746 ms/step; 32768 rays per rank (2.9 M rows: the
+            # scatter-add is 1 ms, the exchange 0.15) 4.43 -> 4.46-4.51 ms/step -- two launches of a long scatter-add cost
+            # more than the exchange they hide, so "auto" splits short steps only
+            if M is None:
+                M = self._bufs["M"] if self._bufs is not None else _pad_up(max(int(self.model.mean_count), 0), 128)
+            return self.exchange_kind == "nvls" and 0 < M <= (1 << 20)
+        return bool(self.overlap_exchange)
+
+    def _scatter_and_exchange(self, b, M):
+        """Table scatter-add in two groups of levels with the fine group's slice of the arena exchanged beside the coarse
+        group's scatter-add (second stream, flag channel 1); everything is recorded into the step's graph."""
+        m = self.model
+        lib = _lib.load()
+        P, S, chk = _lib.ptr, _lib.stream(), _lib.check
+        g = m.fdesc.grid
+        nm, F, L, Ls = m.sigma_net.n_mlp, int(g.n_features), int(g.n_levels), self.overlap_split_level
+        sp = m.sigma_net.params
+        grad_table = sp.grad[nm:]
+        ex = self.exchange
+        fine_lo = self._ex_off[id(sp)] + nm + int(g.offset[Ls]) * F  # first float of level Ls in the arena
+        assert fine_lo % 4 == 0
+        chk(lib.snerf_hashgrid_backward_levels(g, P(b["xyzs"]), float(m.bound), P(b["d_enc"]), M, P(grad_table), Ls, L, S),
+            "scatter fine levels")
+        if self._ex_stream is None:
+            self._ex_stream = torch.cuda.Stream(device=self.rays_o.device, priority=-1)
+        cur = torch.cuda.current_stream()
+        self._ex_stream.wait_stream(cur)
+        with torch.cuda.stream(self._ex_stream):
+            ex.all_reduce(lo=fine_lo, hi=ex.n_floats, channel=1)
+        chk(lib.snerf_hashgrid_backward_levels(g, P(b["xyzs"]), float(m.bound), P(b["d_enc"]), M, P(grad_table), 0, Ls, S),
+            "scatter coarse levels")
+        ex.all_reduce(lo=0, hi=fine_lo, channel=0)
+        cur.wait_stream(self._ex_stream)
+
     def _fused_backward(self, b, M, mark, composite=True, exchange=True):
         m, N, C = self.model, self.n_rays, self.model.channel_dim
         lib = _lib.load()
@@ -361,10 +411,16 @@ class TrainStep:
         if composite:
             mark("composite_bwd")
         flags = (_lib.BWD_ZERO_TABLE_GRAD | _lib.BWD_ZERO_W_GRADS) if (self.zero_in_backward and not self._opt_zeroes) else 0
+        split = exchange and self.exchange is not None and b.get("d_enc") is not None and self._overlap_exchange_on(M)
+        d_enc = b.get("d_enc") if (split or self.exchange is None) else None  # (stop before the scatter-add only for a split)
         chk(lib.snerf_field_backward_ex(m.fdesc, P(b["xyzs"]), P(b["dirs"]), M, P(spd[nm:]), P(spd[:nm]), P(cp.detach()),
                                         P(b["g_sig"]), P(b["g_rgb"]), prec, P(sp.grad[nm:]), P(sp.grad[:nm]), P(cp.grad),
                                         P(b["saved"]), b["saved_bytes"], P(b["field_ws"]), b["field_ws_bytes"],
-                                        P(b.get("d_enc")), flags, S), "field backward")
+                                        P(d_enc), flags, S), "field backward")
+        if split:
+            self._scatter_and_exchange(b, M)
+            mark("field_bwd")
+            return
         mark("field_bwd")
         if self.exchange is not None and exchange:  # all ranks' gradients summed in place, same stream: part of the captured step
             self.exchange.all_reduce()

@@ -53,13 +53,16 @@ def main():
     scale = float(g_ref.abs().max())
 
     out = {"world": world, "loss_ref": loss_ref, "kinds": {}}
-    for kind in ("nvls", "p2p", "nccl"):
+    # "+split": the in-graph exchange split against the table scatter-add (TrainStep(overlap_exchange=True); the default
+    # for NVLS), "-split": the whole arena after the backward
+    for kind in ("nvls", "nvls-split", "p2p", "p2p+split", "nccl"):
         for use_graph in (False, True):
             key = f"{kind}/{'graph' if use_graph else 'eager'}"
             model = make_model(dev, bitfield)
             try:
                 ts = TrainStep(model, hi - lo, max_steps=MAX_STEPS, use_graph=use_graph, world_size=world,
-                               loss_scale=1.0 / world, exchange=kind, exchange_timeout_ms=20000)
+                               loss_scale=1.0 / world, exchange=kind.split("+")[0].split("-")[0], exchange_timeout_ms=20000,
+                               overlap_exchange=(True if kind.endswith("+split") else False if kind.endswith("-split") else "auto"))
             except RuntimeError as e:  # the same decision on every rank (the set-up agrees on it collectively)
                 out["kinds"][key] = {"unavailable": str(e)[:300]}
                 continue
@@ -76,7 +79,7 @@ def main():
             dist.all_reduce(gmin, op=dist.ReduceOp.MIN)
             calls, waits = ts.exchange.status() if ts.exchange is not None else (0, 0)
             out["kinds"][key] = {
-                "exchange_kind": ts.exchange_kind, "note": ts.exchange_error,
+                "exchange_kind": ts.exchange_kind, "note": ts.exchange_error, "split": ts._overlap_exchange_on(),
                 "grad_rel_err_vs_single_gpu": float((g - g_ref).abs().max()) / scale,
                 "rank_disagreement": float((gmax - gmin).abs().max()) / scale,
                 "loss_mean_over_ranks": float(loss) / world, "timeouts": waits, "exchange_calls": calls}
