@@ -521,7 +521,8 @@ def cfg5_profile(args, dev, world, rank, bitfield, barrier, max_over_ranks, n_to
     ts = TrainStep(model, hi - lo, max_steps=MAX_STEPS, use_graph=not args.no_graph, world_size=world, loss_scale=1.0 / world,
                    exchange=args.exchange, pipeline=args.pipeline,
                    overlap_exchange={"auto": "auto", "on": True, "off": False}[args.overlap_exchange],
-                   overlap_split_level=args.overlap_split_level)
+                   overlap_split_level=[int(v) for v in str(args.overlap_split_level).split(",")],
+                   overlap_side_ctas=args.overlap_side_ctas)
     shards = [tuple(torch.from_numpy(np.ascontiguousarray(a[lo:hi])).to(dev) for a in b[1:]) for b in full]
     packed = [torch.cat([t.reshape(-1) for t in s]) for s in shards]
     ts.warmup(*shards[0], iters=2, batches=shards)
@@ -602,7 +603,8 @@ def run_gpu_arm(args):
     ts = TrainStep(model, RAYS_PER_GPU, max_steps=MAX_STEPS, use_graph=not args.no_graph, world_size=world,
                    loss_scale=1.0 / world, exchange=args.exchange, pipeline=world > 1 and args.pipeline,
                    overlap_exchange={"auto": "auto", "on": True, "off": False}[args.overlap_exchange],
-                   overlap_split_level=args.overlap_split_level)
+                   overlap_split_level=[int(v) for v in str(args.overlap_split_level).split(",")],
+                   overlap_side_ctas=args.overlap_side_ctas)
     d_batches = [tuple(torch.from_numpy(a).to(dev) for a in b[1:]) for b in batches]
     d_packed = [torch.cat([t.reshape(-1) for t in b]) for b in d_batches]   # [rays_o | rays_d | target], resident in HBM
     h_packed = []                                                           # the same in pinned host memory (one H2D copy)
@@ -708,6 +710,7 @@ def run_gpu_arm(args):
                                          "graph, joined before the hash-grid gather); K exchanges for K steps, the last one by "
                                          "finish() inside the timed region") if ts._pipelined() else (
                                          f"split against the table scatter-add: levels [{ts.overlap_split_level}, L) are scattered first "
+                                         f"({ts.overlap_side_ctas} CTAs for that exchange) "
                                          "and their slice of the arena is exchanged on a second stream (flag channel 1) beside the "
                                          "coarse levels' scatter-add; MLP gradients + coarse levels follow on the step's stream"
                                          if ts._overlap_exchange_on() else "after the backward, same stream"),
@@ -938,7 +941,8 @@ def main():
     ap.add_argument("--no-cfg5", action="store_true")
     ap.add_argument("--pipeline", action="store_true")
     ap.add_argument("--overlap-exchange", default="auto", choices=["auto", "on", "off"])
-    ap.add_argument("--overlap-split-level", type=int, default=8)
+    ap.add_argument("--overlap-split-level", default="8", help="cut level(s) of the split exchange, e.g. 8 or 10,6")
+    ap.add_argument("--overlap-side-ctas", type=int, default=8)
     ap.add_argument("--exchange", default="auto", choices=["auto", "nvls", "p2p", "nccl"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -244,14 +244,16 @@ class P2PExchange:
         self._arena, self._flags = ctypes.c_void_p(), ctypes.c_void_p()
 
     # ---- use
-    def all_reduce(self, lo=0, hi=None, channel=0):
+    def all_reduce(self, lo=0, hi=None, channel=0, n_ctas=None):
         """Sum floats [lo, hi) of the arenas of all ranks in place (current stream; capturable in a CUDA graph).
-        Calls that may overlap in time (different streams) must use different channels."""
+        Calls that may overlap in time (different streams) must use different channels.  ``n_ctas`` overrides the
+        exchange's CTA count for this call (an exchange that runs beside another kernel wants fewer)."""
         hi = self.n_floats if hi is None else int(hi)
         if lo % 4 or hi % 4:
             raise ValueError("p2p all_reduce: range bounds must be multiples of 4 floats")
+        n_ctas = self.n_ctas if not n_ctas else int(n_ctas)
         check(self.lib.snerf_p2p_allreduce(ctypes.byref(self.peers), self.rank, self.world, int(lo), hi - int(lo), int(channel),
-                                           self.n_ctas, _lib.stream()), "p2p all-reduce")
+                                           n_ctas, _lib.stream()), "p2p all-reduce")
 
     def raise_on_error(self):
         """Raises when an exchange of this rank gave up waiting for another rank (the kernel left the gradients untouched

@@ -11,6 +11,8 @@ occupancy bitfield is broadcast from rank 0, and the flat gradients (colour MLP,
 with NCCL.  The reference itself does not synchronise NeRF gradients (it unwraps the model from DDP, train.py:188);
 the oracle for the sharded step is the single-GPU step on the concatenated batch.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -70,7 +72,7 @@ class TrainStep:
     def __init__(self, model, n_rays, max_steps=1024, bg_color=1, T_thresh=1e-4, use_graph=True, world_size=1,
                  loss_scale=1.0, fused=True, perturb=False, dt_gamma=0, optimizer=None, overlap_allreduce=False,
                  scatter_groups=2, group=None, exchange="auto", exchange_timeout_ms=0, pipeline=False,
-                 overlap_exchange="auto", overlap_split_level=8):
+                 overlap_exchange="auto", overlap_split_level=8, overlap_side_ctas=8):
         self.model, self.n_rays, self.max_steps = model, int(n_rays), int(max_steps)
         self.bg_color, self.T_thresh, self.world_size = bg_color, T_thresh, world_size
         self.loss_scale = loss_scale
@@ -106,9 +108,16 @@ class TrainStep:
         # [overlap_split_level, L) -- the bulk of the bytes, the tail of the gradient arena -- are scattered first and their
         # slice is exchanged on a high-priority second stream (its own flag channel) while the coarse levels are still being
         # scattered; the rest (MLP gradients + coarse levels) follows on the step's stream.  "auto": on for the NVLS kernel
-        # (32 CTAs: it runs beside the scatter-add), off for the peer kernel (2-3 ranks: measured 763 vs 768 us/step).
+        # (few CTAs: it runs beside the scatter-add), off for the peer kernel (2 B200: 0.718 whole, 0.737 split).
+        # overlap_split_level: an int, or several cut levels (up to 3: one flag channel per exchanged group) -- measured on
+        # 4 B200: one cut at 8: 0.735 ms/step, cuts (10, 6): 0.742, (11, 8, 5): 0.762, whole: 0.774.
+        # overlap_side_ctas: CTAs of the exchanges that run beside a scatter-add -- 8 B200, cut at 8: 0.7446 / 0.7359 /
+        # 0.7327 ms/step at 32 / 16 / 8 CTAs (alone, the whole-arena exchange is fastest at 32).
         self.overlap_exchange = overlap_exchange
-        self.overlap_split_level = int(overlap_split_level)
+        self.overlap_split_levels = ([int(v) for v in overlap_split_level] if isinstance(overlap_split_level, (list, tuple))
+                                     else [int(overlap_split_level)])
+        self.overlap_split_level = self.overlap_split_levels[0]
+        self.overlap_side_ctas = int(overlap_side_ctas)
         self._ex_stream = None
         dev = next(model.parameters()).device
         C = model.channel_dim
@@ -356,7 +365,7 @@ class TrainStep:
         if self.exchange is None or _precision_code(self.model.precision) != _lib.PRECISION_BF16:
             return False
         L = int(self.model.fdesc.grid.n_levels)
-        if not (0 < self.overlap_split_level < L):
+        if not any(0 < v < L for v in self.overlap_split_levels):
             return False
         if self.overlap_exchange == "auto":
             # measured on 8 B200 (NVLS): 4096 rays per rank 0.7765 -> 0.746 ms/step; 32768 rays per rank (2.9 M rows: the
@@ -368,29 +377,35 @@ class TrainStep:
         return bool(self.overlap_exchange)
 
     def _scatter_and_exchange(self, b, M):
-        """Table scatter-add in two groups of levels with the fine group's slice of the arena exchanged beside the coarse
-        group's scatter-add (second stream, flag channel 1); everything is recorded into the step's graph."""
+        """Table scatter-add in groups of levels, fine levels first, with each finished group's slice of the arena exchanged
+        beside the next group's scatter-add (second stream, its own flag channel); the last group's slice travels with the
+        MLP gradients on the step's stream.  Everything is recorded into the step's graph."""
         m = self.model
         lib = _lib.load()
         P, S, chk = _lib.ptr, _lib.stream(), _lib.check
         g = m.fdesc.grid
-        nm, F, L, Ls = m.sigma_net.n_mlp, int(g.n_features), int(g.n_levels), self.overlap_split_level
+        nm, F, L = m.sigma_net.n_mlp, int(g.n_features), int(g.n_levels)
         sp = m.sigma_net.params
         grad_table = sp.grad[nm:]
         ex = self.exchange
-        fine_lo = self._ex_off[id(sp)] + nm + int(g.offset[Ls]) * F  # first float of level Ls in the arena
-        assert fine_lo % 4 == 0
-        chk(lib.snerf_hashgrid_backward_levels(g, P(b["xyzs"]), float(m.bound), P(b["d_enc"]), M, P(grad_table), Ls, L, S),
-            "scatter fine levels")
+        cuts = sorted({v for v in self.overlap_split_levels if 0 < v < L}, reverse=True)[:_lib.SNERF_P2P_CHANNELS - 1]
+        table0 = self._ex_off[id(sp)] + nm  # first float of the table in the arena
         if self._ex_stream is None:
             self._ex_stream = torch.cuda.Stream(device=self.rays_o.device, priority=-1)
         cur = torch.cuda.current_stream()
-        self._ex_stream.wait_stream(cur)
-        with torch.cuda.stream(self._ex_stream):
-            ex.all_reduce(lo=fine_lo, hi=ex.n_floats, channel=1)
-        chk(lib.snerf_hashgrid_backward_levels(g, P(b["xyzs"]), float(m.bound), P(b["d_enc"]), M, P(grad_table), 0, Ls, S),
+        hi_level, hi_float = L, ex.n_floats
+        for k, lvl in enumerate(cuts):
+            chk(lib.snerf_hashgrid_backward_levels(g, P(b["xyzs"]), float(m.bound), P(b["d_enc"]), M, P(grad_table), lvl,
+                                                   hi_level, S), "scatter levels")
+            lo_float = table0 + int(g.offset[lvl]) * F
+            assert lo_float % 4 == 0
+            self._ex_stream.wait_stream(cur)
+            with torch.cuda.stream(self._ex_stream):
+                ex.all_reduce(lo=lo_float, hi=hi_float, channel=1 + k, n_ctas=self.overlap_side_ctas)
+            hi_level, hi_float = lvl, lo_float
+        chk(lib.snerf_hashgrid_backward_levels(g, P(b["xyzs"]), float(m.bound), P(b["d_enc"]), M, P(grad_table), 0, hi_level, S),
             "scatter coarse levels")
-        ex.all_reduce(lo=0, hi=fine_lo, channel=0)
+        ex.all_reduce(lo=0, hi=hi_float, channel=0)
         cur.wait_stream(self._ex_stream)
 
     def _fused_backward(self, b, M, mark, composite=True, exchange=True):
