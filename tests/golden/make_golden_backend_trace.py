@@ -8,10 +8,12 @@ pinned bit-exactly against the reference kernels (tests/test_oracle.py).  ``Tens
 analytic one made of separately rounded fp32 torch ops (same bits on CPU and GPU).  A recorder notes, for every backend
 call, the function name, every argument (tensors by value BEFORE the call) and the output tensors AFTER the call.
 
-What runs: one training ``run_cuda`` on the first-epoch path (mean_count = 0: N*max_steps rows, raymarching.py:196-229),
-its backward (composite_rays_train_backward), one training ``run_cuda`` with a too-small ``mean_count`` (overflowing rays
-are dropped, raymarching.cu:417), one full inference ``run_cuda`` (the n_step schedule of nerf/renderer.py:130, every
-iteration), and direct wrapper calls of sph_from_ray / morton3D / morton3D_invert / packbits.
+What runs, for each scene of tests/trace_scene.py (s1: one cascade, the reference's defaults; s2: bound 2 = two cascades,
+dt_gamma 1/128, 4 channels, density_scale 0.5): one training ``run_cuda`` on the first-epoch path (mean_count = 0:
+N*max_steps rows, raymarching.py:196-229), its backward (composite_rays_train_backward), one training ``run_cuda`` with a
+too-small ``mean_count`` (overflowing rays are dropped, raymarching.cu:417), one full inference ``run_cuda`` (the n_step
+schedule of nerf/renderer.py:130, every iteration), for s2 also a perturbed training and inference run; and direct
+wrapper calls of sph_from_ray / morton3D / morton3D_invert / packbits.
 
 ``tests/test_backend_trace.py`` replays the trace on the GPU against ``stable_nerf_b200.backend`` (the same ten functions
 over libsnerf_b200.so) and against ``stable_nerf_b200.raymarching`` + ``NeRFRenderer`` (the drop-in operator surface).
@@ -34,7 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, "/root/reference")
 
 from oracle import oracle as orc  # noqa: E402
-from trace_scene import SCENE, analytic_field, scene_inputs  # noqa: E402
+from trace_scene import SCENES, analytic_field, scene_inputs  # noqa: E402
 
 torch.set_num_threads(1)
 torch.Tensor.cuda = lambda self, *a, **k: self
@@ -169,59 +171,80 @@ def mark(label):
     trace.append({"fn": "#", "label": label})
 
 
-inp = scene_inputs()
-m = Field(bound=SCENE["bound"], channel_dim=SCENE["channel_dim"], density_scale=SCENE["density_scale"])
-m.density_bitfield.copy_(torch.from_numpy(inp["bitfield"]))
-results = {}
+results, inputs = {}, {}
+totals = {}
+for name, SC in SCENES.items():
+    inp = scene_inputs(name)
+    inputs[name] = inp
+    kw = dict(bg_color=SC["bg_color"], max_steps=SC["max_steps"], T_thresh=SC["T_thresh"], dt_gamma=SC["dt_gamma"])
 
-# ---- training, first-epoch path (mean_count = 0)
-m.train()
-mark("train_first_epoch")
-o, d = torch.from_numpy(inp["train_o"])[None], torch.from_numpy(inp["train_d"])[None]
-out = m.run_cuda(o, d, bg_color=SCENE["bg_color"], max_steps=SCENE["max_steps"], T_thresh=SCENE["T_thresh"])
-results["train_image"], results["train_depth"] = _np(out["image"]), _np(out["depth"])
-results["train_weights_sum"] = _np(out["weights_sum"])
-results["train_counter"] = _np(m.step_counter[0])
+    def model(cls=Field):
+        mm = cls(bound=SC["bound"], channel_dim=SC["channel_dim"], density_scale=SC["density_scale"])
+        mm.density_bitfield.copy_(torch.from_numpy(inp["bitfield"]))
+        return mm
 
-# ---- its backward: d(sum(image * w) + sum(weights_sum * 0.5)) through composite_rays_train (the wrapper's autograd Function)
-mark("train_backward")
-xyzs_probe = {}
+    m = model()
+    R = lambda k, v: results.__setitem__(f"{name}_{k}", v)  # noqa: E731
 
+    # ---- training, first-epoch path (mean_count = 0)
+    m.train()
+    mark(f"{name}:train_first_epoch")
+    o, d = torch.from_numpy(inp["train_o"])[None], torch.from_numpy(inp["train_d"])[None]
+    out = m.run_cuda(o, d, **kw)
+    R("train_image", _np(out["image"])), R("train_depth", _np(out["depth"])), R("train_weights_sum", _np(out["weights_sum"]))
+    R("train_counter", _np(m.step_counter[0]))
+    total = int(_np(m.step_counter[0])[0])
+    totals[name] = total
 
-class FieldGrad(Field):
-    def forward(self, x, dd):
-        s, c = analytic_field(x, dd, self.channel_dim)
-        s, c = s.clone().requires_grad_(True), c.clone().requires_grad_(True)
-        xyzs_probe["s"], xyzs_probe["c"] = s, c
-        return s, c
+    # ---- its backward through composite_rays_train (the wrapper's autograd Function): d sum(image * w)
+    mark(f"{name}:train_backward")
+    probe = {}
 
+    class FieldGrad(Field):
+        def forward(self, x, dd):
+            s, c = analytic_field(x, dd, self.channel_dim)
+            s, c = s.clone().requires_grad_(True), c.clone().requires_grad_(True)
+            probe["s"], probe["c"] = s, c
+            return s, c
 
-mg = FieldGrad(bound=SCENE["bound"], channel_dim=SCENE["channel_dim"], density_scale=SCENE["density_scale"])
-mg.density_bitfield.copy_(torch.from_numpy(inp["bitfield"]))
-mg.train()
-out = mg.run_cuda(o, d, bg_color=SCENE["bg_color"], max_steps=SCENE["max_steps"], T_thresh=SCENE["T_thresh"])
-w_img = torch.from_numpy(inp["loss_weights"]).view_as(out["image"])
-(out["image"] * w_img).sum().backward()
-results["train_grad_sigmas"], results["train_grad_rgbs"] = _np(xyzs_probe["s"].grad), _np(xyzs_probe["c"].grad)
+    mg = model(FieldGrad)
+    mg.train()
+    out = mg.run_cuda(o, d, **kw)
+    w_img = torch.from_numpy(inp["loss_weights"]).view_as(out["image"])
+    (out["image"] * w_img).sum().backward()
+    R("train_grad_sigmas", _np(probe["s"].grad)), R("train_grad_rgbs", _np(probe["c"].grad))
 
-# ---- training with an under-estimated mean_count: rays whose samples do not fit are dropped (raymarching.cu:417)
-mark("train_mean_count")
-total = int(results["train_counter"][0])
-m.mean_count = max(total * 3 // 4, 1)
-out = m.run_cuda(o, d, bg_color=SCENE["bg_color"], max_steps=SCENE["max_steps"], T_thresh=SCENE["T_thresh"])
-results["train_mc_image"], results["train_mc_depth"] = _np(out["image"]), _np(out["depth"])
-results["train_mc_mean_count"] = np.int64(m.mean_count)
+    # ---- training with an under-estimated mean_count: rays whose samples do not fit are dropped (raymarching.cu:417)
+    mark(f"{name}:train_mean_count")
+    m.mean_count = max(total * 3 // 4, 1)
+    out = m.run_cuda(o, d, **kw)
+    R("train_mc_image", _np(out["image"])), R("train_mc_depth", _np(out["depth"]))
+    m.mean_count = 0
 
-# ---- inference loop, every iteration
-mark("eval")
-m.eval()
-eo, ed = torch.from_numpy(inp["eval_o"])[None], torch.from_numpy(inp["eval_d"])[None]
-with torch.no_grad():
-    out = m.run_cuda(eo, ed, bg_color=SCENE["bg_color"], max_steps=SCENE["max_steps"], T_thresh=SCENE["T_thresh_eval"])
-results["eval_image"], results["eval_depth"] = _np(out["image"]), _np(out["depth"])
+    # ---- inference loop, every iteration
+    mark(f"{name}:eval")
+    m.eval()
+    eo, ed = torch.from_numpy(inp["eval_o"])[None], torch.from_numpy(inp["eval_d"])[None]
+    kw_eval = dict(kw, T_thresh=SC["T_thresh_eval"])
+    with torch.no_grad():
+        out = m.run_cuda(eo, ed, **kw_eval)
+    R("eval_image", _np(out["image"])), R("eval_depth", _np(out["depth"]))
+
+    # ---- perturbed runs (the wrapper draws the noises with torch.rand: they are recorded as inputs of the backend calls,
+    # so only the call-by-call replay covers these)
+    if SC["perturbed"]:
+        torch.manual_seed(1234)
+        mark(f"{name}:train_perturbed")
+        m.train()
+        m.run_cuda(o, d, perturb=True, **kw)
+        mark(f"{name}:eval_perturbed")
+        m.eval()
+        with torch.no_grad():
+            m.run_cuda(eo, ed, perturb=True, **kw_eval)
 
 # ---- the small operators through the unmodified wrapper
 mark("utils")
+inp = inputs["s1"]
 coords = torch.from_numpy(inp["coords"])
 idx = ref_rm.morton3D(coords)
 back = ref_rm.morton3D_invert(idx)
@@ -235,13 +258,14 @@ by_fn = {}
 for r in trace:
     by_fn[r["fn"]] = by_fn.get(r["fn"], 0) + 1
 print("backend calls:", n_calls, by_fn)
-print("train samples", total, "mean_count run", int(m.mean_count))
+print("train samples per scene", totals)
 out_npz = dict(store)
 out_npz["trace_json"] = np.frombuffer(json.dumps(trace).encode(), np.uint8)
 for k, v in results.items():
     out_npz["result_" + k] = v
-for k in ("bitfield", "train_o", "train_d", "eval_o", "eval_d", "loss_weights"):
-    out_npz["input_" + k] = inp[k]
+for name, inp in inputs.items():
+    for k in ("bitfield", "train_o", "train_d", "eval_o", "eval_d", "loss_weights"):
+        out_npz[f"input_{name}_{k}"] = inp[k]
 path = os.path.join(HERE, "backend_trace.npz")
 np.savez_compressed(path, **out_npz)
 print("wrote", path, os.path.getsize(path), "bytes,", len(store), "arrays")

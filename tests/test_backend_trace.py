@@ -5,8 +5,9 @@ replayed on the GPU:
   * call by call against ``stable_nerf_b200.backend`` -- the ten functions of raymarching.h:7-18 over libsnerf_b200.so,
     what the reference's wrapper binds in place of ``_raymarching`` (INTEGRATION.md section B);
   * run by run against the drop-in operator surface (``stable_nerf_b200.raymarching`` under this repo's ``NeRFRenderer``
-    with the same analytic field): first-epoch training render and its backward, training with an under-estimated
-    ``mean_count`` (dropped rays), the whole inference loop.
+    with the same analytic field), for both scenes of tests/trace_scene.py (one cascade / two cascades + dt_gamma + 4
+    channels): first-epoch training render and its backward, training with an under-estimated ``mean_count`` (dropped
+    rays), the whole inference loop.
 
 Bars: integers and every marching output bit-exact (sample packing in ray order, as the oracle's); compositing sums and
 near/far-derived depths <= 1e-4 relative (max-norm); sph_from_ray <= 1e-6.
@@ -19,7 +20,7 @@ import numpy as np
 import pytest
 import torch
 
-from trace_scene import SCENE, analytic_field
+from trace_scene import SCENES, analytic_field
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "backend_trace.npz")
 EXACT = {"near_far_from_aabb", "morton3D", "morton3D_invert", "packbits", "march_rays_train", "march_rays"}
@@ -50,7 +51,12 @@ def test_trace_covers_the_whole_backend_surface(golden):
         params = list(inspect.signature(getattr(backend, r["fn"])).parameters.values())
         assert len(params) == N_ARGS[r["fn"]] and all(p.default is inspect.Parameter.empty for p in params), r["fn"]
     labels = [r["label"] for r in trace if r["fn"] == "#"]
-    assert labels == ["train_first_epoch", "train_backward", "train_mean_count", "eval", "utils"]
+    want = []
+    for name, sc in SCENES.items():
+        want += [f"{name}:{k}" for k in ("train_first_epoch", "train_backward", "train_mean_count", "eval")]
+        if sc["perturbed"]:
+            want += [f"{name}:train_perturbed", f"{name}:eval_perturbed"]
+    assert labels == want + ["utils"]
 
 
 def _close(got, want, tol, what):
@@ -90,16 +96,20 @@ def test_backend_replays_every_reference_call(golden, built_lib, cuda):
             else:
                 _close(got, want, 1e-6 if r["fn"] == "sph_from_ray" else 1e-4, what)
         n += 1
-    assert n == 47
+    assert n == 98
 
 
 @pytest.mark.gpu
-def test_drop_in_surface_reproduces_the_reference_runs(golden, built_lib, cuda):
+@pytest.mark.parametrize("name", list(SCENES))
+def test_drop_in_surface_reproduces_the_reference_runs(name, golden, built_lib, cuda):
     from stable_nerf_b200 import raymarching  # noqa: F401  (the module nerf/renderer.py:5 would import)
     from stable_nerf_b200.renderer import NeRFRenderer
     z, _ = golden
+    SC = SCENES[name]
     dev = torch.device("cuda:0")
     probe = {}
+    G = lambda k: z[f"result_{name}_{k}"]  # noqa: E731
+    I = lambda k: torch.from_numpy(z[f"input_{name}_{k}"]).to(dev)  # noqa: E731,E741
 
     class Field(NeRFRenderer):
         native_loop = False  # forward is overridden: the generic loop through the operator calls
@@ -111,38 +121,31 @@ def test_drop_in_surface_reproduces_the_reference_runs(golden, built_lib, cuda):
                 probe["s"], probe["c"] = s, c
             return s, c
 
-    def model():
-        m = Field(bound=SCENE["bound"], channel_dim=SCENE["channel_dim"], density_scale=SCENE["density_scale"]).to(dev)
-        m.density_bitfield.copy_(torch.from_numpy(z["input_bitfield"]))
-        return m
-
-    kw = dict(bg_color=SCENE["bg_color"], max_steps=SCENE["max_steps"], T_thresh=SCENE["T_thresh"])
-    o = torch.from_numpy(z["input_train_o"]).to(dev)[None]
-    d = torch.from_numpy(z["input_train_d"]).to(dev)[None]
+    m = Field(bound=SC["bound"], channel_dim=SC["channel_dim"], density_scale=SC["density_scale"]).to(dev)
+    m.density_bitfield.copy_(torch.from_numpy(z[f"input_{name}_bitfield"]))
+    kw = dict(bg_color=SC["bg_color"], max_steps=SC["max_steps"], T_thresh=SC["T_thresh"], dt_gamma=SC["dt_gamma"])
+    o, d = I("train_o")[None], I("train_d")[None]
     # ---- first-epoch training render + backward
-    m = model()
     m.train()
     out = m.run_cuda(o, d, **kw)
-    assert np.array_equal(m.step_counter[0].cpu().numpy(), z["result_train_counter"])
-    _close(out["image"].detach().cpu().numpy(), z["result_train_image"], 1e-4, "train image")
-    _close(out["depth"].detach().cpu().numpy(), z["result_train_depth"], 1e-4, "train depth")
-    _close(out["weights_sum"].detach().cpu().numpy(), z["result_train_weights_sum"], 1e-4, "train weights_sum")
-    w = torch.from_numpy(z["input_loss_weights"]).to(dev).view_as(out["image"])
+    assert np.array_equal(m.step_counter[0].cpu().numpy(), G("train_counter"))
+    _close(out["image"].detach().cpu().numpy(), G("train_image"), 1e-4, "train image")
+    _close(out["depth"].detach().cpu().numpy(), G("train_depth"), 1e-4, "train depth")
+    _close(out["weights_sum"].detach().cpu().numpy(), G("train_weights_sum"), 1e-4, "train weights_sum")
+    w = I("loss_weights").view_as(out["image"])
     (out["image"] * w).sum().backward()
-    _close(probe["s"].grad.cpu().numpy(), z["result_train_grad_sigmas"], 1e-4, "grad sigmas")
-    _close(probe["c"].grad.cpu().numpy(), z["result_train_grad_rgbs"], 1e-4, "grad rgbs")
+    _close(probe["s"].grad.cpu().numpy(), G("train_grad_sigmas"), 1e-4, "grad sigmas")
+    _close(probe["c"].grad.cpu().numpy(), G("train_grad_rgbs"), 1e-4, "grad rgbs")
     # ---- under-estimated mean_count: the rays that do not fit are dropped, the same ones (ray-ordered offsets)
-    m.mean_count = int(z["result_train_counter"][0]) * 3 // 4
+    m.mean_count = max(int(G("train_counter")[0]) * 3 // 4, 1)
     with torch.no_grad():
         out = m.run_cuda(o, d, **kw)
-    _close(out["image"].cpu().numpy(), z["result_train_mc_image"], 1e-4, "mean_count image")
-    _close(out["depth"].cpu().numpy(), z["result_train_mc_depth"], 1e-4, "mean_count depth")
+    _close(out["image"].cpu().numpy(), G("train_mc_image"), 1e-4, "mean_count image")
+    _close(out["depth"].cpu().numpy(), G("train_mc_depth"), 1e-4, "mean_count depth")
     # ---- the inference loop
     m.eval()
-    eo = torch.from_numpy(z["input_eval_o"]).to(dev)[None]
-    ed = torch.from_numpy(z["input_eval_d"]).to(dev)[None]
-    kw["T_thresh"] = SCENE["T_thresh_eval"]
+    kw["T_thresh"] = SC["T_thresh_eval"]
     with torch.no_grad():
-        out = m.run_cuda(eo, ed, **kw)
-    _close(out["image"].cpu().numpy(), z["result_eval_image"], 1e-4, "eval image")
-    _close(out["depth"].cpu().numpy(), z["result_eval_depth"], 1e-4, "eval depth")
+        out = m.run_cuda(I("eval_o")[None], I("eval_d")[None], **kw)
+    _close(out["image"].cpu().numpy(), G("eval_image"), 1e-4, "eval image")
+    _close(out["depth"].cpu().numpy(), G("eval_depth"), 1e-4, "eval depth")

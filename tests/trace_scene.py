@@ -4,8 +4,15 @@ and an analytic field whose fp32 values are the same on every device."""
 import numpy as np
 import torch
 
-SCENE = dict(bound=1, channel_dim=3, density_scale=1, max_steps=128, T_thresh=1e-4, T_thresh_eval=1e-4, bg_color=1,
-             n_train=160, n_eval=144)
+# s1: one cascade, the reference's defaults.  s2: bound 2 (two cascades), exponential stepping (dt_gamma), 4 channels,
+# density_scale 0.5, plus a perturbed training / inference run (the wrapper's torch.rand noises travel as recorded inputs)
+SCENES = {
+    "s1": dict(bound=1, channel_dim=3, density_scale=1, max_steps=128, T_thresh=1e-4, T_thresh_eval=1e-4, bg_color=1,
+               dt_gamma=0, n_train=160, eval_hw=12, eval_focal=16.0, seed=5, perturbed=False),
+    "s2": dict(bound=2, channel_dim=4, density_scale=0.5, max_steps=64, T_thresh=1e-4, T_thresh_eval=1e-3, bg_color=0.5,
+               dt_gamma=1.0 / 128, n_train=96, eval_hw=10, eval_focal=13.0, seed=11, perturbed=True),
+}
+SCENE = SCENES["s1"]
 
 
 def analytic_field(x, d, channel_dim):
@@ -26,15 +33,18 @@ def analytic_field(x, d, channel_dim):
     return sigma, rgb.contiguous()
 
 
-def scene_inputs():
-    """numpy inputs of the trace (generator only: the test reads every input back from the golden file)."""
+def scene_inputs(name="s1"):
+    """numpy inputs of a scene's trace (generator only: the test reads every input back from the golden file)."""
+    import math
     from stable_nerf_b200 import synthetic as syn
-    grid = syn.occupancy_grid(lego_like=True, seed=0)
+    sc = SCENES[name]
+    cascades = 1 + math.ceil(math.log2(sc["bound"]))
+    grid = syn.occupancy_grid(cascades=cascades, bound=float(sc["bound"]), lego_like=True, seed=0)
     bitfield = syn.pack_bitfield(grid)
-    train_o, train_d = syn.train_batch(SCENE["n_train"], 100, 100, 138.0, n_views=2, seed=5)
-    eval_o, eval_d = syn.full_frame(12, 12, 16.0, seed=7)
-    rng = np.random.default_rng(99)
+    train_o, train_d = syn.train_batch(sc["n_train"], 100, 100, 138.0, n_views=2, seed=sc["seed"])
+    eval_o, eval_d = syn.full_frame(sc["eval_hw"], sc["eval_hw"], sc["eval_focal"], seed=sc["seed"] + 2)
+    rng = np.random.default_rng(99 + sc["seed"])
     return dict(bitfield=bitfield, train_o=train_o, train_d=train_d, eval_o=eval_o, eval_d=eval_d,
-                loss_weights=rng.random((SCENE["n_train"], SCENE["channel_dim"]), dtype=np.float32),
+                loss_weights=rng.random((sc["n_train"], sc["channel_dim"]), dtype=np.float32),
                 coords=rng.integers(0, 128, size=(257, 3)).astype(np.int32),
                 grid_values=rng.random((2, 2048), dtype=np.float32))
