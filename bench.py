@@ -942,7 +942,7 @@ def main():
     ap.add_argument("--pipeline", action="store_true")
     ap.add_argument("--overlap-exchange", default="auto", choices=["auto", "on", "off"])
     ap.add_argument("--overlap-split-level", default="8", help="cut level(s) of the split exchange, e.g. 8 or 10,6")
-    ap.add_argument("--overlap-side-ctas", type=int, default=8)
+    ap.add_argument("--overlap-side-ctas", type=int, default=16)
     ap.add_argument("--exchange", default="auto", choices=["auto", "nvls", "p2p", "nccl"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

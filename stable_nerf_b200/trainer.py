@@ -72,7 +72,7 @@ class TrainStep:
     def __init__(self, model, n_rays, max_steps=1024, bg_color=1, T_thresh=1e-4, use_graph=True, world_size=1,
                  loss_scale=1.0, fused=True, perturb=False, dt_gamma=0, optimizer=None, overlap_allreduce=False,
                  scatter_groups=2, group=None, exchange="auto", exchange_timeout_ms=0, pipeline=False,
-                 overlap_exchange="auto", overlap_split_level=8, overlap_side_ctas=8):
+                 overlap_exchange="auto", overlap_split_level=8, overlap_side_ctas=16):
         self.model, self.n_rays, self.max_steps = model, int(n_rays), int(max_steps)
         self.bg_color, self.T_thresh, self.world_size = bg_color, T_thresh, world_size
         self.loss_scale = loss_scale
@@ -112,7 +112,8 @@ class TrainStep:
         # overlap_split_level: an int, or several cut levels (up to 3: one flag channel per exchanged group) -- measured on
         # 4 B200: one cut at 8: 0.735 ms/step, cuts (10, 6): 0.742, (11, 8, 5): 0.762, whole: 0.774.
         # overlap_side_ctas: CTAs of the exchanges that run beside a scatter-add -- 8 B200, cut at 8: 0.7446 / 0.7359 /
-        # 0.7327 ms/step at 32 / 16 / 8 CTAs (alone, the whole-arena exchange is fastest at 32).
+        # 0.7327 ms/step at 32 / 16 / 8 CTAs; 4 B200: 0.7351 / 0.7291-0.7320 / 0.7374 / 0.8050 at 32 / 16 / 8 / 4 (alone,
+        # the whole-arena exchange is fastest at 32).  16: within 0.5 % of the best on both and away from the cliff below 8.
         self.overlap_exchange = overlap_exchange
         self.overlap_split_levels = ([int(v) for v in overlap_split_level] if isinstance(overlap_split_level, (list, tuple))
                                      else [int(overlap_split_level)])
