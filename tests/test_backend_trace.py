@@ -59,6 +59,25 @@ def test_trace_covers_the_whole_backend_surface(golden):
     assert labels == want + ["utils"]
 
 
+def test_backend_signatures_equal_the_reference_header():
+    """parameter names and order of every backend function against submodules/raymarching/src/raymarching.h:7-18 (read from
+    /root/reference where it exists: the build container; skipped on the GPU box)"""
+    import re
+    from stable_nerf_b200 import backend
+    hdr = "/root/reference/submodules/raymarching/src/raymarching.h"
+    if not os.path.exists(hdr):
+        pytest.skip("reference sources not present")
+    text = open(hdr).read()
+    found = 0
+    for m in re.finditer(r"void\s+(\w+)\s*\(([^;]*)\)\s*;", text):
+        name, args = m.group(1), [a.strip().split()[-1] for a in m.group(2).split(",")]
+        ours = list(inspect.signature(getattr(backend, name)).parameters)
+        # (the reference's march_rays_train / packbits headers call the occupancy bitfield `grid`, like ours)
+        assert ours == args, f"{name}: {ours} != {args}"
+        found += 1
+    assert found == len(N_ARGS) == 10
+
+
 def _close(got, want, tol, what):
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
     assert got.shape == want.shape, what
