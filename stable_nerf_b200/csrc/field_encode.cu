@@ -89,7 +89,10 @@ __global__ void __launch_bounds__(kEncThreads) k_hashgrid_fwd(snerf_grid_desc g,
 // 16.4 M sectors to the L2 = 0.52 per clk per SM; issue 55 %, LSU data pipe 64 %, L2 atomics 42 % (55 % on the busiest
 // slice): no single unit is saturated any more, the warps wait on the gradient tile, the scan's shuffles and the
 // reductions' queue in turn.
-SNERF_TUNABLE g_dedupe_max_res = 300;  // levels with resolution <= this merge equal cells inside a warp (measured optimum)
+// levels with resolution <= this merge equal cells inside a warp.  With the five-step scan the optimum was 300 (finer levels
+// have no runs to merge and paid for the scan); with the scan depth following the warp's longest run merging everywhere is
+// the fastest (345 216 rows: 122.0 / 110.0 / 107.1 / 106.0 / 106.0 us at 150 / 300 / 420 / 600 / 4096, 332 without merging)
+SNERF_TUNABLE g_dedupe_max_res = 4096;
 
 SNERF_TUNABLE g_scatter_adaptive = 1;   // scan depth follows the warp's longest run (round 2 A/B, cfg2 step: 0.6185 -> 0.6110 ms; both: 0.6064)
 
