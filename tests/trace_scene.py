@@ -13,6 +13,10 @@ SCENES = {
                dt_gamma=1.0 / 128, n_train=96, eval_hw=10, eval_focal=13.0, seed=11, perturbed=True),
 }
 SCENE = SCENES["s1"]
+# the whole-step goldens (tests/golden/make_golden_step.py) also run BASELINE.json's configs[3] at its full size: two 64x64
+# views = 8192 rays, 4 channels, max_steps 256 (a sane focal; the reference's degenerate one is covered by the live tests)
+STEP_SCENES = dict(SCENES, cfg4=dict(bound=1, channel_dim=4, density_scale=1, max_steps=256, T_thresh=1e-4, T_thresh_eval=1e-4,
+                                     bg_color=1, dt_gamma=0, n_train=8192, eval_hw=16, eval_focal=20.0, seed=21, perturbed=False))
 
 
 def analytic_field(x, d, channel_dim):
@@ -37,11 +41,15 @@ def scene_inputs(name="s1"):
     """numpy inputs of a scene's trace (generator only: the test reads every input back from the golden file)."""
     import math
     from stable_nerf_b200 import synthetic as syn
-    sc = SCENES[name]
+    sc = STEP_SCENES[name]
     cascades = 1 + math.ceil(math.log2(sc["bound"]))
     grid = syn.occupancy_grid(cascades=cascades, bound=float(sc["bound"]), lego_like=True, seed=0)
     bitfield = syn.pack_bitfield(grid)
-    train_o, train_d = syn.train_batch(sc["n_train"], 100, 100, 138.0, n_views=2, seed=sc["seed"])
+    if name == "cfg4":  # two full 64x64 views
+        views = [syn.full_frame(64, 64, 90.0, seed=sc["seed"] + v) for v in range(2)]
+        train_o, train_d = np.concatenate([v[0] for v in views]), np.concatenate([v[1] for v in views])
+    else:
+        train_o, train_d = syn.train_batch(sc["n_train"], 100, 100, 138.0, n_views=2, seed=sc["seed"])
     eval_o, eval_d = syn.full_frame(sc["eval_hw"], sc["eval_hw"], sc["eval_focal"], seed=sc["seed"] + 2)
     rng = np.random.default_rng(99 + sc["seed"])
     return dict(bitfield=bitfield, train_o=train_o, train_d=train_d, eval_o=eval_o, eval_d=eval_d,
