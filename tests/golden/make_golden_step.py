@@ -34,11 +34,11 @@ from utils.loss_utils import l1_loss  # noqa: E402  (unmodified)
 
 out = {}
 torch.set_num_threads(8)  # (the MLP matmuls of the 8192-ray case; every comparison of the test has a 1e-4 bar)
-for name, C, table_scale in (("s1", 3, 1e4), ("s2", 4, 1e4), ("cfg4", 4, 1e4)):
+for name, C, table_scale in (("s1", 3, 1e4), ("s2", 4, 1e4), ("cfg4", 4, 1e4), ("cfg2", 3, 1e4)):
     SC = SCENES[name]
     inp = scene_inputs(name)
     m = ref_network.NeRFNetwork(channel_dim=C, bound=SC["bound"], density_scale=SC["density_scale"])
-    seed = 9000 + C
+    seed = 9000 + C + (100 if name == "cfg2" else 0)
     ws, table, wc = syn.field_params(m.sigma_net.n_mlp, m.sigma_net.gdesc.n_entries * 2, m.color_net.params.numel(),
                                      shapes_sigma=m.sigma_net.shapes, shapes_color=m.color_net.shapes, seed=seed)
     table = (table * np.float32(table_scale)).astype(np.float32)  # U(-1e-4, 1e-4) * 1e4: non-degenerate densities
@@ -47,7 +47,8 @@ for name, C, table_scale in (("s1", 3, 1e4), ("s2", 4, 1e4), ("cfg4", 4, 1e4)):
         m.color_net.params.copy_(torch.from_numpy(wc))
     m.density_bitfield.copy_(torch.from_numpy(inp["bitfield"]))
     kw = dict(max_steps=SC["max_steps"], T_thresh=SC["T_thresh"], dt_gamma=SC["dt_gamma"])
-    rng = np.random.default_rng(31 + C)
+    img_seed = 31 + C + (100 if name == "cfg2" else 0)
+    rng = np.random.default_rng(img_seed)
     o, d = torch.from_numpy(inp["train_o"])[None], torch.from_numpy(inp["train_d"])[None]
     images = torch.from_numpy(rng.random((1, o.shape[1], C), dtype=np.float32))
     big = o.shape[1] > 1000  # store seeds / strided probes instead of full arrays
@@ -64,7 +65,7 @@ for name, C, table_scale in (("s1", 3, 1e4), ("s2", 4, 1e4), ("cfg4", 4, 1e4)):
     sel = nz[::max(1, nz.size // 4000)]
     P = lambda k, v: out.__setitem__(f"{name}_{k}", v)  # noqa: E731
     P("param_seed", np.int64(seed)), P("table_scale", np.float32(table_scale))
-    P("images_seed", np.int64(31 + C)), P("images", images.numpy()[:, ::(16 if big else 1)])
+    P("images_seed", np.int64(img_seed)), P("images", images.numpy()[:, ::(16 if big else 1)])
     P("train_pred", pred.detach().numpy()[:, ::(16 if big else 1)]), P("train_loss", np.float32(loss.item()))
     P("train_counter", m.step_counter[0].numpy().copy())
     P("grad_w_sigma_probe", gs[:nm][::7].copy()), P("grad_w_sigma_norm", np.float64(np.linalg.norm(gs[:nm].astype(np.float64))))

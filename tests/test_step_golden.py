@@ -2,7 +2,8 @@
 (tests/golden/make_golden_step.py: nerf/network.py train_step / eval_step / test_step -> nerf/renderer.py run_cuda ->
 submodules/raymarching wrappers -> utils/loss_utils.py l1_loss -> backward, all unmodified, over the stand-ins of
 tests/ref_standins.py).  Three cases: one cascade / 3 channels; two cascades, dt_gamma, density_scale 0.5 / 4 channels;
-BASELINE.json's configs[3] at its full size (two 64x64 views = 8192 rays, 4 channels, max_steps 256: 181 756 samples).
+BASELINE.json's configs[3] (two 64x64 views = 8192 rays, 4 channels, max_steps 256: 181 756 samples) and configs[1], the
+headline workload (4096 rays of an 800x800 view, max_steps 1024), both at full size.
 
 Compared: rendered image, loss, sample counter, d loss / d (sigma MLP, colour MLP, hash table) -- through this repo's
 ``NeRFNetwork.train_step`` + autograd AND through the fused ``TrainStep`` (the product's training path) -- and the images /
@@ -20,7 +21,9 @@ from trace_scene import STEP_SCENES as SCENES
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step.npz")
-CASES = [("s1", 3), ("s2", 4), ("cfg4", 4)]  # cfg4: 8192 rays (two 64x64 views), max_steps 256: BASELINE configs[3] at full size
+# cfg4: 8192 rays (two 64x64 views), max_steps 256 = BASELINE configs[3]; cfg2: 4096 rays, max_steps 1024 = configs[1], the
+# headline workload -- both at full size
+CASES = [("s1", 3), ("s2", 4), ("cfg4", 4), ("cfg2", 3)]
 
 
 def _rel(a, b):

@@ -16,7 +16,10 @@ SCENE = SCENES["s1"]
 # the whole-step goldens (tests/golden/make_golden_step.py) also run BASELINE.json's configs[3] at its full size: two 64x64
 # views = 8192 rays, 4 channels, max_steps 256 (a sane focal; the reference's degenerate one is covered by the live tests)
 STEP_SCENES = dict(SCENES, cfg4=dict(bound=1, channel_dim=4, density_scale=1, max_steps=256, T_thresh=1e-4, T_thresh_eval=1e-4,
-                                     bg_color=1, dt_gamma=0, n_train=8192, eval_hw=16, eval_focal=20.0, seed=21, perturbed=False))
+                                     bg_color=1, dt_gamma=0, n_train=8192, eval_hw=16, eval_focal=20.0, seed=21, perturbed=False),
+                   # ... and configs[1], the headline workload: 4096 random rays of an 800x800 view, max_steps 1024
+                   cfg2=dict(bound=1, channel_dim=3, density_scale=1, max_steps=1024, T_thresh=1e-4, T_thresh_eval=1e-4,
+                             bg_color=1, dt_gamma=0, n_train=4096, eval_hw=16, eval_focal=20.0, seed=0, perturbed=False))
 
 
 def analytic_field(x, d, channel_dim):
@@ -48,6 +51,8 @@ def scene_inputs(name="s1"):
     if name == "cfg4":  # two full 64x64 views
         views = [syn.full_frame(64, 64, 90.0, seed=sc["seed"] + v) for v in range(2)]
         train_o, train_d = np.concatenate([v[0] for v in views]), np.concatenate([v[1] for v in views])
+    elif name == "cfg2":  # bench.py's workload(4096, seed)
+        train_o, train_d = syn.train_batch(sc["n_train"], seed=sc["seed"])
     else:
         train_o, train_d = syn.train_batch(sc["n_train"], 100, 100, 138.0, n_views=2, seed=sc["seed"])
     eval_o, eval_d = syn.full_frame(sc["eval_hw"], sc["eval_hw"], sc["eval_focal"], seed=sc["seed"] + 2)
