@@ -120,3 +120,46 @@ def test_train_step_exchange_argument_on_cpu():
     assert ts.exchange is None and ts.exchange_kind == "nccl" and not ts.overlap_allreduce
     assert TrainStep(m, 16, world_size=1, use_graph=False).exchange_kind == "none"
     assert all(p.grad is not None and p.grad.shape == p.shape for p in ts.params)
+
+
+def test_split_exchange_policy_and_slices():
+    """TrainStep(overlap_exchange=...): "auto" splits the in-graph exchange against the table scatter-add only for the
+    NVSwitch kernel, the bf16 path and steps of at most 2^20 rows; the fine group's slice starts at a 16-byte aligned float
+    of the arena and the groups cover the table without a gap (host logic only: no exchange is made)."""
+    import torch
+    from stable_nerf_b200 import NeRFNetwork
+    from stable_nerf_b200.trainer import TrainStep
+
+    class FakeExchange:  # stands where P2PExchange would be; never called
+        n_floats = 0
+
+    m = NeRFNetwork(precision="bf16")
+    ts = TrainStep(m, 64, use_graph=False)
+    assert ts.overlap_split_levels == [8] and ts.overlap_side_ctas == 16 and not ts._overlap_exchange_on(356352)  # no exchange
+    ts.exchange, ts.exchange_kind = FakeExchange(), "nvls"
+    assert ts._overlap_exchange_on(356352) and ts._overlap_exchange_on(1 << 20)
+    assert not ts._overlap_exchange_on((1 << 20) + 128) and not ts._overlap_exchange_on(0)
+    ts.exchange_kind = "p2p"
+    assert not ts._overlap_exchange_on(356352)
+    ts.overlap_exchange = True
+    assert ts._overlap_exchange_on(356352) and ts._overlap_exchange_on(5 << 20)
+    ts.overlap_exchange = False
+    assert not ts._overlap_exchange_on(356352)
+    ts.overlap_exchange, ts.exchange_kind = "auto", "nvls"
+    m.precision = "fp32"
+    assert not ts._overlap_exchange_on(356352)
+    m.precision = "bf16"
+    ts2 = TrainStep(m, 64, use_graph=False, overlap_split_level=(10, 6, 99, 0))
+    assert ts2.overlap_split_levels == [10, 6, 99, 0]
+    g = m.fdesc.grid
+    L, F, nm = int(g.n_levels), int(g.n_features), m.sigma_net.n_mlp
+    cuts = sorted({v for v in ts2.overlap_split_levels if 0 < v < L}, reverse=True)
+    assert cuts == [10, 6]
+    # arena order of TrainStep._setup_p2p: [colour MLP | sigma MLP | table]; slices [lo(level), end) per cut, then the rest
+    table0 = (m.color_net.params.numel() + 3) // 4 * 4 + nm
+    hi = table0 + int(g.n_entries) * F
+    for lvl in cuts:
+        lo = table0 + int(g.offset[lvl]) * F
+        assert lo % 4 == 0 and table0 < lo < hi
+        hi = lo
+    assert hi > table0  # the coarse group is not empty and travels with the MLP gradients
